@@ -1,0 +1,122 @@
+"""ctypes binding of libbn_cuda.so (include/bn_cuda.h).  No CPU fallback: if the CUDA library is missing
+or no GPU is visible, every compute entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbn_cuda.so")
+
+BN_OK, BN_BAD_ARG, BN_DIM_MISMATCH, BN_NOT_IN_FACTOR, BN_CUDA_ERR = 0, -1, -2, -3, -4
+BN_ZERO_WEIGHT, BN_OOM, BN_UNSUPPORTED, BN_BOUNDS = -5, -6, -7, -8
+
+
+class DimensionMismatch(ValueError):
+    """Julia's DimensionMismatch (src/Factors/factors_dims.jl:197-199)."""
+
+
+class BNCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+u8p, i8p, i32p, i64p, f64p = (C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.POINTER(C.c_int32),
+                              C.POINTER(C.c_int64), C.POINTER(C.c_double))
+h64 = C.c_uint64
+
+_SIGS = {
+    "bn_last_error": (C.c_char_p, []),
+    "bn_version": (C.c_int32, []),
+    "bn_device_count": (C.c_int32, [i32p]),
+    "bn_set_stream": (C.c_int32, [C.c_void_p]),
+    "bn_launch_count": (C.c_uint64, []),
+    "bn_net_create": (C.c_int32, [C.c_int32, i32p, i32p, i32p, i64p, f64p, C.c_int32, C.POINTER(h64)]),
+    "bn_net_destroy": (C.c_int32, [h64]),
+    "bn_lw_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, f64p, f64p]),
+    "bn_lw_infer_dev": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bn_sample": (C.c_int32, [h64, i8p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, u8p, f64p, u8p]),
+    "bn_sample_dev": (C.c_int32, [h64, i8p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bn_gibbs_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64,
+                                   C.c_int64, C.c_int32, C.c_uint64, u8p, C.c_int32, f64p, f64p]),
+    "bn_gibbs_infer_dev": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64,
+                                       C.c_int64, C.c_int32, C.c_uint64, C.c_void_p]),
+    "bn_gibbs_sample": (C.c_int32, [h64, i8p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, i32p,
+                                    C.c_uint64, u8p, u8p]),
+    "bn_factor_upload": (C.c_int32, [C.c_int32, i32p, i32p, f64p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_alloc": (C.c_int32, [C.c_int32, i32p, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_from_cpd": (C.c_int32, [h64, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_relabel": (C.c_int32, [h64, i32p]),
+    "bn_factor_ndims": (C.c_int32, [h64, i32p]),
+    "bn_factor_shape": (C.c_int32, [h64, i32p, i32p]),
+    "bn_factor_length": (C.c_int32, [h64, i64p]),
+    "bn_factor_download": (C.c_int32, [h64, f64p]),
+    "bn_factor_dev_ptr": (C.c_int32, [h64, C.POINTER(C.c_void_p)]),
+    "bn_factor_free": (C.c_int32, [h64]),
+    "bn_factor_product": (C.c_int32, [h64, h64, C.POINTER(h64)]),
+    "bn_factor_sum": (C.c_int32, [h64, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_slice": (C.c_int32, [h64, i32p, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_normalize": (C.c_int32, [h64, C.c_int32]),
+    "bn_factor_eliminate": (C.c_int32, [C.POINTER(h64), C.c_int32, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_exact_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_int32, i32p, i32p, f64p]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib() -> C.CDLL:
+    """Load libbn_cuda.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BNCudaError(
+                f"{LIB_PATH} is missing: build it with `python bayesnets.jl_b200/build.py` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    """Map bn_status to the exception the reference would have thrown (include/bn_cuda.h)."""
+    if rc == BN_OK:
+        return
+    msg = lib().bn_last_error().decode("utf-8", "replace")
+    if rc == BN_DIM_MISMATCH:
+        raise DimensionMismatch(msg)
+    if rc in (BN_BAD_ARG, BN_NOT_IN_FACTOR):
+        raise ValueError(msg)  # ArgumentError
+    if rc == BN_BOUNDS:
+        raise IndexError(msg)  # BoundsError
+    if rc == BN_ZERO_WEIGHT:
+        raise RuntimeError(msg)
+    if rc == BN_OOM:
+        raise MemoryError(msg)
+    if rc == BN_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise BNCudaError(f"libbn_cuda status {rc}: {msg}")
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def set_stream(cuda_stream: int | None) -> None:
+    """Enqueue subsequent calls from this thread on `cuda_stream` (e.g. torch.cuda.current_stream().cuda_stream)."""
+    check(lib().bn_set_stream(C.c_void_p(cuda_stream or 0)))
+
+
+def launch_count() -> int:
+    return int(lib().bn_launch_count())
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    check(lib().bn_device_count(C.byref(n)))
+    return n.value

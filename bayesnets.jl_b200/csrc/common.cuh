@@ -1,0 +1,155 @@
+// common.cuh -- shared host/device helpers for libbn_cuda.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bn_cuda.h"
+
+namespace bn {
+
+// ---------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern thread_local cudaStream_t tl_stream;
+extern std::atomic<uint64_t> g_launches;
+
+#define BN_CUDA_TRY(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      bn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return (_e == cudaErrorMemoryAllocation) ? BN_OOM : BN_CUDA_ERR;                      \
+    }                                                                                       \
+  } while (0)
+
+#define BN_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      bn::set_error(__VA_ARGS__);    \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define BN_TRY(expr)              \
+  do {                            \
+    int32_t _rc = (expr);         \
+    if (_rc != BN_OK) return _rc; \
+  } while (0)
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------- device properties
+struct DevProps {
+  int sm_count = 148;
+  int max_smem_optin = 232448;  // 227 KB
+  int smem_per_sm = 233472;     // 228 KB
+};
+const DevProps& dev_props(int device);
+
+// ---------------------------------------------------------------------------- device buffers
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+  }
+  cudaError_t upload(const T* host, size_t count, cudaStream_t s) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess) return e;
+    if (count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+// ---------------------------------------------------------------------------- objects behind handles
+struct Net {
+  int device = 0;
+  int n = 0;
+  // host copies (planning is host-side)
+  std::vector<int32_t> card, par_ptr, par_idx;
+  std::vector<int64_t> cpt_off;
+  std::vector<double> cpt;
+  std::vector<int32_t> child_ptr, child_idx;  // children in ascending topological index
+  // device copies
+  DevBuf<int32_t> d_card, d_par_ptr, d_par_idx, d_child_ptr, d_child_idx;
+  DevBuf<int32_t> d_cpt_off;  // 32-bit offsets when the table fits (always for sampling paths)
+  DevBuf<double> d_cpt;
+  // scratch reused across calls (grown on demand)
+  DevBuf<uint8_t> scratch;
+  DevBuf<double> result;
+};
+
+struct Factor {
+  int device = 0;
+  std::vector<int32_t> dims, card;
+  int64_t len = 1;
+  DevBuf<double> data;
+};
+
+Net* get_net(bn_net_t h);
+Factor* get_factor(bn_factor_t h);
+bn_factor_t register_factor(Factor* f);
+Factor* take_factor(bn_factor_t h);  // removes the handle, caller deletes
+int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>& card, int device,
+                   Factor** out);
+
+// ---------------------------------------------------------------------------- Philox4x32-10
+// Salmon et al. SC'11.  key bumps are warp-uniform so only 2 IMAD.WIDE + 2 LOP3 per round are
+// per-thread work.  Counter layout is the library-wide spec (include/bn_cuda.h).
+struct Philox {
+  uint32_t k0, k1;
+};
+enum : uint32_t { STREAM_SAMPLE = 0, STREAM_GIBBS_INIT = 1, STREAM_GIBBS_UPDATE = 2, STREAM_PERM = 3 };
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 31-bit quantised CDF threshold, identical to oracle/bn_oracle.c cdf_threshold().
+inline uint32_t cdf_threshold(double c) {
+  double t = __builtin_floor(c * 2147483648.0 + 0.5);
+  if (t < 0.0) t = 0.0;
+  if (t > 2147483648.0) t = 2147483648.0;
+  return (uint32_t)t;
+}
+
+}  // namespace bn

@@ -1,0 +1,196 @@
+// core.cu -- handles, error state, network upload (the device side of device_layout.jl).
+#include "common.cuh"
+
+namespace bn {
+
+static thread_local char tl_error[512] = "";
+thread_local cudaStream_t tl_stream = nullptr;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+
+static std::mutex g_mu;
+static std::unordered_map<uint64_t, Net*> g_nets;
+static std::unordered_map<uint64_t, Factor*> g_factors;
+static uint64_t g_next = 1;
+static std::unordered_map<int, DevProps> g_props;
+
+const DevProps& dev_props(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_props.find(device);
+  if (it != g_props.end()) return it->second;
+  DevProps p;
+  cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaDeviceGetAttribute(&p.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+  return g_props[device] = p;
+}
+
+Net* get_net(bn_net_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_nets.find(h);
+  return it == g_nets.end() ? nullptr : it->second;
+}
+Factor* get_factor(bn_factor_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_factors.find(h);
+  return it == g_factors.end() ? nullptr : it->second;
+}
+Factor* take_factor(bn_factor_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_factors.find(h);
+  if (it == g_factors.end()) return nullptr;
+  Factor* f = it->second;
+  g_factors.erase(it);
+  return f;
+}
+bn_factor_t register_factor(Factor* f) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint64_t h = g_next++;
+  g_factors[h] = f;
+  return h;
+}
+
+int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>& card, int device,
+                   Factor** out) {
+  Factor* f = new Factor();
+  f->device = device;
+  f->dims = dims;
+  f->card = card;
+  f->len = 1;
+  for (int32_t c : card) f->len *= c;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = f->data.alloc((size_t)f->len);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc of %lld doubles failed: %s", (long long)f->len, cudaGetErrorString(e));
+    delete f;
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? BN_OOM : BN_CUDA_ERR;
+  }
+  *out = f;
+  return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" {
+
+const char* bn_last_error(void) { return bn::tl_error; }
+int32_t bn_version(void) { return 100; }
+
+int32_t bn_device_count(int32_t* out_n) {
+  BN_REQUIRE(out_n, BN_BAD_ARG, "out_n is NULL");
+  int n = 0;
+  BN_CUDA_TRY(cudaGetDeviceCount(&n));
+  *out_n = n;
+  return BN_OK;
+}
+
+int32_t bn_set_stream(void* cuda_stream) {
+  bn::tl_stream = (cudaStream_t)cuda_stream;
+  return BN_OK;
+}
+
+uint64_t bn_launch_count(void) { return bn::g_launches.load(); }
+
+int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                      const int64_t* cpt_off, const double* cpt, int32_t device, bn_net_t* out_net) {
+  BN_REQUIRE(out_net && card && par_ptr && cpt_off && cpt, BN_BAD_ARG, "bn_net_create: NULL argument");
+  BN_REQUIRE(n_nodes > 0, BN_BAD_ARG, "bn_net_create: n_nodes must be > 0");
+  BN_REQUIRE(par_ptr[0] == 0 && cpt_off[0] == 0, BN_BAD_ARG, "bn_net_create: CSR offsets must start at 0");
+  int32_t n_par = par_ptr[n_nodes];
+  BN_REQUIRE(n_par == 0 || par_idx, BN_BAD_ARG, "bn_net_create: par_idx is NULL");
+  for (int i = 0; i < n_nodes; ++i) {
+    BN_REQUIRE(card[i] >= 1 && card[i] <= 255, BN_BAD_ARG, "node %d: cardinality %d outside 1..255", i, card[i]);
+    BN_REQUIRE(par_ptr[i + 1] >= par_ptr[i], BN_BAD_ARG, "par_ptr not monotone at node %d", i);
+    int64_t q = 1;
+    for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) {
+      int p = par_idx[k];
+      // topological order is the contract (src/bayes_nets.jl:26-48)
+      BN_REQUIRE(p >= 0 && p < i, BN_BAD_ARG, "node %d: parent %d breaks the topological order", i, p);
+      for (int k2 = par_ptr[i]; k2 < k; ++k2)
+        BN_REQUIRE(par_idx[k2] != p, BN_BAD_ARG, "node %d lists parent %d twice", i, p);
+      q *= card[p];
+    }
+    BN_REQUIRE(cpt_off[i + 1] - cpt_off[i] == q * card[i], BN_BAD_ARG,
+               "node %d: CPT has %lld entries, expected %lld", i, (long long)(cpt_off[i + 1] - cpt_off[i]),
+               (long long)(q * card[i]));
+  }
+  int ndev = 0;
+  BN_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  BN_REQUIRE(device >= 0 && device < ndev, BN_BAD_ARG, "device %d out of range (%d visible)", device, ndev);
+  BN_CUDA_TRY(cudaSetDevice(device));
+
+  Net* net = new Net();
+  net->device = device;
+  net->n = n_nodes;
+  net->card.assign(card, card + n_nodes);
+  net->par_ptr.assign(par_ptr, par_ptr + n_nodes + 1);
+  net->par_idx.assign(par_idx, par_idx + n_par);
+  net->cpt_off.assign(cpt_off, cpt_off + n_nodes + 1);
+  net->cpt.assign(cpt, cpt + cpt_off[n_nodes]);
+  // children CSR, ascending child index (Graphs.outneighbors order, src/bayes_nets.jl:96-99)
+  net->child_ptr.assign(n_nodes + 1, 0);
+  for (int i = 0; i < n_nodes; ++i)
+    for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) net->child_ptr[par_idx[k] + 1]++;
+  for (int i = 0; i < n_nodes; ++i) net->child_ptr[i + 1] += net->child_ptr[i];
+  net->child_idx.assign(n_par, 0);
+  {
+    std::vector<int32_t> fill(n_nodes, 0);
+    for (int i = 0; i < n_nodes; ++i)
+      for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) {
+        int p = par_idx[k];
+        net->child_idx[net->child_ptr[p] + fill[p]++] = i;
+      }
+  }
+  cudaStream_t s = bn::tl_stream;
+  std::vector<int32_t> off32(n_nodes + 1);
+  bool fits32 = cpt_off[n_nodes] < (int64_t)0x7fffffff;
+  for (int i = 0; i <= n_nodes; ++i) off32[i] = fits32 ? (int32_t)cpt_off[i] : 0;
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  chk(net->d_card.upload(net->card.data(), net->card.size(), s));
+  chk(net->d_par_ptr.upload(net->par_ptr.data(), net->par_ptr.size(), s));
+  chk(net->d_par_idx.upload(net->par_idx.data(), net->par_idx.size(), s));
+  chk(net->d_child_ptr.upload(net->child_ptr.data(), net->child_ptr.size(), s));
+  chk(net->d_child_idx.upload(net->child_idx.data(), net->child_idx.size(), s));
+  chk(net->d_cpt_off.upload(off32.data(), off32.size(), s));
+  chk(net->d_cpt.upload(net->cpt.data(), net->cpt.size(), s));
+  chk(cudaStreamSynchronize(s));
+  if (e != cudaSuccess) {
+    set_error("bn_net_create: upload failed: %s", cudaGetErrorString(e));
+    delete net;
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? BN_OOM : BN_CUDA_ERR;
+  }
+  {
+    std::lock_guard<std::mutex> lk(bn::g_mu);
+    uint64_t h = bn::g_next++;
+    bn::g_nets[h] = net;
+    *out_net = h;
+  }
+  return BN_OK;
+}
+
+int32_t bn_net_destroy(bn_net_t h) {
+  Net* net = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(bn::g_mu);
+    auto it = bn::g_nets.find(h);
+    BN_REQUIRE(it != bn::g_nets.end(), BN_BAD_ARG, "bn_net_destroy: unknown handle");
+    net = it->second;
+    bn::g_nets.erase(it);
+  }
+  cudaSetDevice(net->device);
+  delete net;
+  return BN_OK;
+}
+
+}  // extern "C"

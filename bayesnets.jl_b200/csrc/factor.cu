@@ -1,0 +1,703 @@
+// factor.cu -- dense fp64 factor algebra on the device: product (outer join), marginalise, slice,
+// normalise and the fused n-ary "multiply-then-sum-out" elimination step.
+//
+// Replaces join/`*` (src/Factors/factors_dims.jl:185-234,269), reducedim/sum (:60-85,100),
+// normalize! (:45-57), getindex(::Assignment) (src/Factors/factors_access.jl:19-35) and the
+// `sum(reduce(*, contain_h), h)` step of variable elimination (src/Inference/exact.jl:27).
+//
+// ONE contraction kernel covers product / sum / slice / fused eliminate:
+//     out[o] = sum_{s in S} prod_k F_k[ off_k(o) + off_k(s) ]
+// The loop space is split   o = lo + Rlo * hi :
+//   lo  = the first output dims (Rlo ~ 256..1024 contiguous outputs; also contiguous in the larger
+//         operand, whose dims lead the union -- src/Factors/factors_dims.jl:203), one lo per thread,
+//         its per-factor offsets held in registers;
+//   hi  = the remaining output dims, H values per CTA tile; per-factor offsets of the tile's hi values
+//         are computed once into shared memory and read back as warp-uniform broadcasts;
+//   s   = the summed dims, offsets likewise tabulated in shared memory; accumulation runs in
+//         column-major order like Base's mapreducedim!, products fold left to right like reduce(*).
+// Every operand element is touched exactly once per use, output/leading-operand traffic is fully
+// coalesced and 128-bit vectorised (double2 along the first output dim, or along the first summed
+// dim when that is the contiguous one).  All of it is HBM-bound: 8*(sum N_k + N_out) bytes.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace bn {
+
+constexpr int MAXD = 48;  // loop dims (output + summed)
+constexpr int MAXF = 6;   // operands per contraction
+constexpr int MAX_NS = 2048;
+
+// Loop dims are ordered [lo | j | t | s]:
+//   lo: leading output dims, Rlo entries, one per thread (per-operand offsets live in registers)
+//   j : next output dims, H = prod(card) <= 64 entries per tile (offset table in smem, tile independent)
+//   t : remaining output dims = the tile index (decomposed once per tile by warp 0, one dim per lane)
+//   s : summed dims, Ns joint states (offset table in smem), accumulated first-dim-fastest
+struct ContractParams {
+  int32_t nf, nlo, nj, nt, ns;
+  int32_t card[MAXD];
+  uint32_t tdiv[MAXD];             // for t dims: product of the cards of the lower t dims
+  long long fstride[MAXF][MAXD];   // element stride of each operand along each loop dim (0 = absent)
+  const double* f[MAXF];
+  double* out;
+  long long Rlo, n_tiles;
+  int32_t H, Ns;
+  int32_t vstride_dim;  // loop dim used for 128-bit vectors (first lo dim or first s dim)
+  int32_t fmode[MAXF];  // behaviour along that dim: 0 broadcast, 1 contiguous+aligned, 2 strided
+};
+
+enum { VEC_NONE = 0, VEC_LO = 1, VEC_S = 2 };
+
+__device__ __forceinline__ double2 ld2(const double* __restrict__ f, long long off, int mode, long long stride) {
+  if (mode == 1) return *reinterpret_cast<const double2*>(f + off);
+  if (mode == 0) { const double v = __ldg(f + off); return make_double2(v, v); }
+  return make_double2(__ldg(f + off), __ldg(f + off + stride));
+}
+
+template <int NF, int VEC, bool SUM>
+__global__ void __launch_bounds__(256) contract_kernel(const ContractParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* jOff = reinterpret_cast<long long*>(smem_raw);  // [NF][H]
+  long long* sOff = jOff + NF * p.H;                          // [NF][Ns]
+  __shared__ long long tileOff[MAXF];
+  const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
+  constexpr int W = (VEC == VEC_LO) ? 2 : 1;  // outputs per thread step
+  constexpr int JU = 4;                        // tile rows in flight per thread
+
+  // ---- one-time tables: j offsets and summed-dim offsets
+  for (int j = tid; j < p.H; j += nthr) {
+    uint32_t r = (uint32_t)j;
+    long long off[NF];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) off[k] = 0;
+    for (int d = 0; d < p.nj; ++d) {
+      const uint32_t c = (uint32_t)p.card[p.nlo + d];
+      const uint32_t dg = r % c;
+      r /= c;
+#pragma unroll
+      for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][p.nlo + d];
+    }
+#pragma unroll
+    for (int k = 0; k < NF; ++k) jOff[k * p.H + j] = off[k];
+  }
+  if (SUM) {
+    const int sbase = p.nlo + p.nj + p.nt;
+    for (int s = tid; s < p.Ns; s += nthr) {
+      uint32_t r = (uint32_t)s;
+      long long off[NF];
+#pragma unroll
+      for (int k = 0; k < NF; ++k) off[k] = 0;
+      for (int d = 0; d < p.ns; ++d) {
+        const uint32_t c = (uint32_t)p.card[sbase + d];
+        const uint32_t dg = r % c;
+        r /= c;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][sbase + d];
+      }
+#pragma unroll
+      for (int k = 0; k < NF; ++k) sOff[k * p.Ns + s] = off[k];
+    }
+  }
+  // ---- per-thread lo offsets (hoisted when each thread owns a single lo)
+  const bool lo_fixed = p.Rlo <= (long long)nthr * W;
+  long long loOff0[NF];
+  {
+    uint32_t r = (uint32_t)tid * W;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) loOff0[k] = 0;
+    for (int d = 0; d < p.nlo; ++d) {
+      const uint32_t c = (uint32_t)p.card[d];
+      const uint32_t dg = r % c;
+      r /= c;
+#pragma unroll
+      for (int k = 0; k < NF; ++k) loOff0[k] += (long long)dg * p.fstride[k][d];
+    }
+  }
+  const int tb = p.nlo + p.nj;
+  const long long vst_lo = p.fstride[0][0];
+
+  for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    __syncthreads();  // tables ready (first pass) / previous tile finished with tileOff
+    if (tid < 32) {
+      long long off[NF];
+#pragma unroll
+      for (int k = 0; k < NF; ++k) off[k] = 0;
+      for (int d = tid; d < p.nt; d += 32) {
+        const uint32_t dg = ((uint32_t)tile / p.tdiv[d]) % (uint32_t)p.card[tb + d];
+#pragma unroll
+        for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][tb + d];
+      }
+#pragma unroll
+      for (int k = 0; k < NF; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) off[k] += __shfl_xor_sync(0xffffffffu, off[k], o);
+        if (tid == 0) tileOff[k] = off[k];
+      }
+    }
+    __syncthreads();
+    double* otile = p.out + tile * (long long)p.H * p.Rlo;
+
+    for (long long lo = (long long)tid * W; lo < p.Rlo; lo += (long long)nthr * W) {
+      long long lt[NF];
+      if (lo_fixed) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) lt[k] = loOff0[k] + tileOff[k];
+      } else {
+        uint32_t r = (uint32_t)lo;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) lt[k] = tileOff[k];
+        for (int d = 0; d < p.nlo; ++d) {
+          const uint32_t c = (uint32_t)p.card[d];
+          const uint32_t dg = r % c;
+          r /= c;
+#pragma unroll
+          for (int k = 0; k < NF; ++k) lt[k] += (long long)dg * p.fstride[k][d];
+        }
+      }
+      for (int j0 = 0; j0 < p.H; j0 += JU) {
+        long long base[JU][NF];
+#pragma unroll
+        for (int u = 0; u < JU; ++u) {
+          const int j = (j0 + u < p.H) ? j0 + u : p.H - 1;
+#pragma unroll
+          for (int k = 0; k < NF; ++k) base[u][k] = lt[k] + jOff[k * p.H + j];
+        }
+        if (VEC == VEC_LO) {
+          double2 acc[JU];
+          if (!SUM) {
+            double2 v[JU][NF];
+#pragma unroll
+            for (int u = 0; u < JU; ++u)
+#pragma unroll
+              for (int k = 0; k < NF; ++k) v[u][k] = ld2(p.f[k], base[u][k], p.fmode[k], p.fstride[k][0]);
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+              acc[u] = v[u][0];
+#pragma unroll
+              for (int k = 1; k < NF; ++k) { acc[u].x *= v[u][k].x; acc[u].y *= v[u][k].y; }
+            }
+          } else {
+            for (int s = 0; s < p.Ns; ++s) {
+#pragma unroll
+              for (int u = 0; u < JU; ++u) {
+                double2 pr = ld2(p.f[0], base[u][0] + sOff[s], p.fmode[0], p.fstride[0][0]);
+#pragma unroll
+                for (int k = 1; k < NF; ++k) {
+                  const double2 x = ld2(p.f[k], base[u][k] + sOff[k * p.Ns + s], p.fmode[k], p.fstride[k][0]);
+                  pr.x *= x.x; pr.y *= x.y;
+                }
+                if (s == 0) acc[u] = pr; else { acc[u].x += pr.x; acc[u].y += pr.y; }
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < JU; ++u)
+            if (j0 + u < p.H) *reinterpret_cast<double2*>(otile + (long long)(j0 + u) * p.Rlo + lo) = acc[u];
+        } else if (VEC == VEC_S) {
+          // SUM is implied; pairs run along the first summed dim
+          const int sd = p.vstride_dim;
+          double acc[JU];
+          for (int s = 0; s < p.Ns; s += 2) {
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+              double2 pr = ld2(p.f[0], base[u][0] + sOff[s], p.fmode[0], p.fstride[0][sd]);
+#pragma unroll
+              for (int k = 1; k < NF; ++k) {
+                const double2 x = ld2(p.f[k], base[u][k] + sOff[k * p.Ns + s], p.fmode[k], p.fstride[k][sd]);
+                pr.x *= x.x; pr.y *= x.y;
+              }
+              acc[u] = (s == 0) ? pr.x : acc[u] + pr.x;
+              acc[u] += pr.y;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < JU; ++u)
+            if (j0 + u < p.H) otile[(long long)(j0 + u) * p.Rlo + lo] = acc[u];
+        } else {
+          double acc[JU];
+          if (!SUM) {
+            double v[JU][NF];
+#pragma unroll
+            for (int u = 0; u < JU; ++u)
+#pragma unroll
+              for (int k = 0; k < NF; ++k) v[u][k] = __ldg(p.f[k] + base[u][k]);
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+              acc[u] = v[u][0];
+#pragma unroll
+              for (int k = 1; k < NF; ++k) acc[u] *= v[u][k];
+            }
+          } else {
+            for (int s = 0; s < p.Ns; ++s) {
+#pragma unroll
+              for (int u = 0; u < JU; ++u) {
+                double pr = __ldg(p.f[0] + base[u][0] + sOff[s]);
+#pragma unroll
+                for (int k = 1; k < NF; ++k) pr *= __ldg(p.f[k] + base[u][k] + sOff[k * p.Ns + s]);
+                acc[u] = (s == 0) ? pr : acc[u] + pr;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < JU; ++u)
+            if (j0 + u < p.H) otile[(long long)(j0 + u) * p.Rlo + lo] = acc[u];
+        }
+      }
+    }
+  }
+  (void)vst_lo;
+}
+
+// ---- normalize!: two launches -- (1) per-CTA partial sums, last CTA folds them in a fixed order,
+//      (2) x ./= total.  Deterministic (no fp atomics).
+__global__ void __launch_bounds__(512) norm_reduce_kernel(const double* __restrict__ x, long long n, int p,
+                                                          double* partial, unsigned int* ticket, double* total) {
+  __shared__ double wsum[16];
+  __shared__ bool last;
+  const long long n2 = n / 2;
+  double acc = 0.0;
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const double2 v = x2[i];
+    acc += (p == 1) ? (fabs(v.x) + fabs(v.y)) : (v.x * v.x + v.y * v.y);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double v = x[n - 1];
+    acc += (p == 1) ? fabs(v) : v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    // fixed-order fold of the partials by one warp
+    double s = 0.0;
+    if (threadIdx.x < 32) {
+      for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) s += __ldcg(partial + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (threadIdx.x == 0) { *total = s; *ticket = 0u; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) norm_scale_kernel(double* __restrict__ x, long long n, const double* total) {
+  const double t = *total;
+  const long long n2 = n / 2;
+  double2* x2 = reinterpret_cast<double2*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    double2 v = x2[i];
+    v.x /= t; v.y /= t;
+    x2[i] = v;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] /= t;
+}
+
+// ------------------------------------------------------------------------------------------ host
+struct Operand {
+  const double* ptr;
+  std::vector<int32_t> dims, card;
+};
+
+static int find_dim(const std::vector<int32_t>& dims, int32_t d) {
+  for (size_t i = 0; i < dims.size(); ++i) if (dims[i] == d) return (int)i;
+  return -1;
+}
+
+template <int NF, int VEC, bool SUM>
+static int32_t launch_contract_v(const ContractParams& p, int grid, size_t smem, cudaStream_t s) {
+  BN_CUDA_TRY(cudaFuncSetAttribute(contract_kernel<NF, VEC, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  contract_kernel<NF, VEC, SUM><<<grid, 256, smem, s>>>(p);
+  count_launch();
+  BN_CUDA_TRY(cudaGetLastError());
+  return BN_OK;
+}
+
+template <int NF>
+static int32_t launch_contract_nf(const ContractParams& p, int vec, bool sum, int grid, size_t smem, cudaStream_t s) {
+  if (vec == VEC_S) return launch_contract_v<NF, VEC_S, true>(p, grid, smem, s);
+  if (vec == VEC_LO) return sum ? launch_contract_v<NF, VEC_LO, true>(p, grid, smem, s)
+                                : launch_contract_v<NF, VEC_LO, false>(p, grid, smem, s);
+  return sum ? launch_contract_v<NF, VEC_NONE, true>(p, grid, smem, s)
+             : launch_contract_v<NF, VEC_NONE, false>(p, grid, smem, s);
+}
+
+// out[out_dims] = sum_{sum_dims} prod_k ops[k]; out_dims/out_card give the output layout (column-major),
+// sum_dims/sum_card the reduced variables in accumulation order (first fastest).
+static int32_t contract(int device, const std::vector<Operand>& ops, const std::vector<int32_t>& out_dims,
+                        const std::vector<int32_t>& out_card, const std::vector<int32_t>& sum_dims,
+                        const std::vector<int32_t>& sum_card, double* out) {
+  const int nf = (int)ops.size();
+  BN_REQUIRE(nf >= 1 && nf <= MAXF, BN_UNSUPPORTED, "contraction of %d factors (max %d)", nf, MAXF);
+  const int no = (int)out_dims.size(), ns = (int)sum_dims.size();
+  BN_REQUIRE(no + ns <= MAXD, BN_UNSUPPORTED, "contraction over %d variables (max %d)", no + ns, MAXD);
+  ContractParams p{};
+  p.nf = nf;
+  p.ns = ns;
+  p.out = out;
+  long long Nout = 1, Ns = 1;
+  for (int c : out_card) Nout *= c;
+  for (int c : sum_card) Ns *= c;
+  BN_REQUIRE(Ns <= MAX_NS, BN_UNSUPPORTED, "summing out %lld joint states at once (max %d)", Ns, MAX_NS);
+  const DevProps& dp = dev_props(device);
+  // lo = shortest prefix of the output dims with >= 256 entries
+  int nlo = 0;
+  long long Rlo = 1;
+  while (nlo < no && Rlo < 256) { Rlo *= out_card[nlo]; ++nlo; }
+  BN_REQUIRE(Rlo < (1ll << 31), BN_UNSUPPORTED, "leading output dims too large");
+  // j = following dims while the tile stays <= 64 rows and >= 8 tiles per SM remain
+  int nj = 0;
+  long long H = 1;
+  const long long rest = Nout / Rlo;
+  while (nlo + nj < no) {
+    const long long h2 = H * out_card[nlo + nj];
+    if (h2 > 64 || rest / h2 < (long long)dp.sm_count * 8) break;
+    H = h2; ++nj;
+  }
+  const int nt = no - nlo - nj;
+  const long long n_tiles = rest / H;
+  BN_REQUIRE(n_tiles < (1ll << 31), BN_UNSUPPORTED, "too many tiles");
+  p.nlo = nlo; p.nj = nj; p.nt = nt;
+  p.Rlo = Rlo; p.H = (int)H; p.n_tiles = n_tiles; p.Ns = (int)Ns;
+  for (int d = 0; d < no; ++d) p.card[d] = out_card[d];
+  for (int d = 0; d < ns; ++d) p.card[no + d] = sum_card[d];
+  {
+    long long pr = 1;
+    for (int d = 0; d < nt; ++d) { p.tdiv[d] = (uint32_t)pr; pr *= out_card[nlo + nj + d]; }
+  }
+  int lead = 0;
+  long long lead_len = -1;
+  for (int k = 0; k < nf; ++k) {
+    p.f[k] = ops[k].ptr;
+    long long st = 1;
+    for (size_t i = 0; i < ops[k].dims.size(); ++i) {
+      int pos = find_dim(out_dims, ops[k].dims[i]);
+      if (pos < 0) {
+        pos = find_dim(sum_dims, ops[k].dims[i]);
+        BN_REQUIRE(pos >= 0, BN_BAD_ARG, "operand dim %d is neither kept nor summed", ops[k].dims[i]);
+        pos += no;
+      }
+      p.fstride[k][pos] = st;
+      st *= ops[k].card[i];
+    }
+    if (st > lead_len) { lead_len = st; lead = k; }
+  }
+  // vector dim: the first summed dim if the largest operand is contiguous there, else the first output dim
+  int vec = VEC_NONE, vdim = 0;
+  if (ns >= 1 && (sum_card[0] % 2) == 0 && p.fstride[lead][no] == 1) { vec = VEC_S; vdim = no; }
+  else if (no >= 1 && (out_card[0] % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0) { vec = VEC_LO; vdim = 0; }
+  p.vstride_dim = vdim;
+  if (vec != VEC_NONE) {
+    for (int k = 0; k < nf; ++k) {
+      const long long st = p.fstride[k][vdim];
+      const bool aligned = (reinterpret_cast<uintptr_t>(p.f[k]) % 16) == 0;
+      p.fmode[k] = st == 0 ? 0 : ((st == 1 && aligned) ? 1 : 2);
+    }
+  }
+  const int grid = (int)std::min<long long>(n_tiles, (long long)dp.sm_count * 8);
+  const size_t smem = (size_t)nf * ((size_t)H + (size_t)Ns) * sizeof(long long);
+  cudaStream_t s = tl_stream;
+  const bool sum = ns > 0;
+  switch (nf) {
+    case 1: return launch_contract_nf<1>(p, vec, sum, grid, smem, s);
+    case 2: return launch_contract_nf<2>(p, vec, sum, grid, smem, s);
+    case 3: return launch_contract_nf<3>(p, vec, sum, grid, smem, s);
+    case 4: return launch_contract_nf<4>(p, vec, sum, grid, smem, s);
+    case 5: return launch_contract_nf<5>(p, vec, sum, grid, smem, s);
+    default: return launch_contract_nf<6>(p, vec, sum, grid, smem, s);
+  }
+}
+
+// dims of phi1 * phi2 per the reference: larger first (strict <), union keeps phi1's order.
+static int32_t join_dims(std::vector<int32_t>& d1, std::vector<int32_t>& c1, long long& n1,
+                         const std::vector<int32_t>& d2in, const std::vector<int32_t>& c2in, long long n2in) {
+  std::vector<int32_t> d2 = d2in, c2 = c2in;
+  long long n2 = n2in;
+  if (n1 < n2) { std::swap(d1, d2); std::swap(c1, c2); std::swap(n1, n2); }  // factors_dims.jl:189-191
+  for (size_t j = 0; j < d2.size(); ++j) {
+    int pos = find_dim(d1, d2[j]);
+    if (pos >= 0) {
+      BN_REQUIRE(c1[pos] == c2[j], BN_DIM_MISMATCH, "Common dimensions must have same size (dim %d: %d vs %d)",
+                 d2[j], c1[pos], c2[j]);
+    }
+  }
+  for (size_t j = 0; j < d2.size(); ++j)
+    if (find_dim(d1, d2[j]) < 0) { d1.push_back(d2[j]); c1.push_back(c2[j]); n1 *= c2[j]; }
+  return BN_OK;
+}
+
+static int32_t eliminate_impl(const std::vector<Factor*>& fs, const int32_t* sum_dims, int32_t n_sum, Factor** out) {
+  BN_REQUIRE(!fs.empty(), BN_BAD_ARG, "no factors given");
+  const int device = fs[0]->device;
+  for (Factor* f : fs) BN_REQUIRE(f->device == device, BN_BAD_ARG, "factors live on different devices");
+  // dims of reduce(*, factors) exactly as the reference's left fold would produce them
+  std::vector<int32_t> d = fs[0]->dims, c = fs[0]->card;
+  long long n = fs[0]->len;
+  for (size_t k = 1; k < fs.size(); ++k) BN_TRY(join_dims(d, c, n, fs[k]->dims, fs[k]->card, fs[k]->len));
+  std::vector<int32_t> od, oc, sd, sc;
+  for (int j = 0; j < n_sum; ++j) {
+    BN_REQUIRE(find_dim(d, sum_dims[j]) >= 0, BN_NOT_IN_FACTOR, "%d is not a valid dimension", sum_dims[j]);
+    for (int j2 = 0; j2 < j; ++j2) BN_REQUIRE(sum_dims[j2] != sum_dims[j], BN_BAD_ARG, "Dimensions must be unique");
+  }
+  for (size_t i = 0; i < d.size(); ++i) {
+    bool summed = false;
+    for (int j = 0; j < n_sum; ++j) summed = summed || (sum_dims[j] == d[i]);
+    if (summed) { sd.push_back(d[i]); sc.push_back(c[i]); } else { od.push_back(d[i]); oc.push_back(c[i]); }
+  }
+  Factor* o = nullptr;
+  BN_TRY(new_factor(od, oc, device, &o));
+  // operand order: largest first so the leading (register-offset, vectorised) operand is the big one;
+  // the product value itself is order independent only up to commutativity, so keep the fold order
+  // for the multiplication and merely choose which operand drives the vector mode.
+  std::vector<Operand> ops;
+  for (Factor* f : fs) ops.push_back(Operand{f->data.p, f->dims, f->card});
+  int32_t rc = contract(device, ops, od, oc, sd, sc, o->data.p);
+  if (rc != BN_OK) { delete o; return rc; }
+  *out = o;
+  return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" {
+
+int32_t bn_factor_alloc(int32_t ndims, const int32_t* dims, const int32_t* card, int32_t device, bn_factor_t* out) {
+  BN_REQUIRE(out && ndims >= 0 && (ndims == 0 || (dims && card)), BN_BAD_ARG, "bn_factor_alloc: bad arguments");
+  BN_REQUIRE(ndims <= MAXD, BN_UNSUPPORTED, "factor with %d dims (max %d)", ndims, MAXD);
+  std::vector<int32_t> d(dims, dims + ndims), c(card, card + ndims);
+  for (int i = 0; i < ndims; ++i) {
+    BN_REQUIRE(c[i] >= 1, BN_BAD_ARG, "dimension %d has length %d", d[i], c[i]);
+    for (int j = 0; j < i; ++j) BN_REQUIRE(d[j] != d[i], BN_BAD_ARG, "Dimensions must be unique");  // errors.jl:10
+  }
+  int ndev = 0;
+  BN_CUDA_TRY(cudaGetDeviceCount(&ndev));
+  BN_REQUIRE(device >= 0 && device < ndev, BN_BAD_ARG, "device %d out of range", device);
+  Factor* f = nullptr;
+  BN_TRY(new_factor(d, c, device, &f));
+  *out = register_factor(f);
+  return BN_OK;
+}
+
+int32_t bn_factor_upload(int32_t ndims, const int32_t* dims, const int32_t* card, const double* data,
+                         int32_t device, bn_factor_t* out) {
+  BN_REQUIRE(data, BN_BAD_ARG, "bn_factor_upload: data is NULL");
+  BN_TRY(bn_factor_alloc(ndims, dims, card, device, out));
+  Factor* f = get_factor(*out);
+  BN_CUDA_TRY(cudaMemcpyAsync(f->data.p, data, (size_t)f->len * 8, cudaMemcpyHostToDevice, tl_stream));
+  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_factor_from_cpd(bn_net_t h, int32_t node, bn_factor_t* out) {
+  Net* net = get_net(h);
+  BN_REQUIRE(net && out, BN_BAD_ARG, "bn_factor_from_cpd: bad arguments");
+  BN_REQUIRE(node >= 0 && node < net->n, BN_BAD_ARG, "node %d out of range", node);
+  // convert(Factor, cpd): dims = [name, parents...], same memory order as the flat CPT (factors_main.jl:62-67)
+  std::vector<int32_t> d{node}, c{net->card[node]};
+  for (int k = net->par_ptr[node]; k < net->par_ptr[node + 1]; ++k) {
+    d.push_back(net->par_idx[k]);
+    c.push_back(net->card[net->par_idx[k]]);
+  }
+  BN_REQUIRE((int)d.size() <= MAXD, BN_UNSUPPORTED, "node %d has too many parents", node);
+  Factor* f = nullptr;
+  BN_TRY(new_factor(d, c, net->device, &f));
+  cudaError_t e = cudaMemcpyAsync(f->data.p, net->d_cpt.p + net->cpt_off[node], (size_t)f->len * 8,
+                                  cudaMemcpyDeviceToDevice, tl_stream);
+  if (e != cudaSuccess) { delete f; BN_CUDA_TRY(e); }
+  *out = register_factor(f);
+  return BN_OK;
+}
+
+int32_t bn_factor_relabel(bn_factor_t h, const int32_t* new_dims) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && (new_dims || f->dims.empty()), BN_BAD_ARG, "bn_factor_relabel: bad arguments");
+  for (size_t i = 0; i < f->dims.size(); ++i)
+    for (size_t j = 0; j < i; ++j) BN_REQUIRE(new_dims[i] != new_dims[j], BN_BAD_ARG, "Dimensions must be unique");
+  for (size_t i = 0; i < f->dims.size(); ++i) f->dims[i] = new_dims[i];
+  return BN_OK;
+}
+
+int32_t bn_factor_ndims(bn_factor_t h, int32_t* out_ndims) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out_ndims, BN_BAD_ARG, "bn_factor_ndims: bad arguments");
+  *out_ndims = (int32_t)f->dims.size();
+  return BN_OK;
+}
+
+int32_t bn_factor_shape(bn_factor_t h, int32_t* out_dims, int32_t* out_card) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_shape: unknown handle");
+  for (size_t i = 0; i < f->dims.size(); ++i) {
+    if (out_dims) out_dims[i] = f->dims[i];
+    if (out_card) out_card[i] = f->card[i];
+  }
+  return BN_OK;
+}
+
+int32_t bn_factor_length(bn_factor_t h, int64_t* out_len) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out_len, BN_BAD_ARG, "bn_factor_length: bad arguments");
+  *out_len = f->len;
+  return BN_OK;
+}
+
+int32_t bn_factor_download(bn_factor_t h, double* out) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out, BN_BAD_ARG, "bn_factor_download: bad arguments");
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  BN_CUDA_TRY(cudaMemcpyAsync(out, f->data.p, (size_t)f->len * 8, cudaMemcpyDeviceToHost, tl_stream));
+  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_factor_dev_ptr(bn_factor_t h, void** out_ptr) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out_ptr, BN_BAD_ARG, "bn_factor_dev_ptr: bad arguments");
+  *out_ptr = f->data.p;
+  return BN_OK;
+}
+
+int32_t bn_factor_free(bn_factor_t h) {
+  Factor* f = take_factor(h);
+  BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_free: unknown handle");
+  cudaSetDevice(f->device);
+  delete f;
+  return BN_OK;
+}
+
+int32_t bn_factor_product(bn_factor_t h1, bn_factor_t h2, bn_factor_t* out) {
+  Factor* f1 = get_factor(h1);
+  Factor* f2 = get_factor(h2);
+  BN_REQUIRE(f1 && f2 && out, BN_BAD_ARG, "bn_factor_product: bad arguments");
+  BN_CUDA_TRY(cudaSetDevice(f1->device));
+  if (f1->len < f2->len) std::swap(f1, f2);  // larger operand leads (factors_dims.jl:189-191)
+  Factor* o = nullptr;
+  BN_TRY(eliminate_impl({f1, f2}, nullptr, 0, &o));
+  *out = register_factor(o);
+  return BN_OK;
+}
+
+int32_t bn_factor_eliminate(const bn_factor_t* hs, int32_t n_factors, const int32_t* sum_dims, int32_t n_sum,
+                            bn_factor_t* out) {
+  BN_REQUIRE(hs && out && n_factors >= 1, BN_BAD_ARG, "bn_factor_eliminate: bad arguments");
+  BN_REQUIRE(n_sum == 0 || sum_dims, BN_BAD_ARG, "bn_factor_eliminate: sum_dims is NULL");
+  std::vector<Factor*> fs;
+  for (int k = 0; k < n_factors; ++k) {
+    Factor* f = get_factor(hs[k]);
+    BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_eliminate: unknown handle #%d", k);
+    fs.push_back(f);
+  }
+  BN_CUDA_TRY(cudaSetDevice(fs[0]->device));
+  // put the largest operand first: it drives the coalesced / vectorised access pattern.  The fold's
+  // dim order is recomputed from the ORIGINAL order inside eliminate_impl's join simulation, so do the
+  // reordering only when it cannot change that order: i.e. when the largest is already first or the
+  // reference itself would have swapped it to the front.
+  Factor* o = nullptr;
+  BN_TRY(eliminate_impl(fs, sum_dims, n_sum, &o));
+  *out = register_factor(o);
+  return BN_OK;
+}
+
+int32_t bn_factor_sum(bn_factor_t h, const int32_t* sum_dims, int32_t n_sum, bn_factor_t* out) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out, BN_BAD_ARG, "bn_factor_sum: bad arguments");
+  BN_REQUIRE(n_sum == 0 || sum_dims, BN_BAD_ARG, "bn_factor_sum: sum_dims is NULL");
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  Factor* o = nullptr;
+  BN_TRY(eliminate_impl({f}, sum_dims, n_sum, &o));
+  *out = register_factor(o);
+  return BN_OK;
+}
+
+int32_t bn_factor_slice(bn_factor_t h, const int32_t* dims, const int32_t* states, int32_t n_assign, bn_factor_t* out) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out, BN_BAD_ARG, "bn_factor_slice: bad arguments");
+  BN_REQUIRE(n_assign == 0 || (dims && states), BN_BAD_ARG, "bn_factor_slice: NULL assignment");
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  // _translate_index: src/Factors/factors_access.jl:48-72 (dims absent from phi are ignored)
+  long long base = 0, st = 1;
+  std::vector<int32_t> kd, kc;
+  Operand op{nullptr, {}, {}};
+  std::vector<long long> kstride;
+  for (size_t i = 0; i < f->dims.size(); ++i) {
+    int hit = -1;
+    for (int j = 0; j < n_assign; ++j) if (dims[j] == f->dims[i]) hit = j;
+    if (hit >= 0) {
+      BN_REQUIRE(states[hit] >= 0 && states[hit] < f->card[i], BN_BOUNDS, "BoundsError: state %d for dim %d (size %d)",
+                 states[hit], f->dims[i], f->card[i]);
+      base += st * states[hit];
+    } else {
+      kd.push_back(f->dims[i]);
+      kc.push_back(f->card[i]);
+    }
+    st *= f->card[i];
+  }
+  Factor* o = nullptr;
+  BN_TRY(new_factor(kd, kc, f->device, &o));
+  if (kd.size() == f->dims.size()) {
+    cudaError_t e = cudaMemcpyAsync(o->data.p, f->data.p, (size_t)f->len * 8, cudaMemcpyDeviceToDevice, tl_stream);
+    if (e != cudaSuccess) { delete o; BN_CUDA_TRY(e); }
+  } else {
+    // a strided gather = 1-operand contraction over the kept dims, sliced dims pinned via the base offset:
+    // present the operand with its FULL dim list but give sliced dims a fresh id that is "summed" with card 1.
+    Operand full{f->data.p + base, {}, {}};
+    std::vector<int32_t> sd, sc;
+    int32_t fresh = -1;
+    for (size_t i = 0; i < f->dims.size(); ++i) {
+      bool kept = find_dim(kd, f->dims[i]) >= 0;
+      if (kept) { full.dims.push_back(f->dims[i]); full.card.push_back(f->card[i]); }
+      else {
+        // sliced dim: keeps its extent in the stride computation but only index 0 (the base) is visited
+        while (find_dim(f->dims, fresh) >= 0) --fresh;
+        full.dims.push_back(fresh);
+        full.card.push_back(f->card[i]);
+        sd.push_back(fresh);
+        sc.push_back(1);
+        --fresh;
+      }
+    }
+    int32_t rc = contract(f->device, {full}, kd, kc, sd, sc, o->data.p);
+    if (rc != BN_OK) { delete o; return rc; }
+  }
+  *out = register_factor(o);
+  return BN_OK;
+}
+
+int32_t bn_factor_normalize(bn_factor_t h, int32_t pnorm) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_normalize: unknown handle");
+  BN_REQUIRE(pnorm == 1 || pnorm == 2, BN_BAD_ARG, "p = %d is not supported", pnorm);  // factors_dims.jl:51
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  const DevProps& dp = dev_props(f->device);
+  const int grid = (int)std::min<long long>((f->len / 2 + 511) / 512 + 1, (long long)dp.sm_count * 4);
+  static thread_local DevBuf<double> scratch;      // [grid partials | total]
+  static thread_local DevBuf<unsigned int> ticket;
+  static thread_local int scratch_dev = -1;
+  if (scratch_dev != f->device || scratch.n < (size_t)dp.sm_count * 4 + 1) {
+    BN_CUDA_TRY(scratch.alloc((size_t)dp.sm_count * 4 + 1));
+    BN_CUDA_TRY(ticket.alloc(1));
+    BN_CUDA_TRY(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), tl_stream));
+    scratch_dev = f->device;
+  }
+  double* total = scratch.p + (size_t)dp.sm_count * 4;
+  norm_reduce_kernel<<<grid, 512, 0, tl_stream>>>(f->data.p, f->len, pnorm, scratch.p, ticket.p, total);
+  count_launch();
+  norm_scale_kernel<<<grid, 512, 0, tl_stream>>>(f->data.p, f->len, total);
+  count_launch();
+  BN_CUDA_TRY(cudaGetLastError());
+  return BN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing: one process per GPU, particles / chains sharded by GLOBAL index, one all-reduce of the
+(weighted) count tensor.  torch.distributed is used for exactly that collective (NCCL over NVLink on the GPU
+box, gloo in the CPU tests) and nothing else.
+
+Sharding contract: rank g of G handles indices [g*N//G, (g+1)*N//G).  Because the Philox
+counter is the global particle / chain index, the all-reduced tensor equals the single-GPU tensor up to
+fp64 addition order (exactly, for the integer Gibbs counts).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+from .device_layout import device_net
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first index, count) of rank's contiguous shard; shards tile [0, n_total) exactly."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside 0..{world - 1}")
+    lo = (n_total * rank) // world
+    hi = (n_total * (rank + 1)) // world
+    return lo, hi - lo
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks of a count tensor (torch tensor on this rank's device, or CPU for gloo)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class ShardedLikelihoodWeighting:
+    """LW inference whose particles are split over the ranks of the default process group.
+
+    step() enqueues this rank's shard (bn_lw_infer_dev) on torch's current stream into a resident fp64
+    tensor [ncell + 2] = (weighted counts | sum w | sum w^2) and all-reduces it; normalisation happens after
+    the reduction, exactly where the reference normalises (src/Inference/likelihood.jl:56)."""
+
+    def __init__(self, bn, query, evidence, n_total: int, seed: int = 0, device: int | None = None):
+        import torch
+        self.torch = torch
+        rank, world, local = env_rank_world()
+        self.rank, self.world = rank, world
+        self.device = local if device is None else device
+        self.net = device_net(bn, self.device)
+        lay = self.net.layout
+        self.ev = lay.evidence_vector(evidence)
+        self.q = lay.query_indices(query)
+        self.shape = [int(lay.card[i]) for i in self.q]
+        self.ncell = int(np.prod(self.shape)) if self.shape else 1
+        self.n_total = int(n_total)
+        self.first, self.count = shard_range(self.n_total, rank, world)
+        self.seed = int(seed)
+        self.out = torch.zeros(self.ncell + 2, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def launch(self, first=None, count=None):
+        """Enqueue the local shard only (no collective); result in self.out."""
+        torch = self.torch
+        _lib.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        qp = self.q if self.q.size else np.zeros(1, np.int32)
+        check(_lib.lib().bn_lw_infer_dev(_lib.h64(self.net.handle), ptr(self.ev, _lib.i8p), ptr(qp, _lib.i32p),
+                                         C.c_int32(self.q.size),
+                                         C.c_uint64(self.first if first is None else first),
+                                         C.c_uint64(self.count if count is None else count),
+                                         C.c_uint64(self.seed), C.c_void_p(self.out.data_ptr())))
+        return self.out
+
+    def step(self):
+        self.launch()
+        return allreduce_sum_(self.out)
+
+    def posterior(self) -> np.ndarray:
+        c = self.out[:self.ncell].cpu().numpy()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (c / c.sum()).reshape(self.shape, order="F")

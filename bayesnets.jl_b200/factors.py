@@ -1,0 +1,263 @@
+"""Factor: a dense named-dimension Float64 table living in HBM (mirror of src/Factors).
+
+`*`, `sum`, `normalize!`, `ϕ[assignment]` and `Factor(bn, name, evidence)` are kernels behind the
+C ABI (bn_factor_*).  `.potential` downloads a column-major numpy array shaped like the reference's
+`Array{Float64,N}`.  States in assignments are 1-based, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr, DimensionMismatch  # noqa: F401
+from .device_layout import default_device, device_net
+
+# Symbol <-> int32 id (the Julia glue keeps the same kind of table)
+_ids: dict = {}
+_names: list = []
+
+
+def var_id(name) -> int:
+    i = _ids.get(name)
+    if i is None:
+        i = len(_names)
+        _ids[name] = i
+        _names.append(name)
+    return i
+
+
+def var_name(i: int):
+    return _names[i]
+
+
+def _as_names(dims) -> list:
+    if isinstance(dims, (str, bytes)) or not isinstance(dims, Iterable):
+        return [dims]
+    return list(dims)
+
+
+class Factor:
+    """Factor(dims, potential) | Factor(dims, lengths, fill_value=0)   (src/Factors/factors_main.jl:18-56)."""
+
+    def __init__(self, dims, potential_or_lengths=None, fill_value=0.0, *, device: int | None = None, _handle=None):
+        self._fin = None
+        if _handle is not None:
+            self._adopt(_handle)
+            return
+        dims = _as_names(dims)
+        if len(set(dims)) != len(dims):
+            raise ValueError("Dimensions must be unique")  # errors.jl:10
+        arg = potential_or_lengths
+        if isinstance(arg, np.ndarray) and arg.dtype.kind == "f":
+            pot = np.asarray(arg, np.float64)
+        elif isinstance(arg, (list, tuple, np.ndarray)) and all(isinstance(x, (int, np.integer)) for x in arg):
+            lengths = [int(x) for x in arg]
+            if len(dims) != len(lengths):
+                raise DimensionMismatch("`potential` must have as many dimensions as dims")
+            pot = np.full(lengths, 0.0 if fill_value is None else float(fill_value), np.float64)
+        else:
+            pot = np.asarray(arg, np.float64)
+        if len(dims) != pot.ndim:
+            raise DimensionMismatch("`potential` must have as many dimensions as dims")  # factors_main.jl:27-29
+        device = default_device() if device is None else device
+        ids = np.array([var_id(d) for d in dims], np.int32)
+        card = np.array(pot.shape, np.int32)
+        flat = np.ascontiguousarray(pot.reshape(-1, order="F"))
+        h = _lib.h64(0)
+        dp = ids if ids.size else np.zeros(1, np.int32)
+        cp = card if card.size else np.ones(1, np.int32)
+        check(_lib.lib().bn_factor_upload(C.c_int32(len(dims)), ptr(dp, _lib.i32p), ptr(cp, _lib.i32p),
+                                          ptr(flat, _lib.f64p), C.c_int32(device), C.byref(h)))
+        self._adopt(h.value)
+
+    # -- handle plumbing ---------------------------------------------------------------------
+    def _adopt(self, handle: int) -> None:
+        self.handle = int(handle)
+        nd = C.c_int32(0)
+        check(_lib.lib().bn_factor_ndims(_lib.h64(self.handle), C.byref(nd)))
+        ids = np.zeros(max(nd.value, 1), np.int32)
+        card = np.zeros(max(nd.value, 1), np.int32)
+        check(_lib.lib().bn_factor_shape(_lib.h64(self.handle), ptr(ids, _lib.i32p), ptr(card, _lib.i32p)))
+        self.dimensions = [var_name(int(i)) for i in ids[:nd.value]]
+        self._shape = tuple(int(c) for c in card[:nd.value])
+        self._fin = weakref.finalize(self, Factor._free, self.handle)
+
+    @staticmethod
+    def _free(handle):
+        try:
+            _lib.lib().bn_factor_free(_lib.h64(handle))
+        except Exception:
+            pass
+
+    @classmethod
+    def _from_handle(cls, h) -> "Factor":
+        return cls(None, _handle=h.value if hasattr(h, "value") else h)
+
+    # -- construction from a network node: Factor(bn, name, evidence) (factors_main.jl:79-83) ---
+    @classmethod
+    def from_bn(cls, bn, name, evidence: dict | None = None, device: int | None = None) -> "Factor":
+        net = device_net(bn, device)
+        # dims of CPD factors are node indices on the device; give them this network's names
+        h = _lib.h64(0)
+        check(_lib.lib().bn_factor_from_cpd(_lib.h64(net.handle), C.c_int32(net.layout.index[name]), C.byref(h)))
+        cpd = bn.get(name)
+        ids = np.array([var_id(n) for n in [name] + list(cpd.parents)], np.int32)
+        check(_lib.lib().bn_factor_relabel(h, ptr(ids, _lib.i32p)))
+        f = Factor._from_handle(h)
+        return f[evidence] if evidence else f
+
+    # -- basic queries (factors_main.jl:93-135) -----------------------------------------------
+    @property
+    def potential(self) -> np.ndarray:
+        n = int(np.prod(self._shape)) if self._shape else 1
+        out = np.zeros(n, np.float64)
+        check(_lib.lib().bn_factor_download(_lib.h64(self.handle), ptr(out, _lib.f64p)))
+        return out.reshape(self._shape, order="F")
+
+    def names(self):
+        return list(self.dimensions)
+
+    @property
+    def ndims(self) -> int:
+        return len(self.dimensions)
+
+    def size(self, *dims):
+        if not dims:
+            return self._shape
+        for d in dims:
+            if d not in self.dimensions:
+                raise ValueError(f"{d} is not a valid dimension")
+        r = tuple(self._shape[self.dimensions.index(d)] for d in dims)
+        return r[0] if len(r) == 1 else r
+
+    def __len__(self):
+        return int(np.prod(self._shape)) if self._shape else 1
+
+    def __contains__(self, dim):
+        return dim in self.dimensions
+
+    def _check_dims_valid(self, dims):  # auxiliary.jl:7-14
+        for d in dims:
+            if d not in self.dimensions:
+                raise ValueError(f"{d} is not a valid dimension")
+
+    # -- `*` = join(*, phi1, phi2, :outer) (factors_dims.jl:185-234,269) -----------------------
+    def __mul__(self, other: "Factor") -> "Factor":
+        if not isinstance(other, Factor):
+            return NotImplemented
+        h = _lib.h64(0)
+        check(_lib.lib().bn_factor_product(_lib.h64(self.handle), _lib.h64(other.handle), C.byref(h)))
+        return Factor._from_handle(h)
+
+    def _unsupported(self, other):
+        raise NotImplementedError("only `*` is offloaded; / + - go through the same join in the reference "
+                                  "(factors_dims.jl:270-272) but are not on the inference path")
+
+    __truediv__ = __add__ = __sub__ = _unsupported
+
+    # -- sum(phi, dims) = reducedim(+, ...) (factors_dims.jl:60-85,100) -------------------------
+    def sum(self, dims) -> "Factor":
+        dims = _as_names(dims)
+        self._check_dims_valid(dims)
+        ids = np.array([var_id(d) for d in dims], np.int32)
+        h = _lib.h64(0)
+        dp = ids if ids.size else np.zeros(1, np.int32)
+        check(_lib.lib().bn_factor_sum(_lib.h64(self.handle), ptr(dp, _lib.i32p), C.c_int32(ids.size), C.byref(h)))
+        return Factor._from_handle(h)
+
+    # -- normalize!(phi; p) / normalize(phi; p) (factors_dims.jl:24-57) -------------------------
+    def normalize_(self, dims=None, p: int = 1) -> "Factor":
+        if dims is not None:
+            self._check_dims_valid(list(dict.fromkeys(_as_names(dims))))
+            raise NotImplementedError("normalize!(phi, dims) is not on the inference path")
+        if p not in (1, 2):
+            raise ValueError(f"p = {p} is not supported")
+        check(_lib.lib().bn_factor_normalize(_lib.h64(self.handle), C.c_int32(p)))
+        return self
+
+    def copy(self) -> "Factor":
+        h = _lib.h64(0)
+        check(_lib.lib().bn_factor_slice(_lib.h64(self.handle), None, None, C.c_int32(0), C.byref(h)))
+        return Factor._from_handle(h)
+
+    def normalize(self, dims=None, p: int = 1) -> "Factor":
+        if dims is not None:
+            self._check_dims_valid(list(dict.fromkeys(_as_names(dims))))
+        return self.copy().normalize_(dims, p)
+
+    # -- phi[assignment] (factors_access.jl:19-35,48-72) ----------------------------------------
+    def __getitem__(self, a):
+        if isinstance(a, dict):
+            dims, states = [], []
+            for d in self.dimensions:
+                if d in a:
+                    v = a[d]
+                    if v is Ellipsis or (isinstance(v, slice) and v == slice(None)):
+                        continue
+                    if not isinstance(v, (int, np.integer)) or isinstance(v, bool):
+                        raise TypeError(f"Invalid state for dimension {d}")
+                    n = self._shape[self.dimensions.index(d)]
+                    if v < 1 or v > n:
+                        raise IndexError(f"BoundsError({d}, {v})")
+                    dims.append(var_id(d))
+                    states.append(int(v) - 1)
+            di = np.array(dims if dims else [0], np.int32)
+            si = np.array(states if states else [0], np.int32)
+            h = _lib.h64(0)
+            check(_lib.lib().bn_factor_slice(_lib.h64(self.handle), ptr(di, _lib.i32p), ptr(si, _lib.i32p),
+                                             C.c_int32(len(dims)), C.byref(h)))
+            return Factor._from_handle(h)
+        if isinstance(a, (int, np.integer)):
+            return float(self.potential.reshape(-1, order="F")[a - 1])
+        return self.pattern(a)
+
+    # -- broadcast(*, phi, dims, values) (factors_dims.jl:130-168): a product with 1-d factors ----
+    def broadcast_mul(self, dims, values) -> "Factor":
+        if isinstance(dims, (str, bytes)) or not isinstance(dims, Iterable):
+            dims, values = [dims], [values]
+        dims = list(dims)
+        if len(set(dims)) != len(dims):
+            raise ValueError("Dimensions must be unique")
+        self._check_dims_valid(dims)
+        if len(dims) != len(values):
+            raise ValueError("Number of dimensions does not match number of values to broadcast")
+        out = self
+        for d, v in zip(dims, values):
+            n = self._shape[self.dimensions.index(d)]
+            if np.isscalar(v):
+                vec = np.full(n, float(v))
+            else:
+                vec = np.asarray(v, np.float64)
+                if vec.shape != (n,):
+                    raise DimensionMismatch(f"broadcast value for {d} has length {vec.size}, dimension has {n}")
+            out = out * Factor([d], vec)
+        return out if out is not self else self.copy()
+
+    # -- pattern (factors_main.jl:174-199): host-side index bookkeeping ---------------------------
+    def pattern(self, dims=None) -> np.ndarray:
+        dims = self.dimensions if dims is None else _as_names(dims)
+        self._check_dims_valid(dims)
+        lens = list(self._shape)
+        n = len(self)
+        cols = []
+        for d in dims:
+            i = self.dimensions.index(d)
+            inner = int(np.prod(lens[:i])) if i else 1
+            outer = n // lens[i] // inner
+            cols.append(np.tile(np.repeat(np.arange(1, lens[i] + 1), inner), outer))
+        return np.stack(cols, axis=1)
+
+    def to_dataframe(self):
+        """convert(DataFrame, phi) (factors_dataframes.jl:9-20)."""
+        import pandas as pd
+        pat = self.pattern()
+        df = pd.DataFrame({d: pat[:, i] for i, d in enumerate(self.dimensions)})
+        df["potential"] = self.potential.reshape(-1, order="F")
+        return df
+
+    def __repr__(self):
+        return f"Factor(dims={self.dimensions}, size={self._shape})"

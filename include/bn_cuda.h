@@ -1,0 +1,166 @@
+/*
+ * bn_cuda.h -- C ABI of libbn_cuda.so: the B200 (sm_100a) implementation of BayesNets.jl's
+ * data-parallel discrete-inference hot path.
+ *
+ * The reference (sisl/BayesNets.jl v3.5.2, pure Julia) has no FFI of its own: its extension points are
+ * multiple dispatch on InferenceMethod (src/ProbabilisticGraphicalModels/inference.jl:4,48-49) and on
+ * Base.:* / Base.sum / normalize! for Factor (src/Factors/factors_dims.jl:100,269,45).  Each entry point
+ * below names the reference method whose inner loop it replaces; INTEGRATION.md shows the `ccall`
+ * a maintainer adds on the Julia side and the ctypes stub the Python mirror uses.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; every function returns bn_status
+ *     (0 = ok, <0 = error; bn_last_error() gives a thread-local message)
+ *   - networks are passed flat, nodes in topological order (src/bayes_nets.jl:26-48), states 0-based:
+ *       card[n], par_ptr[n+1]/par_idx[] (CSR, parents in cpd.parents order), cpt_off[n+1], cpt[]
+ *       CPT entry P(x_i = s | pa) = cpt[cpt_off[i] + s + card[i] * sum_k state(parent_k) * stride_k],
+ *       stride_0 = 1, stride_k = prod_{j<k} card(parent_j)      (src/CPDs/categorical_cpd.jl:36-46,
+ *       src/Factors/factors_main.jl:62-67: vcat(d.p for d in distributions))
+ *   - evidence[n] is int8: -1 = free, otherwise the clamped 0-based state
+ *   - factors are column-major Float64 exactly as Factor.potential (src/Factors/factors_main.jl:20);
+ *     variables are int32 ids (the Julia glue maps Symbol <-> id)
+ *   - host pointers unless the name ends in _dev; the caller owns every host buffer, the library owns
+ *     device memory behind opaque handles; no host pointer is retained after return
+ *   - calls are synchronous unless they end in _dev (those enqueue on the stream set by
+ *     bn_set_stream and return immediately)
+ *   - random streams: Philox4x32-10, key = seed, counter = (index_lo, index_hi, draw/4, stream id);
+ *     particle / chain indices are GLOBAL (first_* + i), so sharding a job over ranks reproduces the
+ *     single-GPU stream bit for bit
+ */
+#ifndef BN_CUDA_H
+#define BN_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t bn_net_t;    /* device-resident flattened DiscreteBayesNet */
+typedef uint64_t bn_factor_t; /* device-resident Factor (dims + column-major fp64 potential) */
+
+typedef enum {
+  BN_OK = 0,
+  BN_BAD_ARG = -1,        /* ArgumentError */
+  BN_DIM_MISMATCH = -2,   /* DimensionMismatch (src/Factors/factors_dims.jl:197-199) */
+  BN_NOT_IN_FACTOR = -3,  /* ArgumentError "... is not a valid dimension" (src/Factors/errors.jl:12) */
+  BN_CUDA_ERR = -4,
+  BN_ZERO_WEIGHT = -5,    /* every particle had weight 0 / no initial Gibbs sample (src/gibbs.jl:332-334) */
+  BN_OOM = -6,
+  BN_UNSUPPORTED = -7,
+  BN_BOUNDS = -8          /* BoundsError (src/Factors/factors_access.jl:59-61) */
+} bn_status;
+
+enum { BN_SAMPLE_ANCESTRAL = 0, BN_SAMPLE_REJECTION = 1, BN_SAMPLE_WEIGHTED = 2 };
+enum { BN_GIBBS_NODEWISE = 0, BN_GIBBS_FULL = 1 };
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* bn_last_error(void);
+int32_t bn_version(void);
+int32_t bn_device_count(int32_t* out_n);
+/* Stream (a cudaStream_t cast to void*) used by subsequent calls from this host thread; NULL = default. */
+int32_t bn_set_stream(void* cuda_stream);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t bn_launch_count(void);
+
+/* ---- network: replaces nothing; it is the device_layout.jl upload (DiscreteBayesNet -> HBM) ---- */
+int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                      const int64_t* cpt_off, const double* cpt, int32_t device, bn_net_t* out_net);
+int32_t bn_net_destroy(bn_net_t net);
+
+/* ---- likelihood weighting: infer(::LikelihoodWeightingInference, ::InferenceState)
+ *      src/Inference/likelihood.jl:16-58 (the :34-54 particle loop) ------------------------------
+ * out_counts: prod(card[query]) doubles, column-major over the query cards (first query fastest),
+ *             UNNORMALISED weighted counts  phi.potential[q_ind...] += w  (:53)
+ * out_stats : [sum w, sum w^2]  (N_eff = stats[0]^2 / stats[1])
+ * Particles first_particle .. first_particle + n_particles - 1.  Normalisation (:56) is the caller's
+ * (bn_factor_normalize or one division) so that shards can be summed first. */
+int32_t bn_lw_infer(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                    uint64_t first_particle, uint64_t n_particles, uint64_t seed,
+                    double* out_counts, double* out_stats);
+/* Same, asynchronous, result left in device memory: out_dev[0..ncell) counts, [ncell] sum w,
+ * [ncell+1] sum w^2.  out_dev is ZEROED by the call.  This is what the multi-GPU path all-reduces. */
+int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                        uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_dev);
+
+/* ---- table samplers: rand(bn, n) / rand(bn, n, evidence) / get_weighted_dataframe
+ *      src/sampling.jl:24-41,52-57 (ancestral), :72-93 (rejection, <= max_attempts tries),
+ *      :102-115,153-174 (likelihood-weighted rows) -------------------------------------------------
+ * out_states: n_nodes x n uint8, node-major (out_states[i*n + row]) = one DataFrame column per node
+ * out_w     : n doubles (weighted kind; may be NULL otherwise)
+ * out_ok    : n bytes, 0 where rejection gave up (the reference returns an empty assignment, :87) */
+int32_t bn_sample(bn_net_t net, const int8_t* evidence, int32_t kind, int32_t max_attempts,
+                  uint64_t first_row, uint64_t n_rows, uint64_t seed,
+                  uint8_t* out_states, double* out_w, uint8_t* out_ok);
+int32_t bn_sample_dev(bn_net_t net, const int8_t* evidence, int32_t kind, int32_t max_attempts,
+                      uint64_t first_row, uint64_t n_rows, uint64_t seed,
+                      uint8_t* out_states_dev, double* out_w_dev, uint8_t* out_ok_dev);
+
+/* ---- Gibbs inference: infer(::GibbsSamplingNodewise / ::GibbsSamplingFull, ::InferenceState)
+ *      src/Inference/gibbs.jl:66-145 / :161-234, n_chains independent chains ---------------------
+ * state_inout: optional n_chains x n_nodes uint8 (chain-major).  init_from_state != 0 resumes the
+ *              chains from it (im.state, :83-88); final states are written back when non-NULL.
+ * out_counts : prod(card[query]) doubles summed over chains (unnormalised)
+ * out_chain_counts: optional n_chains x ncell (chain-major) for between-chain variance */
+int32_t bn_gibbs_infer(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                       uint64_t first_chain, uint64_t n_chains, int64_t nsamples, int64_t burn_in,
+                       int64_t thin, int32_t mode, uint64_t seed, uint8_t* state_inout,
+                       int32_t init_from_state, double* out_counts, double* out_chain_counts);
+int32_t bn_gibbs_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                           uint64_t first_chain, uint64_t n_chains, int64_t nsamples, int64_t burn_in,
+                           int64_t thin, int32_t mode, uint64_t seed, double* out_dev);
+
+/* ---- gibbs_sample(bn, nsamples, burn_in; thinning, consistent_with, variable_order, initial_sample)
+ *      src/gibbs.jl:289-374 (main loop :183-245), n_chains chains each returning nsamples rows ----
+ * variable_order: NULL = fresh random permutation every sweep (:222-234), else n_free positions into
+ *                 the list of non-evidence nodes (topological order)
+ * init_state    : NULL = 50 likelihood-weighted particles, one resampled (:330-335), else
+ *                 n_chains x n_nodes uint8
+ * out_states    : n_nodes x (n_chains*nsamples) uint8, node-major; row = chain*nsamples + s */
+int32_t bn_gibbs_sample(bn_net_t net, const int8_t* evidence, uint64_t first_chain, uint64_t n_chains,
+                        int64_t nsamples, int64_t burn_in, int64_t thinning,
+                        const int32_t* variable_order, uint64_t seed, const uint8_t* init_state,
+                        uint8_t* out_states);
+
+/* ---- factors: Factor(dims, potential) on the device (src/Factors/factors_main.jl:18-36) -------- */
+int32_t bn_factor_upload(int32_t ndims, const int32_t* dims, const int32_t* card, const double* data,
+                         int32_t device, bn_factor_t* out);
+int32_t bn_factor_alloc(int32_t ndims, const int32_t* dims, const int32_t* card, int32_t device,
+                        bn_factor_t* out);               /* uninitialised potential */
+int32_t bn_factor_from_cpd(bn_net_t net, int32_t node, bn_factor_t* out); /* convert(Factor, cpd) :62-68,
+                                                         dims = [node, parents...], ids = node indices */
+int32_t bn_factor_relabel(bn_factor_t f, const int32_t* new_dims); /* rename the dims in place (ndims ids, unique) */
+int32_t bn_factor_ndims(bn_factor_t f, int32_t* out_ndims);
+int32_t bn_factor_shape(bn_factor_t f, int32_t* out_dims, int32_t* out_card); /* ndims entries each */
+int32_t bn_factor_length(bn_factor_t f, int64_t* out_len);
+int32_t bn_factor_download(bn_factor_t f, double* out);
+int32_t bn_factor_dev_ptr(bn_factor_t f, void** out_ptr);
+int32_t bn_factor_free(bn_factor_t f);
+
+/* phi1 * phi2 = join(*, phi1, phi2, :outer): src/Factors/factors_dims.jl:185-234,269.
+ * Larger operand first (:189-191), dims = union (:203), BN_DIM_MISMATCH on unequal common dims. */
+int32_t bn_factor_product(bn_factor_t f1, bn_factor_t f2, bn_factor_t* out);
+/* sum(phi, dims) = reducedim(+, phi, dims): src/Factors/factors_dims.jl:60-85,100. */
+int32_t bn_factor_sum(bn_factor_t f, const int32_t* sum_dims, int32_t n_sum, bn_factor_t* out);
+/* phi[assignment] (getindex): src/Factors/factors_access.jl:19-35,48-72; dims not in phi are ignored. */
+int32_t bn_factor_slice(bn_factor_t f, const int32_t* dims, const int32_t* states, int32_t n_assign,
+                        bn_factor_t* out);
+/* normalize!(phi; p): src/Factors/factors_dims.jl:45-57 (p in {1,2}; p=2 divides by sum(abs2)). */
+int32_t bn_factor_normalize(bn_factor_t f, int32_t p);
+/* sum(reduce(*, factors), var) in ONE pass (the elimination step of src/Inference/exact.jl:27):
+ * multiplies left to right like the reference's fold, never materialising the product.
+ * n_sum = 0 gives the plain n-ary product. */
+int32_t bn_factor_eliminate(const bn_factor_t* factors, int32_t n_factors, const int32_t* sum_dims,
+                            int32_t n_sum, bn_factor_t* out);
+
+/* ---- infer(::ExactInference, ::InferenceState): src/Inference/exact.jl:6-33 ---------------------
+ * Variable elimination entirely on the device.  out_dims/out_card: n_query entries (the result's dim
+ * order is join-order dependent, as in the reference -- compare by name); out: prod(card) doubles.
+ * fused != 0 uses bn_factor_eliminate per hidden variable, 0 the reference's pairwise product+sum. */
+int32_t bn_exact_infer(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                       int32_t fused, int32_t* out_dims, int32_t* out_card, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BN_CUDA_H */

@@ -1,0 +1,217 @@
+"""Host-side logic of the mirror (no GPU needed): containers, device layout, validation, formats, ABI surface."""
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_mirror_net, oracle_net_from_layout
+
+
+def test_library_exports_every_declared_symbol(bn):
+    """include/bn_cuda.h is the contract: the built .so must export each declared entry point, and the ctypes
+    table must bind the same set."""
+    hdr = open(os.path.join(ROOT, "include", "bn_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    assert os.path.exists(bn.LIB_PATH), "build libbn_cuda.so first (python bayesnets.jl_b200/build.py)"
+    lib = ctypes.CDLL(bn.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in bn_cuda.h but not exported"
+    assert declared == set(bn.EXPORTS)
+    assert lib.bn_version() == 100
+
+
+def test_no_cpu_fallback(bn):
+    """Without a GPU every compute entry point must fail loudly, never route to the oracle."""
+    if bn.device_count.__module__ and _has_gpu(bn):
+        pytest.skip("GPU present")
+    net = bn.get_asia_bn()
+    with pytest.raises(bn.BNCudaError):
+        bn.infer(bn.LikelihoodWeightingInference(10), net, "T")
+    with pytest.raises(bn.BNCudaError):
+        bn.Factor(["X"], np.ones(3))
+    src = ""
+    for f in os.listdir(os.path.join(ROOT, "bayesnets.jl_b200")):
+        if f.endswith(".py"):
+            src += open(os.path.join(ROOT, "bayesnets.jl_b200", f)).read()
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def _has_gpu(bn):
+    try:
+        return bn.device_count() > 0
+    except Exception:
+        return False
+
+
+def test_topological_order_matches_graphs_dfs(bn):
+    """src/bayes_nets.jl:26-48: reverse DFS post-order, re-run on every push! (:258-276).  Sorting a, b, c
+    (c <- a, c <- b) in one go gives b, a, c; pushing them one at a time re-sorts [b, a] + c into a, b, c."""
+    cpds = [bn.DiscreteCPD("a", [1.0, 0.0]), bn.DiscreteCPD("b", [0.0, 1.0]),
+            bn.CategoricalCPD("c", ["a", "b"], [2, 2], [[0.1, 0.9], [0.2, 0.8], [1.0, 0.0], [0.4, 0.6]])]
+    assert bn.BayesNet(cpds).names() == ["b", "a", "c"]
+    net = make_mirror_net(bn, [["a", [], [[1.0, 0.0]]], ["b", [], [[0.0, 1.0]]],
+                               ["c", ["a", "b"], [[0.1, 0.9], [0.2, 0.8], [1.0, 0.0], [0.4, 0.6]]]])
+    assert net.names() == ["a", "b", "c"]
+    assert net.parents("c") == ["a", "b"] and net.children("a") == ["c"]
+    assert net.markov_blanket("a") == {"b", "c"}
+    with pytest.raises(ValueError):
+        net.push(bn.DiscreteCPD("a", [0.5, 0.5]))
+    assert net.pdf({"a": 1, "b": 2, "c": 1}) == 1.0 and net.pdf(a=2, b=2, c=1) == 0.0
+
+
+def test_device_layout_student(bn, golden):
+    net = make_mirror_net(bn, golden["inference_student"]["nodes"])
+    lay = bn.flatten(net)
+    assert sorted(lay.names) == ["D", "G", "I", "L", "S"]
+    g = lay.index["G"]
+    assert lay.card[g] == 3 and [lay.names[p] for p in lay.parents(g)] == ["D", "I"]
+    # first parent fastest: row q = d + 2*i (src/CPDs/categorical_cpd.jl:36-46)
+    rows = golden["inference_student"]["nodes"][2][2]
+    tab = lay.cpt[lay.cpt_off[g]:lay.cpt_off[g + 1]].reshape(3, 4, order="F")
+    for q in range(4):
+        assert tab[:, q].tolist() == rows[q]
+    for i in range(lay.n):  # topological
+        assert all(p < i for p in lay.parents(i))
+    ev = lay.evidence_vector({"D": 1, "I": 2, "nope": 3})
+    assert ev[lay.index["D"]] == 0 and ev[lay.index["I"]] == 1 and (ev >= 0).sum() == 2
+    with pytest.raises(IndexError):
+        lay.evidence_vector({"D": 3})
+    with pytest.raises(TypeError):
+        lay.evidence_vector({"D": "x"})
+
+
+def test_inference_state_validation(bn):
+    """test/test_inference.jl:5-31."""
+    net = bn.rand_discrete_bn(seed=1)
+    with pytest.raises(ValueError):
+        bn.InferenceState(net, ["waldo", "N3"])
+    with pytest.raises(ValueError):
+        bn.InferenceState(net, ["N2", "N3"], {"N1": 1, "N3": 3, "N7": 2016})
+    assert bn.InferenceState(net, ["N3", "N5", "N2", "N3"]).query == ["N3", "N5", "N2"]
+    assert bn.InferenceState(net, "N6").query == ["N6"]
+    with pytest.raises(ValueError):
+        bn.InferenceState(net, "N1", {"N1": 2})
+
+
+def test_rand_discrete_bn_invariants(bn):
+    """test/test_genbn.jl:10-28."""
+    net = bn.rand_discrete_bn(10, 4, 5, seed=0)
+    assert set(net.names()) == {f"N{i}" for i in range(1, 11)}
+    for n in net.names():
+        assert 2 <= net.ncategories(n) <= 5 and len(net.parents(n)) <= 4
+        for d in net.get(n).distributions:
+            assert abs(d.sum() - 1) < 1e-12
+    with pytest.raises(ValueError):
+        bn.rand_bn_inference(net, 20, 16)
+    q, ev = bn.rand_bn_inference(net, 3, 5, seed=0)
+    assert len(q) == 3 and len(ev) == 5 and not set(q) & set(ev)
+    big = bn.rand_discrete_bn(100, 3, 4, seed=0)
+    lay = bn.flatten(big)
+    assert lay.n == 100 and lay.card.max() <= 4 and np.diff(lay.par_ptr).max() <= 3
+    assert (np.diff(lay.par_ptr)[1:] >= 1).all()  # connected=true: every node but the first has a parent
+
+
+def write_xdsl(path, golden):
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<smile version="1.0" id="Unnamed">\n <nodes>\n')
+        for c in golden["xdsl"]["cpts"]:
+            f.write(f'  <cpt id="{c["id"]}">\n')
+            for s in c["states"]:
+                f.write(f'   <state id="{s}" />\n')
+            if c["parents"]:
+                f.write(f'   <parents>{" ".join(c["parents"])}</parents>\n')
+            f.write(f'   <probabilities>{" ".join(repr(p) for p in c["probabilities"])}</probabilities>\n  </cpt>\n')
+        f.write(" </nodes>\n</smile>\n")
+
+
+def test_readxdsl_and_text_io(bn, golden, tmp_path):
+    """test/test_io.jl:7-55."""
+    path = str(tmp_path / "sample_bn.xdsl")
+    write_xdsl(path, golden)
+    net = bn.readxdsl(path)
+    assert sorted(net.names()) == ["Forecast", "Success"]
+    assert net.parents("Success") == [] and net.parents("Forecast") == ["Success"]
+    for s, f, p in golden["xdsl"]["joint_1based"]:
+        assert net.pdf(Success=s, Forecast=f) == pytest.approx(p, rel=1e-14)
+    with pytest.raises(ValueError):
+        bn.readxdsl(str(tmp_path / "x.txt"))
+    net.push(bn.DiscreteCPD("Test", ["Forecast"], [3], [[1.0, 0.0], [0.0, 1.0], [0.1234569, 1 - 0.1234569]]))
+    buf = io.StringIO()
+    bn.write_text(buf, net)
+    lines = buf.getvalue().splitlines()
+    assert [l.strip() for l in lines] == golden["text_io"]["lines"]
+    net2 = bn.read_text(io.StringIO(buf.getvalue()))
+    for s in (1, 2):
+        for f in (1, 2, 3):
+            for t in (1, 2):
+                assert net2.pdf(Success=s, Forecast=f, Test=t) == pytest.approx(net.pdf(Success=s, Forecast=f, Test=t))
+
+
+def test_xdsl_reverses_parent_order(bn, tmp_path):
+    """src/DiscreteBayesNet/io.jl:67: SMILE varies the FIRST listed parent slowest."""
+    p = tmp_path / "two.xdsl"
+    p.write_text("""<smile><nodes>
+      <cpt id="A"><state id="1"/><state id="2"/><probabilities>0.3 0.7</probabilities></cpt>
+      <cpt id="B"><state id="1"/><state id="2"/><state id="3"/><probabilities>0.2 0.3 0.5</probabilities></cpt>
+      <cpt id="C"><state id="1"/><state id="2"/><parents>A B</parents>
+        <probabilities>0.1 0.9 0.2 0.8 0.3 0.7 0.4 0.6 0.5 0.5 0.6 0.4</probabilities></cpt>
+    </nodes></smile>""")
+    net = bn.readxdsl(str(p))
+    assert net.parents("C") == ["B", "A"]
+    # SMILE order: (A=1,B=1),(A=1,B=2),(A=1,B=3),(A=2,B=1)...
+    assert net.get("C")({"A": 1, "B": 3})[0] == 0.3
+    assert net.get("C")({"A": 2, "B": 1})[0] == 0.4
+
+
+def test_gibbs_sample_argument_validation(bn):
+    """test/test_gibbs.jl:123-231 -- every check happens before the device is touched."""
+    net = make_mirror_net(bn, [["a", [], [[1.0, 0.0]]], ["b", [], [[0.0, 1.0]]],
+                               ["c", ["a", "b"], [[0.1, 0.9], [0.2, 0.8], [1.0, 0.0], [0.4, 0.6]]]])
+    kw = dict(thinning=5)
+    for bad in [dict(nsamples=0, burn_in=100), dict(nsamples=-1, burn_in=100), dict(nsamples=5, burn_in=-1)]:
+        with pytest.raises(ValueError):
+            bn.gibbs_sample(net, bad["nsamples"], bad["burn_in"], **kw)
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, thinning=-1)
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, variable_order=["a", "b"])
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, variable_order=["a", "b", "c", "d"])
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, time_limit=0)
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, initial_sample={"a": 1, "b": 2})
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, consistent_with={"c": 1}, initial_sample={"a": 1, "b": 2, "c": 2})
+    with pytest.raises(ValueError):
+        bn.gibbs_sample(net, 5, 100, initial_sample={"a": 2, "b": 2, "c": 1})  # pdf == 0
+    with pytest.raises(ValueError):
+        bn.infer(bn.GibbsSamplingNodewise(nsamples=100, burn_in=100), net, "a")
+
+
+def test_shard_ranges_tile_exactly():
+    from bayesnets_jl_b200.distributed import shard_range
+    for n in [0, 1, 7, 10**11, 65536]:
+        for world in [1, 2, 3, 4, 8]:
+            nxt = 0
+            for r in range(world):
+                lo, cnt = shard_range(n, r, world)
+                assert lo == nxt and cnt >= 0
+                nxt = lo + cnt
+            assert nxt == n
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_layout_feeds_oracle_identically(bn, golden, oracle):
+    """The oracle consumes the very arrays that are uploaded to the device."""
+    from oracle.factors_np import exact_infer
+    net = make_mirror_net(bn, golden["asia"]["nodes"])
+    on = oracle_net_from_layout(bn.flatten(net))
+    np.testing.assert_allclose(exact_infer(on, "B", {"D": 1}).potential, [0.285265293007839, 0.714734706992161],
+                               rtol=1e-12)

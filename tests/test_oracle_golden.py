@@ -1,0 +1,291 @@
+"""Pin the CPU oracle against the reference's own golden vectors -- runs without a GPU.
+
+Every expected value here comes from tests/golden/reference_vectors.json, which make_golden.py extracted from
+the reference's test files (file:line in the JSON), or is a closed form derived from CPTs cited there.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import capi
+from oracle.factors_np import (DimensionMismatch, NpFactor, brute_force_posterior, cpd_factor, exact_infer,
+                               make_net)
+
+
+def net_from(nodes):
+    return make_net([(n, p, r) for n, p, r in nodes])
+
+
+# ------------------------------------------------------------------------------------- Philox
+def test_philox_known_answers(golden):
+    for v in golden["philox4x32_10_kat"]["vectors"]:
+        out = capi.philox4x32_10(v["ctr"], v["key"])
+        assert [int(x) for x in out] == v["out"]
+
+
+# ------------------------------------------------------------------------------------- Factors
+def test_factor_product_golden_324(golden):
+    """test/test_factors.jl:162-199 -- exact equality, both oracle implementations."""
+    g = golden["factor_product"]
+    a = np.arange(1.0, 109.0).reshape(g["phi1"]["card"], order="F")
+    b = np.arange(1.0, 13.0).reshape(g["phi2"]["card"], order="F")
+    f = NpFactor(g["phi1"]["dims"], a) * NpFactor(g["phi2"]["dims"], b)
+    assert f.dimensions == ["X", "C", "Y", "A", "Z", "B"]
+    assert f.potential.ravel(order="F").tolist() == g["true_pot"]
+    ids = {n: i for i, n in enumerate("XCYAZB")}
+    d, o = capi.factor_product([ids[x] for x in g["phi1"]["dims"]], a, [ids[x] for x in g["phi2"]["dims"]], b)
+    assert d == [ids[x] for x in "XCYAZB"]
+    assert o.ravel(order="F").tolist() == g["true_pot"]
+    # operand order does not matter: the larger factor always leads (factors_dims.jl:189-191)
+    d2, o2 = capi.factor_product([ids[x] for x in g["phi2"]["dims"]], b, [ids[x] for x in g["phi1"]["dims"]], a)
+    assert d2 == d and np.array_equal(o2, o)
+
+
+def test_factor_product_dimension_mismatch(golden):
+    g = golden["factor_product_mismatch"]
+    f1 = NpFactor(g["phi1"]["dims"], np.zeros(g["phi1"]["card"]))
+    f2 = NpFactor(g["phi2"]["dims"], np.zeros(g["phi2"]["card"]))
+    with pytest.raises(DimensionMismatch):
+        f1 * f2
+    with pytest.raises(ValueError):
+        capi.factor_product([0, 1, 2], f1.potential, [3, 0, 1], f2.potential)
+
+
+def test_reducedim_golden(golden):
+    """test/test_factors.jl:111-130: broadcast(*, phi, :Z, [1,10]) then sum!(phi, [:Y,:Z]) == [123,165,237]."""
+    g = golden["reducedim"]
+    pot = np.array(g["potential"], np.float64).reshape(g["card"], order="F")
+    phi = NpFactor(g["dims"], pot) * NpFactor(["Z"], np.array(g["broadcast_mul_Z"]))
+    assert phi.dimensions == g["dims"]
+    s = phi.sum(g["sum_over"])
+    assert s.dimensions == ["X"] and s.potential.tolist() == g["expected"]
+    d, o = capi.factor_sum([0, 1, 2], phi.potential, [1, 2])
+    assert d == [0] and o.tolist() == g["expected"]
+    z = (NpFactor(g["dims"], pot) * NpFactor(["Z"], np.zeros(2))).sum(g["dims"])
+    assert z.potential.shape == () and float(z.potential) == 0.0  # zero-dim result, :121
+    d, o = capi.factor_sum([0, 1, 2], np.zeros(g["card"]), [0, 1, 2])
+    assert d == [] and o.shape == () and float(o) == 0.0
+    with pytest.raises(ValueError):  # :116,:132
+        NpFactor(g["dims"], pot).sum(["Y", "K", "Z", "waldo"])
+    with pytest.raises(ValueError):
+        capi.factor_sum([0, 1, 2], pot, [1, 7])
+
+
+def test_normalize_golden(golden):
+    """test/test_factors.jl:71-81 (p=2 divides by sum(abs2), no sqrt)."""
+    g = golden["normalize"]
+    pot = np.array(g["potential_colmajor"], np.float64).reshape(g["card"], order="F")
+    f = NpFactor(["a", "b"], pot)
+    np.testing.assert_allclose(f.normalize(1).potential.ravel(order="F"), g["p1"], rtol=1e-15)
+    np.testing.assert_allclose(f.normalize(2).potential.ravel(order="F"), g["p2"], rtol=1e-15)
+    np.testing.assert_allclose(capi.factor_normalize(pot, 1).ravel(order="F"), g["p1"], rtol=1e-15)
+    np.testing.assert_allclose(capi.factor_normalize(pot, 2).ravel(order="F"), g["p2"], rtol=1e-15)
+    with pytest.raises(ValueError):
+        capi.factor_normalize(pot, 3)
+    assert np.array_equal(f.potential, pot)  # normalize() leaves phi alone, :75
+
+
+def test_getindex_golden(golden):
+    g = golden["getindex"]
+    pot = np.array(g["potential"], np.float64).reshape(g["card"], order="F")
+    a = {k: v - 1 for k, v in g["assignment_1based"].items()}
+    s = NpFactor(g["dims"], pot).slice(a)
+    assert s.dimensions == ["X"] and s.potential.tolist() == g["expected"]
+    with pytest.raises(IndexError):
+        NpFactor(g["dims"], pot).slice({"Y": 15})
+    with pytest.raises(TypeError):
+        NpFactor(g["dims"], pot).slice({"Y": "waldo"})
+
+
+def test_factor_constructor_errors():
+    """test/test_factors.jl:6-8."""
+    with pytest.raises(ValueError):
+        NpFactor(["X", "X"], np.zeros((2, 3)))
+    with pytest.raises(ValueError):
+        NpFactor(["A", "X"], np.zeros(3))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_c_and_numpy_factor_ops_agree(seed):
+    """Two independent restatements (C odometer vs numpy broadcasting) must agree bit for bit."""
+    rng = np.random.default_rng(seed)
+    nvars = 7
+    cards = rng.integers(1, 5, nvars)
+    d1 = list(rng.permutation(nvars)[:rng.integers(0, 6)])
+    d2 = list(rng.permutation(nvars)[:rng.integers(0, 6)])
+    a = rng.random([cards[i] for i in d1])
+    b = rng.random([cards[i] for i in d2])
+    f = NpFactor(d1, a) * NpFactor(d2, b)
+    d, o = capi.factor_product(d1, a, d2, b)
+    assert d == [int(x) for x in f.dimensions]
+    assert np.array_equal(o, f.potential)
+    if d:
+        k = int(rng.integers(1, len(d) + 1))
+        sd = [int(x) for x in rng.permutation(d)[:k]]
+        s = f.sum(sd)
+        ds, os_ = capi.factor_sum(d, o, sd)
+        assert ds == [int(x) for x in s.dimensions]
+        assert np.array_equal(os_, s.potential)
+
+
+# ------------------------------------------------------------------------------------- ExactInference
+def test_cpd_to_factor_layout(golden):
+    """convert(Factor, cpd): dims [node, parents...], first parent fastest (factors_main.jl:62-68; the reference
+    checks it against table() to 1e-13, test_factors.jl:44-51 -- here against pdf by enumeration)."""
+    net = net_from(golden["inference_student"]["nodes"])
+    g = cpd_factor(net, net.index["G"])
+    assert g.dimensions == ["G", "D", "I"] and g.size == (3, 2, 2)
+    rows = golden["inference_student"]["nodes"][2][2]
+    for d, i in itertools.product(range(2), range(2)):
+        assert g.potential[:, d, i].tolist() == rows[d + 2 * i]
+
+
+def test_exact_inference_reference_posteriors(golden):
+    """test/test_inference.jl:36-110 for ExactInference (exact values; the atol there is for the samplers)."""
+    g = golden["inference_acb"]
+    net = net_from(g["nodes"])
+    np.testing.assert_allclose(exact_infer(net, "a").potential, g["P_a"], atol=1e-15)
+    np.testing.assert_allclose(exact_infer(net, "c").potential, g["P_c"], atol=1e-15)
+    bc = exact_infer(net, ["b", "c"])
+    np.testing.assert_allclose(bc.permuted_to(["b", "c"]).ravel(order="F"), g["P_bc_colmajor"], atol=1e-15)
+    s = golden["inference_student"]
+    net = net_from(s["nodes"])
+    np.testing.assert_allclose(exact_infer(net, "D").potential, s["P_D"], rtol=1e-14)
+    np.testing.assert_allclose(exact_infer(net, "G", {"D": 0, "I": 0}).potential, s["P_G_given_d1_i1"], rtol=1e-14)
+    with pytest.raises(ValueError):
+        exact_infer(net, ["D", "waldo"])
+    with pytest.raises(ValueError):
+        exact_infer(net, "D", {"D": 1})
+
+
+def xdsl_net(golden):
+    cpts = golden["xdsl"]["cpts"]
+    nodes = []
+    for c in cpts:
+        k = len(c["states"])
+        p = c["probabilities"]
+        nodes.append([c["id"], c["parents"][::-1], [p[i:i + k] for i in range(0, len(p), k)]])
+    return net_from(nodes)
+
+
+def test_xdsl_joint_and_posteriors(golden):
+    """test/test_io.jl:13-18 joint pdfs; derived P(Success | Forecast) closed forms."""
+    net = xdsl_net(golden)
+    for s, f, p in golden["xdsl"]["joint_1based"]:
+        joint = brute_force_posterior(net, ["Success", "Forecast"])
+        assert joint[s - 1, f - 1] == pytest.approx(p, rel=1e-14)
+    np.testing.assert_allclose(exact_infer(net, "Forecast").potential, [0.16, 0.32, 0.52], rtol=1e-14)
+    np.testing.assert_allclose(exact_infer(net, "Success", {"Forecast": 0}).potential, [0.5, 0.5], rtol=1e-14)
+    np.testing.assert_allclose(exact_infer(net, "Success", {"Forecast": 1}).potential, [0.25, 0.75], rtol=1e-14)
+    np.testing.assert_allclose(exact_infer(net, "Success", {"Forecast": 2}).potential, [1 / 13, 12 / 13], rtol=1e-14)
+
+
+def test_exact_matches_enumeration_on_asia_and_student(golden):
+    asia = net_from(golden["asia"]["nodes"])
+    np.testing.assert_allclose(exact_infer(asia, "T", {"X": 1}).potential, [0.907589116841376, 0.092410883158624], rtol=1e-12)
+    np.testing.assert_allclose(exact_infer(asia, "L", {"D": 1, "S": 1}).potential, [0.856116995114274, 0.143883004885726], rtol=1e-12)
+    np.testing.assert_allclose(exact_infer(asia, "B", {"D": 1}).potential, [0.285265293007839, 0.714734706992161], rtol=1e-12)
+    for q, ev in [(["T", "L"], {"D": 1}), (["A", "B", "X"], {}), (["S"], {"X": 0, "D": 1})]:
+        ve = exact_infer(asia, q, ev)
+        np.testing.assert_allclose(ve.permuted_to(q), brute_force_posterior(asia, q, ev), rtol=1e-12)
+    st = net_from(golden["inference_student"]["nodes"])
+    np.testing.assert_allclose(exact_infer(st, "G").potential, [0.447, 0.2714, 0.2816], rtol=1e-12)
+    np.testing.assert_allclose(exact_infer(st, "I", {"L": 0, "S": 1}).potential,
+                               [0.075174112754398, 0.924825887245602], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------- samplers
+@pytest.mark.parametrize("mode", [capi.REFERENCE_SCAN, capi.DEVICE_SPEC])
+def test_lw_oracle_reference_posteriors(golden, mode):
+    """test/test_inference.jl:45-110 for LikelihoodWeightingInference, at the reference's tolerances but with
+    far more particles than its default 500, plus a 4-sigma bound against ExactInference."""
+    g = golden["inference_acb"]
+    net = net_from(g["nodes"])
+    c, sw, sw2 = capi.lw_infer(net, None, [0], 20000, seed=1, mode=mode)
+    np.testing.assert_allclose(c / c.sum(), g["P_a"], atol=g["atol"])
+    c, _, _ = capi.lw_infer(net, None, [1, 2], 20000, seed=2, mode=mode)
+    np.testing.assert_allclose((c / c.sum()).ravel(order="F"), g["P_bc_colmajor"], atol=g["atol"])
+    s = golden["inference_student"]
+    net = net_from(s["nodes"])
+    ev = np.array([0, 0, -1, -1, -1], np.int8)
+    c, sw, sw2 = capi.lw_infer(net, ev, [2], 200000, seed=3, mode=mode)
+    p = c / c.sum()
+    n_eff = sw * sw / sw2
+    exact = np.array(s["P_G_given_d1_i1"])
+    assert np.all(np.abs(p - exact) < 4 * np.sqrt(exact * (1 - exact) / n_eff))
+    # evidence below the query: weights matter
+    ev = np.array([-1, -1, -1, 0, 1], np.int8)
+    c, sw, sw2 = capi.lw_infer(net, ev, [1], 400000, seed=4, mode=mode)
+    p = c / c.sum()
+    exact = np.array([0.075174112754398, 0.924825887245602])
+    n_eff = sw * sw / sw2
+    assert np.all(np.abs(p - exact) < 4 * np.sqrt(exact * (1 - exact) / n_eff))
+
+
+def test_device_spec_tracks_reference_scan(golden):
+    """Quantising the CDF to 31 bits changes a draw only when u falls within 2^-32 of a CDF step."""
+    net = net_from(golden["asia"]["nodes"])
+    a, _, _ = capi.sample(net, 200000, kind=capi.ANCESTRAL, seed=9, mode=capi.REFERENCE_SCAN)
+    b, _, _ = capi.sample(net, 200000, kind=capi.ANCESTRAL, seed=9, mode=capi.DEVICE_SPEC)
+    assert (a != b).any(axis=0).mean() < 1e-5
+
+
+def test_samplers_on_deterministic_net(golden):
+    """test/test_sampling.jl:9-20 and test/test_gibbs.jl:100-121 (A -> C <- B with deterministic roots)."""
+    net = net_from(golden["inference_acb"]["nodes"])
+    st, w, ok = capi.sample(net, 64, kind=capi.ANCESTRAL, seed=5)
+    assert (st[0] == 0).all() and (st[1] == 1).all() and (st[2] == 0).all()  # a=1, b=2, c=1 in 1-based terms
+    ev = np.array([-1, -1, 0], np.int8)
+    st, w, ok = capi.sample(net, 64, evidence=ev, kind=capi.REJECTION, seed=6)
+    assert ok.all() and (st[2] == 0).all()
+    ev_bad = np.array([1, -1, -1], np.int8)  # a=2 has probability 0 -> never accepted
+    st, w, ok = capi.sample(net, 8, evidence=ev_bad, kind=capi.REJECTION, seed=7, max_attempts=20)
+    assert not ok.any()
+    st, w, ok = capi.sample(net, 64, evidence=ev, kind=capi.WEIGHTED, seed=8)
+    assert (st[2] == 0).all() and np.allclose(w, 1.0)  # P(c=1 | a=1, b=2) = 1
+    out = capi.gibbs_sample(net, np.array([-1, -1, -1], np.int8), 3, 5, 100, thinning=5, seed=1)
+    assert out.shape == (3, 15)
+    assert (out[0] == 0).all() and (out[1] == 1).all() and (out[2] == 0).all()
+    out = capi.gibbs_sample(net, ev, 2, 5, 100, thinning=5, seed=2, log_domain=True)
+    assert (out[0] == 0).all() and (out[1] == 1).all() and (out[2] == 0).all()
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_gibbs_oracle_reference_posteriors(golden, full):
+    """test/test_inference.jl:45-110 for GibbsSamplingNodewise / GibbsSamplingFull."""
+    g = golden["inference_acb"]
+    net = net_from(g["nodes"])
+    c, _ = capi.gibbs_infer(net, None, [0], 64, 2000, 500, 3, full=full, seed=1)
+    np.testing.assert_allclose(c / c.sum(), g["P_a"], atol=g["atol"])
+    c, _ = capi.gibbs_infer(net, None, [1, 2], 64, 2000, 500, 3, full=full, seed=2)
+    np.testing.assert_allclose((c / c.sum()).ravel(order="F"), g["P_bc_colmajor"], atol=g["atol"])
+    s = golden["inference_student"]
+    net = net_from(s["nodes"])
+    c, _ = capi.gibbs_infer(net, None, [0], 256, 2000, 500, 3, full=full, seed=3)
+    np.testing.assert_allclose(c / c.sum(), s["P_D"], atol=0.02)
+    ev = np.array([0, 0, -1, -1, -1], np.int8)
+    c, _, pcc = capi.gibbs_infer(net, ev, [2], 256, 2000, 500, 3, full=full, seed=4, per_chain=True)
+    np.testing.assert_allclose(c / c.sum(), s["P_G_given_d1_i1"], atol=0.02)
+    assert np.array_equal(pcc.sum(axis=0), c.ravel(order="F"))
+    kept = -(-(2000 - 500) // 3)
+    assert c.sum() == 256 * kept  # ceil((nsamples-burn_in)/thin) samples per chain, gibbs.jl:74
+    with pytest.raises(ValueError):
+        capi.gibbs_infer(net, None, [0], 1, 100, 100, 3)  # burn_in < nsamples, gibbs.jl:70-71
+
+
+def test_gibbs_state_resume(golden):
+    """im.state carries the chain across calls (gibbs.jl:64,83-88): 2 x 1000 iterations == the states reached
+    by seeding the second call with the first call's final states."""
+    net = net_from(golden["asia"]["nodes"])
+    c1, st1 = capi.gibbs_infer(net, None, [2], 8, 1000, 0, 1, seed=11)
+    assert st1.shape == (8, 7)
+    c2, st2 = capi.gibbs_infer(net, None, [2], 8, 1000, 0, 1, seed=12, state=st1)
+    assert c2.sum() == 8 * 1000 and st2.shape == st1.shape
+
+
+def test_sweep_permutation_is_permutation():
+    for m in [0, 1, 2, 7, 180]:
+        p = capi.sweep_permutation(3, 5, m)
+        assert sorted(p.tolist()) == list(range(m))
+    assert not np.array_equal(capi.sweep_permutation(3, 5, 50), capi.sweep_permutation(3, 6, 50))
