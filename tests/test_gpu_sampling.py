@@ -1,0 +1,189 @@
+"""GPU parity: likelihood weighting and the table samplers through the C ABI.
+
+Two bars (north_star):
+  * vs the oracle's DEVICE_SPEC mode on the same seeds: per-particle states and weights are bit-identical, so
+    unweighted counts match exactly and weighted sums to 1e-12 (fp64 addition order differs);
+  * vs ExactInference: every posterior cell within 4 sigma, sigma^2 = p(1-p)/N_eff, N_eff = (sum w)^2/sum w^2.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import make_mirror_net, oracle_net_from_layout
+from oracle import capi
+from oracle.factors_np import exact_infer
+
+pytestmark = pytest.mark.gpu
+
+
+def lw_raw(bn, net, query, evidence, n, seed=0, first=0):
+    im = bn.LikelihoodWeightingInference(nsamples=n, seed=seed, first_particle=first)
+    inf = bn.InferenceState(net, query, evidence)
+    counts = im.raw_counts(inf)
+    return counts, im.last_stats
+
+
+def random_case(bn, n_nodes, seed, n_ev, n_q=2):
+    net = bn.rand_discrete_bn(n_nodes, 3, 4, seed=seed)
+    lay = bn.flatten(net)
+    rng = np.random.default_rng(1000 + seed)
+    while True:
+        picks = [str(x) for x in rng.choice(lay.names, size=n_q + n_ev, replace=False)]
+        query, evn = picks[:n_q], picks[n_q:]
+        evidence = {e: int(rng.integers(1, net.ncategories(e) + 1)) for e in evn}
+        on = oracle_net_from_layout(lay)
+        c, sw, _ = capi.lw_infer(on, lay.evidence_vector(evidence), lay.query_indices(query), 2000, seed=1)
+        if sw > 0:  # reject evidence with P(e) = 0
+            return net, lay, on, query, evidence
+
+
+@pytest.mark.parametrize("seed,n_nodes,n_ev", [(0, 100, 10), (1, 100, 10), (2, 37, 5), (3, 200, 20), (4, 8, 0), (5, 12, 11)])
+def test_lw_matches_oracle_device_spec(bn, seed, n_nodes, n_ev):
+    n_q = 1 if n_nodes - n_ev < 2 else 2
+    net, lay, on, query, evidence = random_case(bn, n_nodes, seed, n_ev, n_q)
+    n = 200_000
+    counts, (sw, sw2) = lw_raw(bn, net, query, evidence, n, seed=seed)
+    oc, osw, osw2 = capi.lw_infer(on, lay.evidence_vector(evidence), lay.query_indices(query), n, seed=seed,
+                                  mode=capi.DEVICE_SPEC)
+    np.testing.assert_allclose(counts, oc.ravel(order="F"), rtol=1e-12, atol=0)
+    assert sw == pytest.approx(osw, rel=1e-12) and sw2 == pytest.approx(osw2, rel=1e-12)
+    if not evidence:  # all weights are 1: counts are integers and must match exactly
+        assert np.array_equal(counts, oc.ravel(order="F")) and sw == n
+
+
+def test_lw_shards_reproduce_single_stream(bn):
+    """Particle ids are global Philox counters: 3 ragged shards == one call."""
+    net, lay, on, query, evidence = random_case(bn, 100, 0, 10)
+    n = 300_001
+    whole, (sw, _) = lw_raw(bn, net, query, evidence, n, seed=5)
+    parts = np.zeros_like(whole)
+    psw = 0.0
+    for first, cnt in [(0, 100_000), (100_000, 7), (100_007, n - 100_007)]:
+        c, (s, _) = lw_raw(bn, net, query, evidence, cnt, seed=5, first=first)
+        parts += c
+        psw += s
+    np.testing.assert_allclose(parts, whole, rtol=1e-12)
+    assert psw == pytest.approx(sw, rel=1e-12)
+    empty, (s0, _) = lw_raw(bn, net, query, evidence, 0, seed=5)
+    assert not empty.any() and s0 == 0.0
+
+
+def test_lw_posterior_within_4_sigma_of_exact(bn):
+    """C2-shaped case: 100 nodes, 10 evidence, 2 query; 2e7 particles; ExactInference (oracle VE) as truth."""
+    net, lay, on, query, evidence = random_case(bn, 100, 0, 10)
+    n = 20_000_000
+    counts, (sw, sw2) = lw_raw(bn, net, query, evidence, n, seed=0)
+    p = counts / counts.sum()
+    n_eff = sw * sw / sw2
+    ev0 = {k: v - 1 for k, v in evidence.items()}
+    exact = exact_infer(on, query, ev0).permuted_to(query).ravel(order="F")
+    sigma = np.sqrt(np.maximum(exact * (1 - exact), 1e-12) / n_eff)
+    assert n_eff > 1000
+    assert np.all(np.abs(p - exact) < 4 * sigma), (p, exact, sigma, n_eff)
+    # and through the public API
+    phi = bn.infer(bn.LikelihoodWeightingInference(nsamples=n, seed=0), net, query, evidence=evidence)
+    assert phi.dimensions == query
+    np.testing.assert_allclose(phi.potential.ravel(order="F"), p, rtol=1e-12)
+
+
+def test_lw_reference_suite(bn, golden):
+    """test/test_inference.jl:45-110 for LikelihoodWeightingInference (default 500 samples, reference atol)."""
+    g = golden["inference_acb"]
+    net = make_mirror_net(bn, g["nodes"])
+    phi = bn.infer(bn.LikelihoodWeightingInference(), net, "a")
+    assert len(phi) == 2
+    assert float(phi[{"a": 1}].potential) == pytest.approx(1.0, abs=g["atol"])
+    assert float(phi[{"a": 2}].potential) == pytest.approx(0.0, abs=g["atol"])
+    phi = bn.infer(bn.LikelihoodWeightingInference(), net, "c")
+    assert float(phi[{"c": 1}].potential) == pytest.approx(1.0, abs=g["atol"])
+    phi = bn.infer(bn.LikelihoodWeightingInference(), net, ["b", "c"])
+    assert phi.size() == (2, 2)
+    np.testing.assert_allclose(phi.potential.ravel(order="F"), g["P_bc_colmajor"], atol=g["atol"])
+    s = golden["inference_student"]
+    net = make_mirror_net(bn, s["nodes"])
+    phi = bn.infer(bn.LikelihoodWeightingInference(nsamples=20000, seed=3), net, "D")
+    np.testing.assert_allclose(phi.potential, s["P_D"], atol=s["atol"])
+    phi = bn.infer(bn.LikelihoodWeightingInference(nsamples=20000, seed=4), net, "G", evidence={"D": 1, "I": 1})
+    assert phi.size() == (3,)
+    np.testing.assert_allclose(phi.potential, s["P_G_given_d1_i1"], atol=s["atol"])
+    # impossible evidence: every weight is 0 -> 0/0 = NaN, as likelihood.jl:56 does
+    acb = make_mirror_net(bn, g["nodes"])
+    phi = bn.infer(bn.LikelihoodWeightingInference(100), acb, "c", evidence={"a": 2})
+    assert np.isnan(phi.potential).all()
+
+
+def test_xdsl_config_c1(bn, golden, tmp_path):
+    """BASELINE config C1: sample_bn.xdsl, LW 100k samples, 1 evidence var, vs ExactInference."""
+    from test_host import write_xdsl
+    path = str(tmp_path / "sample_bn.xdsl")
+    write_xdsl(path, golden)
+    net = bn.readxdsl(path)
+    for f, exact in [(1, [0.5, 0.5]), (2, [0.25, 0.75]), (3, [1 / 13, 12 / 13])]:
+        im = bn.LikelihoodWeightingInference(nsamples=100_000, seed=f)
+        phi = bn.infer(im, net, "Success", evidence={"Forecast": f})
+        sw, sw2 = im.last_stats
+        ex = np.array(exact)
+        assert np.all(np.abs(phi.potential - ex) < 4 * np.sqrt(ex * (1 - ex) / (sw * sw / sw2)))
+        np.testing.assert_allclose(bn.infer(bn.ExactInference(), net, "Success", evidence={"Forecast": f}).potential,
+                                   ex, rtol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["ancestral", "weighted", "rejection"])
+def test_sample_tables_match_oracle(bn, kind):
+    net, lay, on, query, evidence = random_case(bn, 40, 7, 2)
+    from bayesnets_jl_b200.sampling import _sample
+    n = 50_000
+    k = {"ancestral": 0, "rejection": 1, "weighted": 2}[kind]
+    _, st, w, ok = _sample(net, n, evidence, k, 100, 21, None)
+    ost, ow, ook = capi.sample(on, n, evidence=lay.evidence_vector(evidence), kind=k, seed=21, max_attempts=100)
+    assert np.array_equal(ok, ook)
+    assert np.array_equal(st, ost)
+    if kind == "weighted":
+        assert np.array_equal(w, ow)  # per-particle fp64 products are bit-identical
+    if kind == "rejection":
+        evv = lay.evidence_vector(evidence)
+        good = ok.astype(bool)
+        assert good.any()
+        for i in np.nonzero(evv >= 0)[0]:
+            assert (st[i, good] == evv[i]).all()
+        assert (st[:, ~good] == 0xFF).all()
+
+
+def test_rand_reference_suite(bn, golden):
+    """test/test_sampling.jl:1-27 on A -> C <- B."""
+    net = make_mirror_net(bn, golden["inference_acb"]["nodes"])
+    assert bn.rand(net) == {"a": 1, "b": 2, "c": 1}
+    t1 = bn.rand(net, 5)
+    assert t1.shape == (5, 3) and t1["a"].tolist() == [1] * 5 and t1["b"].tolist() == [2] * 5
+    t2 = bn.rand(net, 5, {"c": 1})
+    assert t2.shape == (5, 3) and t2["c"].tolist() == [1] * 5
+    t3 = bn.rand(net, 5, c=1, b=2)
+    assert t3.shape == (5, 3)
+    t4 = bn.rand(net, bn.LikelihoodWeightedSampler({"c": 1}), 5)
+    assert t4.shape == (5, 4) and t4["potential"].sum() == pytest.approx(1.0)
+    with pytest.raises(KeyError):
+        bn.rand(net, 3, {"a": 2})  # P(a=2) = 0: no consistent sample in 100 tries
+    a, w = bn.get_weighted_sample(net, {"c": 1})
+    assert a == {"a": 1, "b": 2, "c": 1} and w == 1.0
+
+
+def test_ancestral_marginals_and_ragged_sizes(bn):
+    net = bn.get_asia_bn()
+    for n in [1, 31, 1025]:
+        assert bn.rand(net, n, seed=n).shape == (n, 7)
+    df = bn.rand(net, 400_000, seed=2)
+    p_s = (df["S"] == 2).mean()
+    assert abs(p_s - 0.5) < 4 * np.sqrt(0.25 / 400_000)
+    p_l = (df["L"] == 2).mean()  # 0.5*0.01 + 0.5*0.1
+    assert abs(p_l - 0.055) < 4 * np.sqrt(0.055 * 0.945 / 400_000)
+
+
+def test_error_paths(bn):
+    net = bn.get_asia_bn()
+    with pytest.raises(ValueError):
+        bn.infer(bn.LikelihoodWeightingInference(10), net, "nope")
+    with pytest.raises(ValueError):
+        bn.infer(bn.LikelihoodWeightingInference(10), net, "T", evidence={"T": 1})
+    with pytest.raises(IndexError):
+        bn.infer(bn.LikelihoodWeightingInference(10), net, "T", evidence={"A": 3})
