@@ -85,6 +85,29 @@ struct DevBuf {
   }
 };
 
+// Stream-ordered pool allocation (cudaMallocAsync) for factor potentials: variable elimination allocates and
+// frees 2^20..2^27-entry intermediates back to back; the default mempool keeps them cached (release
+// threshold = max), so after warm-up an allocation is a pointer bump and frees never synchronise the device.
+void ensure_pool(int device);
+template <typename T>
+struct PoolBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  PoolBuf() = default;
+  PoolBuf(const PoolBuf&) = delete;
+  PoolBuf& operator=(const PoolBuf&) = delete;
+  ~PoolBuf() { release(); }
+  void release() {
+    if (p) cudaFreeAsync(p, tl_stream);
+    p = nullptr; n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), tl_stream);
+  }
+};
+
 // ---------------------------------------------------------------------------- objects behind handles
 struct Net {
   int device = 0;
@@ -107,7 +130,7 @@ struct Factor {
   int device = 0;
   std::vector<int32_t> dims, card;
   int64_t len = 1;
-  DevBuf<double> data;
+  PoolBuf<double> data;
 };
 
 Net* get_net(bn_net_t h);

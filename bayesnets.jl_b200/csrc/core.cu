@@ -31,6 +31,19 @@ const DevProps& dev_props(int device) {
   return g_props[device] = p;
 }
 
+void ensure_pool(int device) {
+  static std::mutex mu;
+  static std::unordered_map<int, bool> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[device] = true;
+}
+
 Net* get_net(bn_net_t h) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_nets.find(h);
@@ -65,6 +78,7 @@ int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>&
   f->len = 1;
   for (int32_t c : card) f->len *= c;
   cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) ensure_pool(device);
   if (e == cudaSuccess) e = f->data.alloc((size_t)f->len);
   if (e != cudaSuccess) {
     set_error("cudaMalloc of %lld doubles failed: %s", (long long)f->len, cudaGetErrorString(e));

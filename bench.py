@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on B200: likelihood-weighting samples/s (+ factor GB/s).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (CPU arm: the oracle restatement on host cores)
+
+Workload (config C2 of BASELINE.json): synthetic rand_discrete_bn(100, max_parents=3, max_states=4)
+net seed 0, 10 evidence nodes with P(e) > 0, 2 query nodes; one STEP = one LW inference pass of 1e9 particles
+PER GPU (weak scaling: N GPUs -> N x 1e9 particles, sharded by global particle id, one all-reduce of the
+weighted-count tensor).  `value` = whole-job particles/s with the network resident in HBM; `e2e` = the same
+through the public infer() call from host buffers (network upload + result download inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lw_samples_per_s"
+UNIT = "samples/s"
+
+
+# ------------------------------------------------------------------------------------------ workload
+def build_case(bn, n_nodes=100, net_seed=0, n_ev=10, n_q=2, check=None):
+    """The C2 case.  `check(query, evidence) -> bool` rejects evidence with P(e) = 0."""
+    net = bn.rand_discrete_bn(n_nodes, 3, 4, seed=net_seed)
+    lay = bn.flatten(net)
+    rng = np.random.default_rng(1000 + net_seed)
+    while True:
+        picks = [str(x) for x in rng.choice(lay.names, size=n_q + n_ev, replace=False)]
+        query, evn = picks[:n_q], picks[n_q:]
+        evidence = {e: int(rng.integers(1, net.ncategories(e) + 1)) for e in evn}
+        if check is None or check(net, lay, query, evidence):
+            return net, lay, query, evidence
+
+
+def algorithmic_bytes_per_particle(lay) -> float:
+    """LW particle = sum_i 8*card_i (the CPT row touched per node, fp64-equivalent)."""
+    return float(8 * int(lay.card.sum()))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_lw(lay, query, evidence, n, seed, threads=None):
+    """Oracle LW (reference restatement, likelihood.jl:34-54 loop) on host cores -> (seconds, threads)."""
+    from oracle import capi
+    from oracle.factors_np import FlatNet
+    capi.build()
+    if threads:
+        capi.set_num_threads(threads)
+    on = FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
+    evv, qi = lay.evidence_vector(evidence), lay.query_indices(query)
+    t0 = time.perf_counter()
+    c, sw, sw2 = capi.lw_infer(on, evv, qi, n, seed=seed, mode=capi.REFERENCE_SCAN)
+    return time.perf_counter() - t0, capi.num_threads(), c
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; Julia itself cannot run here) with all host
+    threads, same config/metric; each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import bayesnets_jl_b200 as bn
+    net, lay, query, evidence = build_case(bn)
+    dt, threads, _ = cpu_lw(lay, query, evidence, 200_000, 1)
+    per_step = int(max(200_000, min(5e7, 200_000 / dt * 4.0)))  # ~4 s of CPU work per step
+    for w in range(args.warmup):
+        cpu_lw(lay, query, evidence, per_step // 4, 100 + w)
+    t = 0.0
+    for k in range(args.steps):
+        dt, threads, _ = cpu_lw(lay, query, evidence, per_step, 200 + k)
+        t += dt
+    value = per_step * args.steps / t
+    sample = f"{per_step} particles/step x {args.steps} steps of the C2 workload (full workload: 1e9/step)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(lay, query, evidence, per_step, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = C/OpenMP restatement of src/Inference/likelihood.jl:34-54 (oracle/bn_oracle.c); the "
+                "Julia package itself cannot run in this image (no julia, deps un-vendored)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(lay, query, evidence, per_gpu, n_gpus):
+    return {
+        "workload": "C2: LW infer on rand_discrete_bn(100,3,4) net_seed=0, 10 evidence, 2 query",
+        "n_nodes": int(lay.n), "cpt_entries": int(lay.cpt.size), "n_evidence": len(evidence),
+        "query_cells": int(np.prod([lay.card[lay.index[q]] for q in query])),
+        "particles_per_step_per_gpu": int(per_gpu), "particles_per_step": int(per_gpu) * n_gpus,
+        "parallelism": f"particles sharded over {n_gpus} GPU(s) by global Philox counter + 1 all-reduce of counts",
+        "l2": "n/a - no HBM-resident operands (program+tables ~20 KB are TMA-staged to smem per launch); "
+              "fresh seed every step, nothing cached",
+    }
+
+
+# ------------------------------------------------------------------------------------------ factor sweep
+def factor_sweep(bn, torch, device, k=24, iters=5):
+    """Factor `*` / sum / normalize / fused eliminate GB/s at 2^k entries (C5 shapes), L2 flushed
+    between iterations, CUDA events on the launching stream."""
+    from bayesnets_jl_b200 import _lib
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    names = [f"w{i}" for i in range(k + 2)]
+    hbm, src = peaks()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{device}")
+
+    def mk(dims):
+        n = 1 << len(dims)
+        return bn.Factor([names[i] for i in dims], rng.random(n).reshape((2,) * len(dims), order="F"))
+
+    def timed(fn):
+        best, tot = 1e9, 0.0
+        for it in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            del out
+            if it >= 2:
+                best = min(best, ms); tot += ms
+        return tot / iters, best
+
+    A = mk(list(range(k)))
+    cases = {}
+    B12 = mk(list(range(0, k, 2)))
+    cases["P1 2^%d x 2^12 interleaved" % k] = (lambda: A * B12, 8 * ((1 << k) + (1 << 12) + (1 << k)))
+    A23, B23 = mk(list(range(k - 1))), mk(list(range(1, k)))
+    cases["P2 dims1..k-1 x dims2..k"] = (lambda: A23 * B23, 8 * (2 * (1 << (k - 1)) + (1 << k)))
+    perm = list(rng.permutation(k))
+    Bp = mk(perm)
+    cases["P3 2^%d x 2^%d permuted" % (k, k)] = (lambda: A * Bp, 8 * 3 * (1 << k))
+    cases["S1 sum innermost"] = (lambda: A.sum(names[0]), 8 * ((1 << k) + (1 << (k - 1))))
+    cases["S2 sum outermost"] = (lambda: A.sum(names[k - 1]), 8 * ((1 << k) + (1 << (k - 1))))
+    cases["S3 sum middle"] = (lambda: A.sum(names[k // 2]), 8 * ((1 << k) + (1 << (k - 1))))
+    cases["S4 sum 4 dims"] = (lambda: A.sum([names[1], names[5], names[11], names[k - 2]]), 8 * ((1 << k) + (1 << (k - 4))))
+    cases["N1 normalize"] = (lambda: A.normalize_(), 8 * 3 * (1 << k))
+    E_b, E_c = mk([0] + list(range(k - 12, k - 1))), mk([0] + list(range(1, 12)))
+
+    def elim():
+        hs = (_lib.h64 * 3)(A.handle, E_b.handle, E_c.handle)
+        sd = np.array([bn.factors.var_id(names[0])], np.int32)
+        out = _lib.h64(0)
+        _lib.check(_lib.lib().bn_factor_eliminate(hs, C.c_int32(3), _lib.ptr(sd, _lib.i32p), C.c_int32(1), C.byref(out)))
+        return bn.Factor._from_handle(out)
+    cases["E1 fused eliminate 3 factors"] = (elim, 8 * ((1 << k) + 2 * (1 << 12) + (1 << (k - 1))))
+    res = []
+    _lib.set_stream(torch.cuda.current_stream(device).cuda_stream)
+    for name, (fn, nbytes) in cases.items():
+        avg, best = timed(fn)
+        res.append({"case": name, "bytes": nbytes, "ms": round(avg, 4), "GB/s": round(nbytes / avg / 1e6, 1),
+                    "frac": round(nbytes / avg / 1e6 / hbm, 3)})
+    return res
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import bayesnets_jl_b200 as bn
+    from bayesnets_jl_b200 import _lib
+    from bayesnets_jl_b200.distributed import ShardedLikelihoodWeighting, env_rank_world
+
+    rank, world, local = env_rank_world()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if args.gpus != world and rank == 0:
+        print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    bn.set_default_device(local)
+    per_gpu = int(args.samples)
+
+    def check(net, lay, query, evidence):  # P(e) > 0 via a short LW run on the device
+        im = bn.LikelihoodWeightingInference(nsamples=4096, seed=1, device=local)
+        im.raw_counts(bn.InferenceState(net, query, evidence))
+        return im.last_stats[0] > 0
+
+    net, lay, query, evidence = build_case(bn, check=check)
+    slw = ShardedLikelihoodWeighting(net, query, evidence, per_gpu * world, seed=0, device=local)
+    stream = torch.cuda.current_stream(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(max(args.warmup, 3)):
+        slw.seed = 1000 + w
+        slw.step()
+    barrier()
+    # ---- timed region: exactly K steps, events on the launching stream
+    launches0 = bn.launch_count()
+    kern_ev = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record(stream)
+        for k in range(args.steps):
+            slw.seed = k
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            slw.launch()
+            b.record(stream)
+            kern_ev.append((a, b))
+            if world > 1:
+                dist.all_reduce(slw.out)
+        e1.record(stream)
+        barrier()
+    launches = bn.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    posterior = slw.posterior()
+    n_eff = float(slw.out[slw.ncell] ** 2 / slw.out[slw.ncell + 1])
+
+    # ---- e2e through the public API with host buffers (network flattened + uploaded every step)
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = int(lay.card.nbytes + lay.par_ptr.nbytes + lay.par_idx.nbytes + lay.cpt_off.nbytes + lay.cpt.nbytes + 24 * 1024)
+    d2h = int((slw.ncell + 2) * 8 + slw.ncell * 8)
+    first, count = slw.first, slw.count
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        net._device_cache = None  # force flatten + bn_net_create (H2D) inside the timed region
+        im = bn.LikelihoodWeightingInference(nsamples=count, seed=500 + k, device=local, first_particle=first)
+        if world > 1:
+            c = torch.from_numpy(im.raw_counts(bn.InferenceState(net, query, evidence))).to(f"cuda:{local}")
+            dist.all_reduce(c)
+            c = c.cpu().numpy()
+        else:
+            phi = bn.infer(im, net, query, evidence=evidence)
+            c = phi.potential
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = per_gpu * world * e2e_steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, src = peaks()
+    bpp = algorithmic_bytes_per_particle(lay)
+    achieved = bpp * per_gpu / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": per_gpu * world * args.steps / (ms_total * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 thresholds / f64 weights",
+        "data": "synthetic", "config": workload_config(lay, query, evidence, per_gpu, world),
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "infer(LikelihoodWeightingInference(nsamples), bn, query; evidence)"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "bn::particle_kernel<MODE_INFER>", "bound": "hbm", "achieved": achieved, "peak": hbm,
+                     "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": f"of {src}",
+                     "algorithmic_bytes_per_particle": bpp, "kernel_ms": kern_ms,
+                     "note": "HBM-EQUIVALENT figure required by SURVEY.md 8(d): the CPT rows a particle touches, "
+                             "counted as fp64 bytes.  The tables are shared-memory resident, so this kernel is "
+                             "bounded by issue slots, not HBM, and frac > 1 is expected; see profiles/ for "
+                             "the ncu issue-slot utilisation."},
+        "posterior": [round(float(x), 6) for x in posterior.ravel(order="F")], "n_eff": n_eff,
+    }
+    if world == 1:
+        dt, threads, _ = cpu_lw(lay, query, evidence, 200_000, 1)
+        n_cpu = int(max(200_000, min(2e8, 200_000 / dt * 12.0)))  # ~12 s of CPU work
+        dt, threads, _ = cpu_lw(lay, query, evidence, n_cpu, 2)
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n_cpu} particles of the same net/evidence/query (full step: {per_gpu})"}
+        if not args.no_factors:
+            fr = factor_sweep(bn, torch, local, k=args.factor_log2)
+            line["factor_roofline"] = {"bound": "hbm", "peak": hbm, "peak_source": f"of {src}", "unit": "GB/s",
+                                       "log2_entries": args.factor_log2, "l2": "flushed (512 MiB memset) between iterations",
+                                       "cases": fr}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=float, default=1e9, help="particles per step per GPU")
+    ap.add_argument("--factor-log2", type=int, default=24)
+    ap.add_argument("--no-factors", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

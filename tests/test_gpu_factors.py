@@ -111,7 +111,7 @@ def test_getindex_golden(bn, golden):
     s = phi[g["assignment_1based"]]
     assert s.dimensions == ["X"] and s.potential.tolist() == g["expected"]
     full = phi[{"X": 2, "Y": 1, "Z": 2}]
-    assert full.potential.shape == () and float(full.potential) == 8.0
+    assert full.potential.shape == () and float(full.potential) == 6.0
 
 
 @pytest.mark.parametrize("seed", range(24))
