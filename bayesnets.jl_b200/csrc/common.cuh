@@ -140,6 +140,30 @@ Factor* take_factor(bn_factor_t h);  // removes the handle, caller deletes
 int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>& card, int device,
                    Factor** out);
 
+// ---------------------------------------------------------------------------- sampling program
+// Host-compiled form of (net, evidence) shared by the generic particle kernel (sampling.cu) and the
+// network-specialised one (specialize.cu).
+struct NodePlan {
+  bool is_evidence = false;
+  int card = 0;
+  uint32_t toff = 0;       // word offset of the node's table inside the table area
+  uint32_t row_words = 0;  // words per table row (thresholds padded; 2 for an fp64 evidence row)
+  std::vector<std::pair<int, uint32_t>> parents;  // FREE parents: (node, stride in rows)
+};
+struct SampleProgram {
+  std::vector<uint32_t> words;  // [prog | tables]
+  uint32_t prog_words = 0;      // multiple of 4
+  uint32_t table_words = 0;     // multiple of 4
+  uint32_t n_free = 0;
+  std::vector<NodePlan> plan;   // one per node, topological order
+};
+int32_t compile_program(const Net& net, const int8_t* evidence, bool treat_all_free, uint32_t state_stride,
+                        SampleProgram* out);
+// specialize.cu: returns BN_OK and sets *used when the NVRTC-specialised kernel handled the launch
+int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
+                              const std::vector<int64_t>& qstride, uint32_t ncell, uint64_t first, uint64_t n,
+                              uint64_t seed, double* out_dev, bool* used);
+
 // ---------------------------------------------------------------------------- Philox4x32-10
 // Salmon et al. SC'11.  key bumps are warp-uniform so only 2 IMAD.WIDE + 2 LOP3 per round are
 // per-thread work.  Counter layout is the library-wide spec (include/bn_cuda.h).

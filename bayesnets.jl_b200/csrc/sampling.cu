@@ -19,13 +19,6 @@ namespace bn {
 enum : uint32_t { K_FREE = 0, K_EVID = 1 };
 constexpr uint32_t THRESH_PAD = 0x80000000u;  // r31 < 2^31 always
 
-struct SampleProgram {
-  std::vector<uint32_t> words;  // [prog | pad to 16 B | tables]
-  uint32_t prog_words = 0;      // multiple of 4
-  uint32_t table_words = 0;     // multiple of 4
-  uint32_t n_free = 0;
-};
-
 static inline uint32_t row_words_free(int card) {
   if (card <= 1) return 1;
   if (card == 2) return 1;
@@ -35,11 +28,12 @@ static inline uint32_t row_words_free(int card) {
 
 // Build program + tables.  `treat_all_free`: ancestral / rejection sampling ignore the evidence while
 // sampling (src/sampling.jl:52-57,79-87).  state_stride = threads per CTA (row pitch of the u8 states).
-static int32_t compile_program(const Net& net, const int8_t* evidence, bool treat_all_free,
-                               uint32_t state_stride, SampleProgram* out) {
+int32_t compile_program(const Net& net, const int8_t* evidence, bool treat_all_free,
+                        uint32_t state_stride, SampleProgram* out) {
   const int n = net.n;
   std::vector<uint32_t> prog, tab;
   prog.reserve((size_t)n * 8);
+  out->plan.clear();
   uint32_t n_free = 0;
   for (int i = 0; i < n; ++i) {
     const bool is_ev = !treat_all_free && evidence && evidence[i] >= 0;
@@ -95,6 +89,13 @@ static int32_t compile_program(const Net& net, const int8_t* evidence, bool trea
       }
     }
     BN_REQUIRE(fp.size() < 65536, BN_UNSUPPORTED, "node %d has too many parents", i);
+    {
+      NodePlan np;
+      np.is_evidence = is_ev; np.card = card; np.toff = toff; np.row_words = rw;
+      int64_t fs = 1;
+      for (auto& pr : fp) { np.parents.emplace_back(pr.first, (uint32_t)fs); fs *= net.card[pr.first]; }
+      out->plan.push_back(std::move(np));
+    }
     prog.push_back((is_ev ? K_EVID : K_FREE) | ((uint32_t)card << 8) | ((uint32_t)fp.size() << 16));
     prog.push_back(toff);
     int64_t fstride = 1;
