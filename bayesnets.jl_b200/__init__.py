@@ -15,7 +15,7 @@ from .bayes_net import (Assignment, BayesNet, CategoricalCPD, DiscreteBayesNet, 
                         get_asia_bn, get_sat_fail_bn, get_sprinkler_bn, rand_bn_inference, rand_cpd,
                         rand_discrete_bn)
 from .device_layout import DeviceLayout, DeviceNet, device_net, flatten, set_default_device  # noqa: F401
-from .factors import Factor  # noqa: F401
+from .factors import Factor, eliminate  # noqa: F401
 from .inference import (ExactInference, GibbsSamplingFull, GibbsSamplingNodewise, InferenceMethod,  # noqa: F401
                         InferenceState, LikelihoodWeightingInference, infer)
 from .io import read_text, readxdsl, write_text  # noqa: F401

@@ -261,3 +261,18 @@ class Factor:
 
     def __repr__(self):
         return f"Factor(dims={self.dimensions}, size={self._shape})"
+
+
+def eliminate(factors: Sequence[Factor], dims) -> Factor:
+    """sum(reduce(*, factors), dims) in ONE kernel: the elimination step of src/Inference/exact.jl:27 without
+    materialising the product.  Values and dimension order equal the reference's left fold followed by sum."""
+    factors = list(factors)
+    if not factors:
+        raise ValueError("eliminate needs at least one factor")
+    ids = np.array([var_id(d) for d in _as_names(dims)], np.int32)
+    hs = (_lib.h64 * len(factors))(*[f.handle for f in factors])
+    out = _lib.h64(0)
+    dp = ids if ids.size else np.zeros(1, np.int32)
+    check(_lib.lib().bn_factor_eliminate(hs, C.c_int32(len(factors)), ptr(dp, _lib.i32p), C.c_int32(ids.size),
+                                         C.byref(out)))
+    return Factor._from_handle(out)

@@ -1,0 +1,302 @@
+# CUDABackend.jl -- `ccall` glue between BayesNets.jl and libbn_cuda.so (include/bn_cuda.h).
+#
+# Add to BayesNets.jl as src/Inference/CUDABackend/CUDABackend.jl and `include` it from src/BayesNets.jl
+# after src/Inference/*.jl and src/DiscreteBayesNet/device_layout.jl.  There is no CUDA.jl dependency and
+# no CPU fallback: every method below is one ccall; if the library cannot be loaded the call throws.
+# Julia is not available in the build image, so this file is reviewed, not executed; its executable twin
+# is bayesnets.jl_b200/{inference,sampling,factors}.py, which binds the same symbols through ctypes and is
+# what tests/ drives (INTEGRATION.md).
+#
+# Dispatch points used (the reference's own extension mechanism):
+#   infer(::InferenceMethod, ::InferenceState)      src/ProbabilisticGraphicalModels/inference.jl:48-49
+#   Base.:*, Base.sum, LinearAlgebra.normalize!     src/Factors/factors_dims.jl:269,100,45
+#   Random.rand(bn, ::BayesNetSampler, n)           src/sampling.jl:24-41
+
+const libbn_cuda = get(ENV, "BAYESNETS_LIBBN_CUDA", "libbn_cuda.so")
+
+const BN_OK = Int32(0)
+const BN_BAD_ARG = Int32(-1)
+const BN_DIM_MISMATCH = Int32(-2)
+const BN_NOT_IN_FACTOR = Int32(-3)
+const BN_ZERO_WEIGHT = Int32(-5)
+const BN_OOM = Int32(-6)
+const BN_BOUNDS = Int32(-8)
+
+_bn_msg() = unsafe_string(ccall((:bn_last_error, libbn_cuda), Cstring, ()))
+
+"Map bn_status to the exception the reference throws at the corresponding site (include/bn_cuda.h)."
+function _bn_check(rc::Int32)
+    rc == BN_OK && return nothing
+    msg = _bn_msg()
+    rc == BN_DIM_MISMATCH && throw(DimensionMismatch(msg))            # factors_dims.jl:197-199
+    (rc == BN_BAD_ARG || rc == BN_NOT_IN_FACTOR) && throw(ArgumentError(msg))  # inference.jl:10-11, errors.jl:12
+    rc == BN_BOUNDS && throw(BoundsError(msg))                         # factors_access.jl:59-61
+    rc == BN_OOM && throw(OutOfMemoryError())
+    error("libbn_cuda status $rc: $msg")
+end
+
+# one resident copy of the network per BayesNet object (WeakKeyDict so it dies with the net)
+const _device_nets = WeakKeyDict{Any,DeviceNet}()
+device_net(bn::DiscreteBayesNet; device::Integer=0) = get!(() -> DeviceNet(bn; device=device), _device_nets, bn)
+
+# ------------------------------------------------------------------------------------------------
+# Likelihood weighting                                     replaces src/Inference/likelihood.jl:16-58
+@with_kw struct CUDALikelihoodWeighting <: InferenceMethod
+    nsamples::Int = 500
+    seed::UInt64 = 0
+    device::Int = 0
+end
+
+function infer(im::CUDALikelihoodWeighting, inf::InferenceState{BN}) where {BN<:DiscreteBayesNet}
+    bn = inf.pgm
+    net = device_net(bn; device=im.device)
+    ev = evidence_vector(net.layout, bn, inf.evidence)
+    q = query_indices(bn, inf.query)
+    ϕ = Factor(inf.query, map(n -> ncategories(bn, n), inf.query))     # likelihood.jl:22
+    stats = zeros(Float64, 2)
+    GC.@preserve ev q ϕ stats begin
+        _bn_check(ccall((:bn_lw_infer, libbn_cuda), Int32,
+                        (UInt64, Ptr{Int8}, Ptr{Int32}, Int32, UInt64, UInt64, UInt64, Ptr{Float64}, Ptr{Float64}),
+                        net.handle, ev, q, length(q), 0, im.nsamples, im.seed, ϕ.potential, stats))
+    end
+    normalize!(ϕ)                                                       # likelihood.jl:56 (0/0 -> NaN as before)
+    return ϕ
+end
+
+# ------------------------------------------------------------------------------------------------
+# Gibbs inference                                   replaces src/Inference/gibbs.jl:66-145 / :161-234
+@with_kw mutable struct CUDAGibbsNodewise <: InferenceMethod
+    nsamples::Int = 2000
+    burn_in::Int = 500
+    thin::Int = 3
+    state::Assignment = Assignment()
+    n_chains::Int = 1          # 1 = the reference's single chain; >1 = independent chains, counts summed
+    seed::UInt64 = 0
+    device::Int = 0
+end
+@with_kw mutable struct CUDAGibbsFull <: InferenceMethod
+    nsamples::Int = 2000
+    burn_in::Int = 500
+    thin::Int = 3
+    state::Assignment = Assignment()
+    n_chains::Int = 1
+    seed::UInt64 = 0
+    device::Int = 0
+end
+_gibbs_mode(::CUDAGibbsNodewise) = Int32(0)
+_gibbs_mode(::CUDAGibbsFull) = Int32(1)
+
+function infer(im::Union{CUDAGibbsNodewise,CUDAGibbsFull}, inf::InferenceState{BN}) where {BN<:DiscreteBayesNet}
+    im.burn_in < im.nsamples || throw(ArgumentError("Burn in ($(im.burn_in)) " *
+                "must be less than number of samples ($(im.nsamples))"))    # gibbs.jl:70-71
+    bn = inf.pgm
+    net = device_net(bn; device=im.device)
+    lay = net.layout
+    ev = evidence_vector(lay, bn, inf.evidence)
+    q = query_indices(bn, inf.query)
+    ϕ = Factor(inf.query, map(n -> ncategories(bn, n), inf.query))
+    n = length(lay.names)
+    st = zeros(UInt8, n, im.n_chains)           # chain-major on the device = column per chain here
+    init = Int32(0)
+    if !isempty(im.state)                        # resume from im.state (gibbs.jl:83-88)
+        for c in 1:im.n_chains, (i, nm) in enumerate(lay.names)
+            st[i, c] = UInt8(get(inf.evidence, nm, im.state[nm]) - 1)
+        end
+        init = Int32(1)
+    end
+    GC.@preserve ev q ϕ st begin
+        _bn_check(ccall((:bn_gibbs_infer, libbn_cuda), Int32,
+                        (UInt64, Ptr{Int8}, Ptr{Int32}, Int32, UInt64, UInt64, Int64, Int64, Int64, Int32, UInt64,
+                         Ptr{UInt8}, Int32, Ptr{Float64}, Ptr{Float64}),
+                        net.handle, ev, q, length(q), 0, im.n_chains, im.nsamples, im.burn_in, im.thin,
+                        _gibbs_mode(im), im.seed, st, init, ϕ.potential, C_NULL))
+    end
+    for (i, nm) in enumerate(lay.names)          # im.state = x (gibbs.jl:141)
+        im.state[nm] = Int(st[i, 1]) + 1
+    end
+    normalize!(ϕ)
+    return ϕ
+end
+
+# ------------------------------------------------------------------------------------------------
+# Exact inference                                           replaces src/Inference/exact.jl:6-33
+@with_kw struct CUDAExact <: InferenceMethod
+    fused::Bool = true        # one product-and-sum kernel per eliminated variable (no materialised product)
+    device::Int = 0
+end
+
+function infer(im::CUDAExact, inf::InferenceState{BN}) where {BN<:DiscreteBayesNet}
+    bn = inf.pgm
+    net = device_net(bn; device=im.device)
+    ev = evidence_vector(net.layout, bn, inf.evidence)
+    q = query_indices(bn, inf.query)
+    isempty(q) && throw(ArgumentError("ExactInference needs at least one query variable"))
+    out = zeros(Float64, prod(ncategories(bn, n) for n in inf.query))
+    od = zeros(Int32, length(q)); oc = zeros(Int32, length(q))
+    GC.@preserve ev q out od oc begin
+        _bn_check(ccall((:bn_exact_infer, libbn_cuda), Int32,
+                        (UInt64, Ptr{Int8}, Ptr{Int32}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+                        net.handle, ev, q, length(q), im.fused, od, oc, out))
+    end
+    # the result's dimension order depends on the join order, exactly as in the reference (exact.jl:31)
+    return Factor(net.layout.names[od .+ 1], reshape(out, Int.(oc)...))
+end
+
+# ------------------------------------------------------------------------------------------------
+# Table samplers                                      replaces src/sampling.jl:24-41,52-57,72-93,153-174
+struct CUDADirectSampler <: BayesNetSampler
+    seed::UInt64
+end
+struct CUDARejectionSampler <: BayesNetSampler
+    evidence::Assignment
+    max_nsamples::Int
+    seed::UInt64
+end
+struct CUDALikelihoodWeightedSampler <: BayesNetSampler
+    evidence::Assignment
+    seed::UInt64
+end
+
+function _sample_table(bn::DiscreteBayesNet, ev::Vector{Int8}, kind::Integer, attempts::Integer, n::Integer, seed)
+    net = device_net(bn)
+    nn = length(net.layout.names)
+    states = Matrix{UInt8}(undef, n, nn)         # node-major on the device = one column per node
+    w = Vector{Float64}(undef, n); ok = Vector{UInt8}(undef, n)
+    GC.@preserve ev states w ok begin
+        _bn_check(ccall((:bn_sample, libbn_cuda), Int32,
+                        (UInt64, Ptr{Int8}, Int32, Int32, UInt64, UInt64, UInt64, Ptr{UInt8}, Ptr{Float64}, Ptr{UInt8}),
+                        net.handle, ev, kind, attempts, 0, n, seed, states, w, ok))
+    end
+    return states, w, ok
+end
+
+function Random.rand(bn::DiscreteBayesNet, s::CUDADirectSampler, nsamples::Integer)
+    states, _, _ = _sample_table(bn, fill(Int8(-1), length(bn)), 0, 1, nsamples, s.seed)
+    return DataFrame([name(cpd) => Int.(states[:, i]) .+ 1 for (i, cpd) in enumerate(bn.cpds)])
+end
+
+function Random.rand(bn::DiscreteBayesNet, s::CUDARejectionSampler, nsamples::Integer)
+    ev = evidence_vector(device_net(bn).layout, bn, s.evidence)
+    states, _, ok = _sample_table(bn, ev, 1, s.max_nsamples, nsamples, s.seed)
+    all(!iszero, ok) || throw(KeyError(name(first(bn.cpds))))   # the reference's empty!(a) then a[n] (sampling.jl:36,87)
+    return DataFrame([name(cpd) => Int.(states[:, i]) .+ 1 for (i, cpd) in enumerate(bn.cpds)])
+end
+
+function Random.rand(bn::DiscreteBayesNet, s::CUDALikelihoodWeightedSampler, nsamples::Integer)
+    ev = evidence_vector(device_net(bn).layout, bn, s.evidence)
+    states, w, _ = _sample_table(bn, ev, 2, 1, nsamples, s.seed)
+    df = DataFrame([name(cpd) => Int.(states[:, i]) .+ 1 for (i, cpd) in enumerate(bn.cpds)])
+    df[!, :p] = w ./ sum(w)                                       # sampling.jl:171-172
+    return df
+end
+
+# gibbs_sample(bn, nsamples, burn_in; ...) on the device    replaces src/gibbs.jl:289-374 (discrete nets)
+function cuda_gibbs_sample(bn::DiscreteBayesNet, nsamples::Integer, burn_in::Integer;
+        thinning::Integer=0, consistent_with::Assignment=Assignment(),
+        variable_order::Union{Vector{Symbol},Nothing}=nothing,
+        initial_sample::Union{Assignment,Nothing}=nothing, seed::Integer=0, n_chains::Integer=1)
+    nsamples > 0 || throw(ArgumentError("nsamples parameter less than 1"))       # gibbs.jl:299-301
+    burn_in >= 0 || throw(ArgumentError("Negative burn_in parameter"))
+    thinning >= 0 || throw(ArgumentError("Negative sample_skip parameter"))
+    net = device_net(bn)
+    lay = net.layout
+    ev = evidence_vector(lay, bn, consistent_with)
+    free = [nm for (i, nm) in enumerate(lay.names) if ev[i] < 0]
+    order = C_NULL
+    if variable_order !== nothing                                                  # gibbs.jl:302-313
+        sort(variable_order) == sort(free) ||
+            throw(ArgumentError("variable_order must contain exactly the non-evidence variables"))
+        order = Int32[findfirst(==(v), free) - 1 for v in variable_order]
+    end
+    init = C_NULL
+    if initial_sample !== nothing                                                  # gibbs.jl:315-324
+        all(haskey(initial_sample, nm) for nm in lay.names) ||
+            throw(ArgumentError("Gibbs sample initial_sample must be an assignment with all variables in the Bayes Net"))
+        init = repeat(UInt8[initial_sample[nm] - 1 for nm in lay.names], 1, n_chains)
+    end
+    out = Matrix{UInt8}(undef, n_chains * nsamples, length(lay.names))
+    GC.@preserve ev order init out begin
+        _bn_check(ccall((:bn_gibbs_sample, libbn_cuda), Int32,
+                        (UInt64, Ptr{Int8}, UInt64, UInt64, Int64, Int64, Int64, Ptr{Int32}, UInt64, Ptr{UInt8}, Ptr{UInt8}),
+                        net.handle, ev, 0, n_chains, nsamples, burn_in, thinning, order, seed, init, out))
+    end
+    return DataFrame([nm => Int.(out[:, i]) .+ 1 for (i, nm) in enumerate(lay.names)])
+end
+
+# ------------------------------------------------------------------------------------------------
+# Device-resident factors: * / sum / normalize!      replaces src/Factors/factors_dims.jl:45-57,60-100,185-269
+mutable struct DeviceFactor
+    handle::UInt64
+    dimensions::NodeNames
+    function DeviceFactor(h::UInt64, dims::NodeNames)
+        f = new(h, dims)
+        finalizer(x -> ccall((:bn_factor_free, libbn_cuda), Int32, (UInt64,), x.handle), f)
+        return f
+    end
+end
+
+# Symbols <-> int32 ids: a process-wide interning table (ids only need to agree between operands)
+const _var_ids = Dict{Symbol,Int32}()
+var_id(s::Symbol) = get!(() -> Int32(length(_var_ids)), _var_ids, s)
+const _var_names = Dict{Int32,Symbol}()
+function _ids(dims::NodeNames)
+    ids = Int32[var_id(d) for d in dims]
+    for (d, i) in zip(dims, ids); _var_names[i] = d; end
+    return ids
+end
+
+function DeviceFactor(ϕ::Factor; device::Integer=0)
+    h = Ref{UInt64}(0)
+    ids = _ids(ϕ.dimensions); card = Int32[size(ϕ.potential)...]
+    GC.@preserve ids card ϕ begin
+        _bn_check(ccall((:bn_factor_upload, libbn_cuda), Int32,
+                        (Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Int32, Ref{UInt64}),
+                        length(ids), ids, card, ϕ.potential, device, h))
+    end
+    return DeviceFactor(h[], copy(ϕ.dimensions))
+end
+
+function _wrap(h::UInt64)
+    nd = Ref{Int32}(0)
+    _bn_check(ccall((:bn_factor_ndims, libbn_cuda), Int32, (UInt64, Ref{Int32}), h, nd))
+    ids = zeros(Int32, nd[]); card = zeros(Int32, nd[])
+    _bn_check(ccall((:bn_factor_shape, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Ptr{Int32}), h, ids, card))
+    return DeviceFactor(h, Symbol[_var_names[i] for i in ids])
+end
+
+function Base.convert(::Type{Factor}, d::DeviceFactor)
+    nd = length(d.dimensions)
+    ids = zeros(Int32, nd); card = zeros(Int32, nd)
+    _bn_check(ccall((:bn_factor_shape, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Ptr{Int32}), d.handle, ids, card))
+    pot = Array{Float64}(undef, Int.(card)...)
+    _bn_check(ccall((:bn_factor_download, libbn_cuda), Int32, (UInt64, Ptr{Float64}), d.handle, pot))
+    return Factor(d.dimensions, pot)
+end
+
+function Base.:*(a::DeviceFactor, b::DeviceFactor)
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_product, libbn_cuda), Int32, (UInt64, UInt64, Ref{UInt64}), a.handle, b.handle, h))
+    return _wrap(h[])
+end
+
+function Base.sum(a::DeviceFactor, dims::NodeNameUnion)
+    ids = _ids(nodeconvert(NodeNames, dims))
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_sum, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Int32, Ref{UInt64}),
+                    a.handle, ids, length(ids), h))
+    return _wrap(h[])
+end
+
+function LinearAlgebra.normalize!(a::DeviceFactor; p::Int=1)
+    _bn_check(ccall((:bn_factor_normalize, libbn_cuda), Int32, (UInt64, Int32), a.handle, p))
+    return a
+end
+
+"sum(reduce(*, factors), h) in one kernel: the elimination step of src/Inference/exact.jl:27."
+function eliminate(factors::Vector{DeviceFactor}, h::NodeName)
+    hs = UInt64[f.handle for f in factors]
+    ids = _ids([h]); out = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_eliminate, libbn_cuda), Int32, (Ptr{UInt64}, Int32, Ptr{Int32}, Int32, Ref{UInt64}),
+                    hs, length(hs), ids, 1, out))
+    return _wrap(out[])
+end
