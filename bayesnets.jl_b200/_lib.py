@@ -36,6 +36,10 @@ _SIGS = {
     "bn_net_destroy": (C.c_int32, [h64]),
     "bn_lw_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, f64p, f64p]),
     "bn_lw_infer_dev": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bn_set_lw_mode": (C.c_int32, [C.c_int32, C.c_int32]),
+    "bn_lw_spec_compile_count": (C.c_uint64, []),
+    "bn_lw_spec_source": (C.c_int32, [C.c_int32, i32p, i32p, i32p, i64p, f64p, i8p, i32p, C.c_int32, C.c_int32,
+                                      C.c_char_p, C.c_int64, i64p, i64p, i32p]),
     "bn_sample": (C.c_int32, [h64, i8p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, u8p, f64p, u8p]),
     "bn_sample_dev": (C.c_int32, [h64, i8p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -110,6 +114,16 @@ def ptr(a, t):
 def set_stream(cuda_stream: int | None) -> None:
     """Enqueue subsequent calls from this thread on `cuda_stream` (e.g. torch.cuda.current_stream().cuda_stream)."""
     check(lib().bn_set_stream(C.c_void_p(cuda_stream or 0)))
+
+
+_LW_MODES = {"auto": 0, "generic": 1, "specialized": 2}
+
+
+def set_lw_mode(mode: str = "auto", prune: bool = True) -> None:
+    """Pick the LW kernel for this thread: "auto" (network-specialised NVRTC kernel when it can be built, generic
+    interpreter otherwise), "generic", or "specialized" (raise if unavailable).  `prune` lets the specialised kernel
+    skip barren nodes (never changes a count bit; see csrc/specialize.cu)."""
+    check(lib().bn_set_lw_mode(C.c_int32(_LW_MODES[mode]), C.c_int32(1 if prune else 0)))
 
 
 def launch_count() -> int:

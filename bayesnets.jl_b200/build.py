@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbn_cuda.so")
-SOURCES = ["core.cu", "sampling.cu", "gibbs.cu", "factor.cu", "exact.cu"]
+SOURCES = ["core.cu", "sampling.cu", "specialize.cu", "gibbs.cu", "factor.cu", "exact.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
     subprocess.check_call(link)
     with open(os.path.join(bdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))

@@ -109,7 +109,13 @@ struct PoolBuf {
 };
 
 // ---------------------------------------------------------------------------- objects behind handles
+struct SpecKernel;  // specialize.cu: one NVRTC-compiled LW kernel per (evidence mask, query)
+struct Net;
+void spec_cache_clear(Net* net);
+
 struct Net {
+  ~Net() { spec_cache_clear(this); }
+  std::unordered_map<std::string, SpecKernel*> spec_cache;
   int device = 0;
   int n = 0;
   // host copies (planning is host-side)

@@ -406,6 +406,11 @@ int32_t bn_lw_infer_dev(bn_net_t h, const int8_t* evidence, const int32_t* query
   BN_TRY(check_query(net, evidence, query, n_query, &qstride, &ncell));
   BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)(ncell + 2) * 8, tl_stream));
   if (n_particles == 0) return BN_OK;
+  // network-specialised kernel first (specialize.cu); the generic interpreter covers everything else
+  bool used = false;
+  BN_TRY(launch_lw_specialized(net, evidence, query, (uint32_t)n_query, qstride, (uint32_t)ncell, first_particle,
+                               n_particles, seed, out_dev, &used));
+  if (used) return BN_OK;
   SampleArgs a{};
   a.first = first_particle;
   a.n = n_particles;

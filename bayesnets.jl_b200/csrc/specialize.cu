@@ -1,0 +1,487 @@
+// specialize.cu -- network-specialised likelihood-weighting kernel (NVRTC, sm_100a).
+//
+// Replaces the particle loop of src/Inference/likelihood.jl:34-54 for one (network, evidence mask, query):
+// the host emits straight-line CUDA for THAT network -- one block of code per node in topological order,
+// particle states in registers, table offsets / parent strides as immediates, the row index as <= 3 IMAD,
+// one LDS per node -- compiles it for sm_100a with NVRTC and caches the cubin in the net handle.
+// Evidence VALUES stay run-time data (they only change table contents, which are uploaded per call).
+//
+// Why: the generic interpreter (sampling.cu) spends ~78 issue slots per node-sample, 3/4 of it decoding
+// the program and moving u8 states through shared memory.  LW on a B200 is bound by issue slots
+// (ALU + FMA pipes), not by HBM, so removing the interpreter is the roofline move.
+//
+// Same random-stream spec as the generic kernel and oracle/bn_oracle.c (DEVICE_SPEC): draw d of a particle
+// is word d&3 of Philox4x32-10(counter = (pid_lo, pid_hi, d>>2, 0), key = seed), d = index of the node
+// among the FREE nodes in topological order; state = #{k : (r >> 1) >= T_k}.  Because draw indices are
+// static, nodes that can influence neither the query nor the weight (not an ancestor of query or evidence:
+// "barren" nodes) may be skipped without changing any count bit.  prune = 0 keeps every node alive (each
+// state feeds a checksum the compiler cannot fold), which is what bench.py's headline number uses.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <memory>
+#include <sstream>
+
+namespace bn {
+
+// ------------------------------------------------------------------------------------------ NVRTC (dlopen)
+struct Nvrtc {
+  void* h = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+  const char* (*GetErrorString)(nvrtcResult);
+  bool ok = false;
+};
+
+static Nvrtc& nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* cands[] = {getenv("BN_NVRTC_PATH"), "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"};
+    for (const char* c : cands) {
+      if (!c) continue;
+      n.h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+      if (n.h) break;
+    }
+    if (!n.h) return;
+#define BN_SYM(field, name) *(void**)(&n.field) = dlsym(n.h, name); if (!n.field) return;
+    BN_SYM(CreateProgram, "nvrtcCreateProgram")
+    BN_SYM(CompileProgram, "nvrtcCompileProgram")
+    BN_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    BN_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    BN_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    BN_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    BN_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    BN_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef BN_SYM
+    n.ok = true;
+  });
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------ driver API
+struct Driver {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                           void**, void**) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+
+static Driver& driver() {
+  static Driver d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn;
+    };
+    d.ok = get("cuModuleLoadData", (void**)&d.ModuleLoadData) && get("cuModuleUnload", (void**)&d.ModuleUnload) &&
+           get("cuModuleGetFunction", (void**)&d.ModuleGetFunction) &&
+           get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute) &&
+           get("cuFuncGetAttribute", (void**)&d.FuncGetAttribute) &&
+           get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&d.OccupancyMaxActiveBlocksPerMultiprocessor) &&
+           get("cuLaunchKernel", (void**)&d.LaunchKernel) && get("cuGetErrorString", (void**)&d.GetErrorString);
+    cudaGetLastError();
+  });
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ code generation
+constexpr int SPEC_MAX_REG_CELLS = 16;  // query tables up to this size accumulate in registers
+
+struct SpecShape {
+  int threads = 256;
+  int min_blocks = 2;
+};
+
+static void live_nodes(const Net& net, const SampleProgram& prg, const int32_t* query, uint32_t n_query, bool prune,
+                       std::vector<char>* live) {
+  const int n = net.n;
+  live->assign(n, prune ? 0 : 1);
+  if (!prune) return;
+  // ancestors (through FREE parents only: evidence parents are folded into the tables) of query and evidence nodes
+  std::vector<int> stack;
+  for (uint32_t j = 0; j < n_query; ++j) stack.push_back(query[j]);
+  for (int i = 0; i < n; ++i) if (prg.plan[i].is_evidence) stack.push_back(i);
+  while (!stack.empty()) {
+    int i = stack.back();
+    stack.pop_back();
+    if ((*live)[i]) continue;
+    (*live)[i] = 1;
+    for (auto& pr : prg.plan[i].parents) stack.push_back(pr.first);
+  }
+}
+
+static const char* kPrelude = R"BNSRC(
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// Philox4x32-10 (Salmon et al. SC'11); identical to common.cuh / oracle/bn_oracle.c
+__device__ __forceinline__ void px(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32& o0, u32& o1, u32& o2, u32& o3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const u32 n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// one-shot TMA bulk copy global -> shared (SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void stage_tables(void* dst, const void* src, u32 bytes, u64* bar) {
+  const u32 b = smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    u32 done = 0;
+    while (done < bytes) {
+      const u32 chunk = bytes - done < 65536u ? bytes - done : 65536u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32((const char*)dst + done)),
+                   "l"((const char*)src + done), "r"(chunk), "r"(b)
+                   : "memory");
+      done += chunk;
+    }
+  }
+  u32 ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(b) : "memory");
+  }
+}
+)BNSRC";
+
+// Emit the kernel for this (net, evidence mask, query).
+static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const int32_t* query, uint32_t n_query,
+                                 const std::vector<int64_t>& qstride, uint32_t ncell, bool prune, const SpecShape& shp,
+                                 uint32_t* n_live_out) {
+  const int n = net.n;
+  std::vector<char> live;
+  live_nodes(net, prg, query, n_query, prune, &live);
+  const bool reg_bins = ncell <= (uint32_t)SPEC_MAX_REG_CELLS;
+  const uint32_t tab_words = prg.table_words;
+  std::ostringstream o;
+  o << "// generated by libbn_cuda (specialize.cu): " << n << " nodes, " << prg.n_free << " free, query cells " << ncell
+    << (prune ? ", barren nodes pruned" : ", all nodes kept alive") << "\n";
+  o << kPrelude;
+  o << "#define NT " << shp.threads << "\n#define TAB_WORDS " << tab_words << "u\n#define NCELL " << ncell << "u\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(NT, " << shp.min_blocks
+    << ") lw_spec(const u32* __restrict__ tab_g, u64 first, u64 n, u32 k0, u32 k1, u32 never, double* __restrict__ out) {\n";
+  o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
+  o << "  __shared__ __align__(8) u64 bar;\n";
+  o << "  const u32* __restrict__ tab = reinterpret_cast<const u32*>(smem_raw);\n";
+  o << "  double* bins = reinterpret_cast<double*>(smem_raw + TAB_WORDS * 4u);\n";
+  o << "  const u32 tid = threadIdx.x;\n";
+  o << "  stage_tables(smem_raw, tab_g, TAB_WORDS * 4u, &bar);\n";
+  o << "  for (u32 c = tid; c < NCELL + 2u; c += NT) bins[c] = 0.0;\n";
+  o << "  __syncthreads();\n";
+  o << "  double sw = 0.0, sw2 = 0.0;\n";
+  if (reg_bins)
+    for (uint32_t c = 0; c < ncell; ++c) o << "  double a" << c << " = 0.0;\n";
+  o << "  for (u64 row = (u64)blockIdx.x * NT + tid; row < n; row += (u64)gridDim.x * NT) {\n";
+  o << "    const u64 pid = first + row;\n";
+  o << "    const u32 c0 = (u32)pid, c1 = (u32)(pid >> 32);\n";
+  o << "    double w = 1.0;\n";
+  if (!prune) o << "    u32 chk = 0u;\n";
+  // which Philox blocks are needed
+  uint32_t d = 0, n_live = 0;
+  int cur_blk = -1;
+  for (int i = 0; i < n; ++i) {
+    const NodePlan& np = prg.plan[i];
+    const uint32_t my_d = d;
+    if (!np.is_evidence) ++d;
+    if (!live[i]) continue;
+    ++n_live;
+    // row address (words)
+    std::ostringstream addr;
+    addr << np.toff << "u";
+    for (auto& pr : np.parents) addr << " + s" << pr.first << " * " << (pr.second * np.row_words) << "u";
+    if (np.is_evidence) {
+      o << "    w *= *reinterpret_cast<const double*>(tab + (" << addr.str() << "));  // node " << i << " (evidence)\n";
+      continue;
+    }
+    const int blk = (int)(my_d >> 2);
+    if (blk != cur_blk) {
+      cur_blk = blk;
+      o << "    u32 r" << blk << "_0, r" << blk << "_1, r" << blk << "_2, r" << blk << "_3;\n";
+      o << "    px(c0, c1, " << blk << "u, 0u, k0, k1, r" << blk << "_0, r" << blk << "_1, r" << blk << "_2, r" << blk
+        << "_3);\n";
+    }
+    std::ostringstream rr;
+    rr << "(r" << blk << "_" << (my_d & 3u) << " >> 1)";
+    o << "    u32 s" << i << ";  // node " << i << ": card " << np.card << ", " << np.parents.size() << " free parents\n";
+    if (np.card <= 1) {
+      o << "    s" << i << " = 0u;\n";
+    } else if (np.card == 2) {
+      o << "    s" << i << " = " << rr.str() << " >= tab[" << addr.str() << "];\n";
+    } else if (np.card == 3) {
+      o << "    { const uint2 t = *reinterpret_cast<const uint2*>(tab + (" << addr.str() << ")); const u32 r = " << rr.str()
+        << "; s" << i << " = (u32)(r >= t.x) + (u32)(r >= t.y); }\n";
+    } else {
+      o << "    { const u32 r = " << rr.str() << "; const u32 ad = " << addr.str() << "; s" << i << " = 0u;\n";
+      for (int k = 0; k + 1 < np.card; k += 4) {
+        o << "      { const uint4 t = *reinterpret_cast<const uint4*>(tab + ad + " << k << "u); s" << i
+          << " += (u32)(r >= t.x) + (u32)(r >= t.y) + (u32)(r >= t.z) + (u32)(r >= t.w); }\n";
+      }
+      o << "    }\n";
+    }
+    if (!prune) o << "    chk += s" << i << ";\n";
+  }
+  // query cell
+  o << "    const u32 cell = 0u";
+  for (uint32_t j = 0; j < n_query; ++j) o << " + s" << query[j] << " * " << (uint32_t)qstride[j] << "u";
+  o << ";\n";
+  if (!prune) o << "    if (chk == never) w = 0.0;  // keeps every state live; never true (host passes 0xFFFFFFFF)\n";
+  if (reg_bins) {
+    for (uint32_t c = 0; c < ncell; ++c) o << "    a" << c << " += (cell == " << c << "u) ? w : 0.0;\n";
+  } else {
+    o << "    atomicAdd(&bins[cell], w);\n";
+  }
+  o << "    sw += w; sw2 += w * w;\n";
+  o << "  }\n";
+  // reductions: warp shuffle, one smem atomic per warp, then one global atomic per (CTA, cell)
+  o << "#pragma unroll\n  for (int of = 16; of > 0; of >>= 1) {\n";
+  o << "    sw += __shfl_xor_sync(0xffffffffu, sw, of); sw2 += __shfl_xor_sync(0xffffffffu, sw2, of);\n";
+  if (reg_bins)
+    for (uint32_t c = 0; c < ncell; ++c) o << "    a" << c << " += __shfl_xor_sync(0xffffffffu, a" << c << ", of);\n";
+  o << "  }\n";
+  o << "  if ((tid & 31u) == 0u) {\n    atomicAdd(&bins[NCELL], sw); atomicAdd(&bins[NCELL + 1u], sw2);\n";
+  if (reg_bins)
+    for (uint32_t c = 0; c < ncell; ++c) o << "    if (a" << c << " != 0.0) atomicAdd(&bins[" << c << "], a" << c << ");\n";
+  o << "  }\n  __syncthreads();\n";
+  o << "  for (u32 c = tid; c < NCELL + 2u; c += NT) if (bins[c] != 0.0) atomicAdd(&out[c], bins[c]);\n";
+  o << "}\n";
+  if (n_live_out) *n_live_out = n_live;
+  return o.str();
+}
+
+static int32_t nvrtc_compile(const std::string& src, std::vector<char>* cubin, std::string* log) {
+  Nvrtc& nv = nvrtc();
+  BN_REQUIRE(nv.ok, BN_UNSUPPORTED, "libnvrtc.so.12 could not be loaded (set BN_NVRTC_PATH)");
+  nvrtcProgram prog;
+  nvrtcResult r = nv.CreateProgram(&prog, src.c_str(), "lw_spec.cu", 0, nullptr, nullptr);
+  BN_REQUIRE(r == NVRTC_SUCCESS, BN_CUDA_ERR, "nvrtcCreateProgram: %s", nv.GetErrorString(r));
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-fmad=false"};
+  r = nv.CompileProgram(prog, 4, opts);
+  size_t ls = 0;
+  nv.GetProgramLogSize(prog, &ls);
+  if (ls > 1 && log) { log->resize(ls); nv.GetProgramLog(prog, &(*log)[0]); }
+  if (r != NVRTC_SUCCESS) {
+    set_error("nvrtcCompileProgram: %s: %.300s", nv.GetErrorString(r), log ? log->c_str() : "");
+    nv.DestroyProgram(&prog);
+    return BN_CUDA_ERR;
+  }
+  size_t cs = 0;
+  nv.GetCUBINSize(prog, &cs);
+  cubin->resize(cs);
+  nv.GetCUBIN(prog, cubin->data());
+  nv.DestroyProgram(&prog);
+  return BN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ kernel cache
+struct SpecKernel {
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  int threads = 0, blocks_per_sm = 0, regs = 0;
+  size_t smem = 0;
+  uint32_t table_words = 0, n_live = 0;
+};
+
+// Compiled kernels are owned by a process-wide table keyed by (device, generated source): re-uploading the same
+// network (a new bn_net_t) or another network with the same structure reuses the cubin instead of paying the
+// NVRTC compile (~1 s for 100 nodes) again.  Net::spec_cache is a non-owning per-handle shortcut.
+static std::mutex g_spec_mu;
+static std::unordered_map<std::string, std::unique_ptr<SpecKernel>> g_spec;
+static std::atomic<uint64_t> g_spec_compiles{0};
+
+void spec_cache_clear(Net* net) { net->spec_cache.clear(); }
+
+static std::string spec_key(const Net& net, const int8_t* evidence, const int32_t* query, uint32_t n_query, bool prune) {
+  std::string k((size_t)net.n, '0');
+  for (int i = 0; i < net.n; ++i) k[i] = (evidence && evidence[i] >= 0) ? '1' : '0';
+  k += prune ? "|p" : "|a";
+  for (uint32_t j = 0; j < n_query; ++j) k += "," + std::to_string(query[j]);
+  return k;
+}
+
+static int32_t cu_fail(const char* what, CUresult r) {
+  const char* s = nullptr;
+  driver().GetErrorString(r, &s);
+  set_error("%s failed: %s", what, s ? s : "?");
+  return BN_CUDA_ERR;
+}
+
+thread_local int tl_lw_mode = 0;   // 0 auto, 1 generic only, 2 specialised required
+thread_local int tl_lw_prune = 1;  // barren-node elimination in the specialised kernel
+
+int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
+                              const std::vector<int64_t>& qstride, uint32_t ncell, uint64_t first, uint64_t n,
+                              uint64_t seed, double* out_dev, bool* used) {
+  *used = false;
+  if (tl_lw_mode == 1) return BN_OK;
+  const bool must = tl_lw_mode == 2;
+  Driver& drv = driver();
+  if (!nvrtc().ok || !drv.ok) {
+    BN_REQUIRE(!must, BN_UNSUPPORTED, "specialised LW kernel unavailable: NVRTC / driver entry points missing");
+    return BN_OK;
+  }
+  const DevProps& dp = dev_props(net->device);
+  SampleProgram prg;
+  BN_TRY(compile_program(*net, evidence, false, 1, &prg));
+  const size_t smem = (size_t)prg.table_words * 4 + (size_t)(ncell + 2) * 8;
+  if (smem + 1024 > (size_t)dp.max_smem_optin || net->n > 4096 || prg.table_words > (1u << 22)) {
+    BN_REQUIRE(!must, BN_UNSUPPORTED, "network too large for the specialised LW kernel");
+    return BN_OK;
+  }
+  const bool prune = tl_lw_prune != 0;
+  const std::string key = spec_key(*net, evidence, query, n_query, prune);
+  SpecKernel* k = nullptr;
+  auto it = net->spec_cache.find(key);
+  if (it != net->spec_cache.end()) {
+    k = it->second;
+  } else {
+    SpecShape shp;
+    uint32_t n_live = 0;
+    const std::string src = gen_lw_source(*net, prg, query, n_query, qstride, ncell, prune, shp, &n_live);
+    const std::string gkey = std::to_string(net->device) + "|" + src;
+    std::lock_guard<std::mutex> lk(g_spec_mu);
+    auto git = g_spec.find(gkey);
+    if (git != g_spec.end()) {
+      k = git->second.get();
+    } else {
+      std::vector<char> cubin;
+      std::string log;
+      g_spec_compiles.fetch_add(1);
+      int32_t rc = nvrtc_compile(src, &cubin, &log);
+      if (rc != BN_OK) {
+        if (must) return rc;
+        g_spec[gkey] = nullptr;  // do not retry a failing compile on every call
+      } else {
+        std::unique_ptr<SpecKernel> nk(new SpecKernel());
+        CUresult r = drv.ModuleLoadData(&nk->mod, cubin.data());
+        if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
+        r = drv.ModuleGetFunction(&nk->fn, nk->mod, "lw_spec");
+        if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
+        nk->threads = shp.threads;
+        nk->smem = smem;
+        nk->table_words = prg.table_words;
+        nk->n_live = n_live;
+        r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+        if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
+        drv.FuncGetAttribute(&nk->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, nk->fn);
+        int occ = 0;
+        r = drv.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, nk->fn, nk->threads, smem);
+        if (r != CUDA_SUCCESS) return cu_fail("cuOccupancyMaxActiveBlocksPerMultiprocessor", r);
+        nk->blocks_per_sm = occ > 0 ? occ : 1;
+        k = nk.get();
+        g_spec[gkey] = std::move(nk);
+      }
+    }
+    net->spec_cache[key] = k;
+  }
+  if (!k) {
+    BN_REQUIRE(!must, BN_CUDA_ERR, "specialised LW kernel failed to compile earlier for this (net, evidence, query)");
+    return BN_OK;
+  }
+  BN_REQUIRE(k->table_words == prg.table_words, BN_CUDA_ERR, "specialised kernel/table mismatch");
+  // tables -> device scratch (evidence values live only here)
+  cudaStream_t s = tl_stream;
+  const size_t bytes = (size_t)prg.table_words * 4;
+  if (net->scratch.n < bytes + 16) BN_CUDA_TRY(net->scratch.alloc((bytes + 16) * 2));
+  const uint32_t* tab_host = prg.words.data() + prg.prog_words;
+  if (bytes) BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, tab_host, bytes, cudaMemcpyHostToDevice, s));
+  long want = (long)((n + k->threads - 1) / k->threads);
+  long full = (long)dp.sm_count * k->blocks_per_sm;
+  unsigned grid = (unsigned)(want < full ? (want > 0 ? want : 1) : full);
+  const uint32_t* tab_dev = reinterpret_cast<const uint32_t*>(net->scratch.p);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), never = 0xFFFFFFFFu;
+  void* args[] = {(void*)&tab_dev, (void*)&first, (void*)&n, (void*)&k0, (void*)&k1, (void*)&never, (void*)&out_dev};
+  CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)s, args, nullptr);
+  if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(lw_spec)", r);
+  count_launch();
+  *used = true;
+  return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" {
+
+uint64_t bn_lw_spec_compile_count(void) { return bn::g_spec_compiles.load(); }
+
+int32_t bn_set_lw_mode(int32_t mode, int32_t prune) {
+  BN_REQUIRE(mode >= 0 && mode <= 2, BN_BAD_ARG, "bn_set_lw_mode: mode %d outside 0..2", mode);
+  bn::tl_lw_mode = mode;
+  bn::tl_lw_prune = prune ? 1 : 0;
+  return BN_OK;
+}
+
+// Host-only (no GPU needed): emit the specialised source for a flat network and, when cubin_size is non-NULL,
+// compile it with NVRTC for sm_100a.  Used by the CPU tests and to inspect / commit the generated code.
+int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                          const int64_t* cpt_off, const double* cpt, const int8_t* evidence, const int32_t* query,
+                          int32_t n_query, int32_t prune, char* out_src, int64_t cap, int64_t* out_len,
+                          int64_t* cubin_size, int32_t* n_live) {
+  BN_REQUIRE(card && par_ptr && cpt_off && cpt && out_len, BN_BAD_ARG, "bn_lw_spec_source: NULL argument");
+  Net net;
+  net.n = n_nodes;
+  net.card.assign(card, card + n_nodes);
+  net.par_ptr.assign(par_ptr, par_ptr + n_nodes + 1);
+  net.par_idx.assign(par_idx, par_idx + par_ptr[n_nodes]);
+  net.cpt_off.assign(cpt_off, cpt_off + n_nodes + 1);
+  net.cpt.assign(cpt, cpt + cpt_off[n_nodes]);
+  SampleProgram prg;
+  BN_TRY(compile_program(net, evidence, false, 1, &prg));
+  std::vector<int64_t> qstride;
+  int64_t cells = 1;
+  for (int j = 0; j < n_query; ++j) {
+    BN_REQUIRE(query[j] >= 0 && query[j] < n_nodes && !(evidence && evidence[query[j]] >= 0), BN_BAD_ARG, "bad query");
+    qstride.push_back(cells);
+    cells *= card[query[j]];
+  }
+  SpecShape shp;
+  uint32_t nl = 0;
+  const std::string src = gen_lw_source(net, prg, query, (uint32_t)n_query, qstride, (uint32_t)cells, prune != 0, shp, &nl);
+  if (n_live) *n_live = (int32_t)nl;
+  *out_len = (int64_t)src.size();
+  if (out_src && cap > 0) {
+    const size_t m = src.size() < (size_t)(cap - 1) ? src.size() : (size_t)(cap - 1);
+    memcpy(out_src, src.data(), m);
+    out_src[m] = 0;
+  }
+  if (cubin_size) {
+    std::vector<char> cubin;
+    std::string log;
+    BN_TRY(nvrtc_compile(src, &cubin, &log));
+    *cubin_size = (int64_t)cubin.size();
+  }
+  return BN_OK;
+}
+
+}  // extern "C"

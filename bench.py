@@ -48,6 +48,19 @@ def algorithmic_bytes_per_particle(lay) -> float:
     return float(8 * int(lay.card.sum()))
 
 
+def live_node_count(lay, query, evidence) -> int:
+    """Nodes that can influence the query or the weight: ancestors of query + evidence through free parents."""
+    ev = {lay.index[e] for e in evidence}
+    stack, live = [lay.index[q] for q in query] + sorted(ev), set()
+    while stack:
+        i = stack.pop()
+        if i in live:
+            continue
+        live.add(i)
+        stack.extend(p for p in lay.parents(i) if p not in ev)
+    return len(live)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -157,7 +170,7 @@ def workload_config(lay, query, evidence, per_gpu, n_gpus):
         "query_cells": int(np.prod([lay.card[lay.index[q]] for q in query])),
         "particles_per_step_per_gpu": int(per_gpu), "particles_per_step": int(per_gpu) * n_gpus,
         "parallelism": f"particles sharded over {n_gpus} GPU(s) by global Philox counter + 1 all-reduce of counts",
-        "l2": "n/a - no HBM-resident operands (program+tables ~20 KB are TMA-staged to smem per launch); "
+        "l2": "n/a - no HBM-resident operands (tables ~20 KB are TMA-staged to smem per launch); "
               "fresh seed every step, nothing cached",
     }
 
@@ -248,6 +261,12 @@ def run_gpu(args):
         return im.last_stats[0] > 0
 
     net, lay, query, evidence = build_case(bn, check=check)
+    # HEADLINE kernel: the network-specialised LW kernel with EVERY node sampled (prune off).  The product default
+    # additionally skips barren nodes (bit-identical counts, ~2.3x fewer node-samples on this case); that and the
+    # generic interpreter are reported under "variants", never as `value`.
+    headline = {"specialized_all": ("specialized", False), "specialized_pruned": ("specialized", True),
+                "generic": ("generic", True)}[args.lw_kernel]
+    bn.set_lw_mode(*headline)
     slw = ShardedLikelihoodWeighting(net, query, evidence, per_gpu * world, seed=0, device=local)
     stream = torch.cuda.current_stream(local)
 
@@ -310,6 +329,30 @@ def run_gpu(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = per_gpu * world * e2e_steps / float(e2e_s.item())
 
+    # ---- other kernel variants on the same workload (short, device-timed; not the headline)
+    variants = {}
+    if world == 1:
+        for name, (mode, prune) in {"specialized_all": ("specialized", False), "specialized_pruned": ("specialized", True),
+                                    "generic": ("generic", True)}.items():
+            if name == args.lw_kernel:
+                continue
+            bn.set_lw_mode(mode, prune)
+            for w in range(2):
+                slw.seed = 2000 + w
+                slw.launch()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            for k in range(2):
+                slw.seed = 3000 + k
+                slw.launch()
+            b.record(stream)
+            torch.cuda.synchronize()
+            variants[name] = {"value": per_gpu * 2 / (a.elapsed_time(b) * 1e-3), "unit": UNIT,
+                              "posterior": [round(float(x), 6) for x in slw.posterior().ravel(order="F")]}
+        bn.set_lw_mode(*headline)
+    live = live_node_count(lay, query, evidence)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -326,7 +369,9 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "infer(LikelihoodWeightingInference(nsamples), bn, query; evidence)"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "bn::particle_kernel<MODE_INFER>", "bound": "hbm", "achieved": achieved, "peak": hbm,
+        "lw_kernel": args.lw_kernel, "nodes_sampled_per_particle": int(lay.n) if args.lw_kernel != "specialized_pruned" else live,
+        "variants": variants, "jit_compiles": int(_lib.lib().bn_lw_spec_compile_count()),
+        "roofline": {"kernel": {"generic": "bn::particle_kernel<MODE_INFER>"}.get(args.lw_kernel, "lw_spec (NVRTC, network-specialised)"), "bound": "hbm", "achieved": achieved, "peak": hbm,
                      "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": f"of {src}",
                      "algorithmic_bytes_per_particle": bpp, "kernel_ms": kern_ms,
                      "note": "HBM-EQUIVALENT figure required by SURVEY.md 8(d): the CPT rows a particle touches, "
@@ -360,6 +405,8 @@ def main():
     ap.add_argument("--samples", type=float, default=1e9, help="particles per step per GPU")
     ap.add_argument("--factor-log2", type=int, default=24)
     ap.add_argument("--no-factors", action="store_true")
+    ap.add_argument("--lw-kernel", default="specialized_all", choices=["specialized_all", "specialized_pruned", "generic"],
+                    help="kernel timed as the headline (default: specialised, every node sampled)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -83,6 +83,21 @@ int32_t bn_lw_infer(bn_net_t net, const int8_t* evidence, const int32_t* query, 
 int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
                         uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_dev);
 
+/* LW kernel selection for subsequent calls from this host thread.
+ * mode : 0 = auto (network-specialised NVRTC kernel when it can be built, else the generic interpreter),
+ *        1 = generic interpreter only, 2 = specialised required (error if unavailable).
+ * prune: != 0 lets the specialised kernel skip "barren" nodes (not an ancestor of a query or evidence node);
+ *        draw indices are static, so the counts are bit-identical either way.  Default: mode 0, prune 1. */
+int32_t bn_set_lw_mode(int32_t mode, int32_t prune);
+/* Number of NVRTC compiles since load (kernels are cached process-wide by generated source). */
+uint64_t bn_lw_spec_compile_count(void);
+/* Host-only (no GPU): emit the CUDA source the specialised LW kernel would be built from for this flat network
+ * and, when cubin_size != NULL, compile it with NVRTC for sm_100a.  out_src may be NULL to query *out_len. */
+int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                          const int64_t* cpt_off, const double* cpt, const int8_t* evidence, const int32_t* query,
+                          int32_t n_query, int32_t prune, char* out_src, int64_t cap, int64_t* out_len,
+                          int64_t* cubin_size, int32_t* n_live);
+
 /* ---- table samplers: rand(bn, n) / rand(bn, n, evidence) / get_weighted_dataframe
  *      src/sampling.jl:24-41,52-57 (ancestral), :72-93 (rejection, <= max_attempts tries),
  *      :102-115,153-174 (likelihood-weighted rows) -------------------------------------------------

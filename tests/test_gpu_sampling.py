@@ -187,3 +187,48 @@ def test_error_paths(bn):
         bn.infer(bn.LikelihoodWeightingInference(10), net, "T", evidence={"T": 1})
     with pytest.raises(IndexError):
         bn.infer(bn.LikelihoodWeightingInference(10), net, "T", evidence={"A": 3})
+
+
+@pytest.fixture
+def lw_mode(bn):
+    yield bn.set_lw_mode
+    bn.set_lw_mode("auto", True)
+
+
+@pytest.mark.parametrize("mode,prune", [("generic", True), ("specialized", True), ("specialized", False)])
+@pytest.mark.parametrize("seed,n_nodes,n_ev,n_q", [(0, 100, 10, 2), (3, 200, 20, 2), (6, 60, 6, 4), (7, 30, 0, 1)])
+def test_lw_kernel_variants_equal_oracle(bn, lw_mode, mode, prune, seed, n_nodes, n_ev, n_q):
+    """The generic interpreter, the NVRTC network-specialised kernel with barren-node pruning and the same kernel
+    with every node kept alive all implement ONE stream spec: counts equal the oracle's (n_q = 4 -> up to 256
+    query cells exercises the shared-memory-atomic accumulation path, <= 16 cells the register path)."""
+    net, lay, on, query, evidence = random_case(bn, n_nodes, seed, n_ev, n_q)
+    lw_mode(mode, prune)
+    n = 150_001
+    launches = bn.launch_count()
+    counts, (sw, sw2) = lw_raw(bn, net, query, evidence, n, seed=seed + 11, first=12345)
+    assert bn.launch_count() == launches + 1
+    oc, osw, osw2 = capi.lw_infer(on, lay.evidence_vector(evidence), lay.query_indices(query), n, seed=seed + 11,
+                                  mode=capi.DEVICE_SPEC, first=12345)
+    np.testing.assert_allclose(counts, oc.ravel(order="F"), rtol=1e-12, atol=0)
+    assert sw == pytest.approx(osw, rel=1e-12) and sw2 == pytest.approx(osw2, rel=1e-12)
+    if not evidence:
+        assert np.array_equal(counts, oc.ravel(order="F"))
+
+
+def test_lw_specialized_kernel_is_cached_per_evidence_mask(bn, lw_mode):
+    """Evidence VALUES are run-time data: changing them must reuse the compiled kernel (fast second call) and still
+    be exact; changing the evidence MASK compiles a new one."""
+    import time
+    net, lay, on, query, evidence = random_case(bn, 100, 0, 10)
+    lw_mode("specialized", True)
+    lw_raw(bn, net, query, evidence, 1000, seed=1)
+    ev2 = dict(evidence)
+    k = next(iter(ev2))
+    ev2[k] = ev2[k] % net.ncategories(k) + 1
+    t0 = time.perf_counter()
+    counts, (sw, _) = lw_raw(bn, net, query, ev2, 50_000, seed=2)
+    assert time.perf_counter() - t0 < 0.2  # no NVRTC compile on this call
+    oc, osw, _ = capi.lw_infer(on, lay.evidence_vector(ev2), lay.query_indices(query), 50_000, seed=2,
+                               mode=capi.DEVICE_SPEC)
+    np.testing.assert_allclose(counts, oc.ravel(order="F"), rtol=1e-12, atol=1e-300)
+    assert sw == pytest.approx(osw, rel=1e-12)

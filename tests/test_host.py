@@ -3,6 +3,7 @@ import ctypes
 import io
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -215,3 +216,25 @@ def test_layout_feeds_oracle_identically(bn, golden, oracle):
     on = oracle_net_from_layout(bn.flatten(net))
     np.testing.assert_allclose(exact_infer(on, "B", {"D": 1}).potential, [0.285265293007839, 0.714734706992161],
                                rtol=1e-12)
+
+
+def test_specialised_lw_source_compiles_without_a_gpu(bn):
+    """The network-specialised LW kernel is generated and NVRTC-compiled for sm_100a on the host; no device is
+    needed for that, so the code generator is covered by the CPU suite (the numerics are covered by -m gpu)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from dump_lw_spec import spec_source
+    net = bn.rand_discrete_bn(40, 3, 4, seed=3)
+    lay = bn.flatten(net)
+    evidence = {"N5": 1, "N17": 2}
+    pruned, cub_p, live_p = spec_source(lay, evidence, ["N9", "N30"], prune=True)
+    full, cub_f, live_f = spec_source(lay, evidence, ["N9", "N30"], prune=False)
+    assert cub_p > 0 and cub_f > 0                      # NVRTC produced a cubin for sm_100a
+    assert live_f == lay.n and 4 <= live_p <= live_f    # barren nodes dropped, query + evidence kept
+    assert "lw_spec" in pruned and "cp.async.bulk" in pruned and "chk" in full and "chk" not in pruned
+    # every state the query cell reads is defined
+    for q in ("N9", "N30"):
+        assert f"u32 s{lay.index[q]};" in pruned
+    # > 16 query cells switches to shared-memory atomics
+    big, _, _ = spec_source(lay, {}, ["N1", "N2", "N3", "N4", "N6"], prune=True, compile=False)
+    ncell = int(np.prod([lay.card[lay.index[f"N{i}"]] for i in (1, 2, 3, 4, 6)]))
+    assert ("atomicAdd(&bins[cell], w)" in big) == (ncell > 16)
