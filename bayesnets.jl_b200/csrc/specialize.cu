@@ -104,9 +104,11 @@ static Driver& driver() {
 // ------------------------------------------------------------------------------------------ code generation
 constexpr int SPEC_MAX_REG_CELLS = 16;  // query tables up to this size accumulate in registers
 
+// 512 x 1 (<= 128 registers) measured best on B200 for the 100-node case (profiles/r1b_lw_spec_sweep.txt);
+// the kernel is bound by the fmaheavy (IMAD.WIDE of Philox) and ALU pipes, not by occupancy.
 struct SpecShape {
-  int threads = 256;
-  int min_blocks = 2;
+  int threads = 512;
+  int min_blocks = 1;
 };
 
 static void live_nodes(const Net& net, const SampleProgram& prg, const int32_t* query, uint32_t n_query, bool prune,
@@ -183,6 +185,8 @@ static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const
   live_nodes(net, prg, query, n_query, prune, &live);
   const bool reg_bins = ncell <= (uint32_t)SPEC_MAX_REG_CELLS;
   const uint32_t tab_words = prg.table_words;
+  const char* style_env = getenv("BN_SPEC_STYLE");
+  const int style = style_env ? atoi(style_env) : 1;
   std::ostringstream o;
   o << "// generated by libbn_cuda (specialize.cu): " << n << " nodes, " << prg.n_free << " free, query cells " << ncell
     << (prune ? ", barren nodes pruned" : ", all nodes kept alive") << "\n";
@@ -206,7 +210,11 @@ static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const
   o << "    const u32 c0 = (u32)pid, c1 = (u32)(pid >> 32);\n";
   o << "    double w = 1.0;\n";
   if (!prune) o << "    u32 chk = 0u;\n";
-  // which Philox blocks are needed
+  // states that no child, query cell or weight reads (only matters when every node is kept alive)
+  std::vector<char> has_reader(n, 0);
+  for (int i = 0; i < n; ++i)
+    for (auto& pr : prg.plan[i].parents) has_reader[pr.first] = 1;
+  for (uint32_t j = 0; j < n_query; ++j) has_reader[query[j]] = 1;
   uint32_t d = 0, n_live = 0;
   int cur_blk = -1;
   for (int i = 0; i < n; ++i) {
@@ -230,25 +238,46 @@ static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const
       o << "    px(c0, c1, " << blk << "u, 0u, k0, k1, r" << blk << "_0, r" << blk << "_1, r" << blk << "_2, r" << blk
         << "_3);\n";
     }
-    std::ostringstream rr;
-    rr << "(r" << blk << "_" << (my_d & 3u) << " >> 1)";
+    std::ostringstream rw;
+    rw << "r" << blk << "_" << (my_d & 3u);
+    const std::string rword = rw.str();
     o << "    u32 s" << i << ";  // node " << i << ": card " << np.card << ", " << np.parents.size() << " free parents\n";
+    const int nth = np.card - 1;  // real thresholds (row padding is never compared)
     if (np.card <= 1) {
       o << "    s" << i << " = 0u;\n";
-    } else if (np.card == 2) {
-      o << "    s" << i << " = " << rr.str() << " >= tab[" << addr.str() << "];\n";
-    } else if (np.card == 3) {
-      o << "    { const uint2 t = *reinterpret_cast<const uint2*>(tab + (" << addr.str() << ")); const u32 r = " << rr.str()
-        << "; s" << i << " = (u32)(r >= t.x) + (u32)(r >= t.y); }\n";
+    } else if (style == 0) {
+      // plain compares; the compiler picks ISETP + SEL/IMAD.MOV sequences
+      o << "    { const u32 r = " << rword << " >> 1; const u32* tp = tab + (" << addr.str() << "); s" << i << " = 0u;\n";
+      if (nth == 1) o << "      s" << i << " = (u32)(r >= tp[0]);\n";
+      else if (nth == 2) o << "      { const uint2 t = *reinterpret_cast<const uint2*>(tp); s" << i << " = (u32)(r >= t.x) + (u32)(r >= t.y); }\n";
+      else
+        for (int k = 0; k < nth; k += 4) {
+          o << "      { const uint4 t = *reinterpret_cast<const uint4*>(tp + " << k << "); s" << i << " += (u32)(r >= t.x)";
+          if (k + 1 < nth) o << " + (u32)(r >= t.y)";
+          if (k + 2 < nth) o << " + (u32)(r >= t.z)";
+          if (k + 3 < nth) o << " + (u32)(r >= t.w)";
+          o << "; }\n";
+        }
+      o << "    }\n";
     } else {
-      o << "    { const u32 r = " << rr.str() << "; const u32 ad = " << addr.str() << "; s" << i << " = 0u;\n";
-      for (int k = 0; k + 1 < np.card; k += 4) {
-        o << "      { const uint4 t = *reinterpret_cast<const uint4*>(tab + ad + " << k << "u); s" << i
-          << " += (u32)(r >= t.x) + (u32)(r >= t.y) + (u32)(r >= t.z) + (u32)(r >= t.w); }\n";
+      // sign-bit form: rb = (r >> 1) | 2^31 (one funnel shift); rb - T has bit 31 set iff (r >> 1) >= T for every
+      // T in [0, 2^31]; two ALU ops per threshold (IADD + LEA.HI / SHF), no predicates, no moves
+      o << "    { const u32 rb = __funnelshift_r(" << rword << ", 1u, 1); const u32* tp = tab + (" << addr.str() << ");\n";
+      if (nth == 1) o << "      s" << i << " = (rb - tp[0]) >> 31;\n";
+      else if (nth == 2) o << "      { const uint2 t = *reinterpret_cast<const uint2*>(tp); s" << i << " = ((rb - t.x) >> 31) + ((rb - t.y) >> 31); }\n";
+      else {
+        o << "      s" << i << " = 0u;\n";
+        for (int k = 0; k < nth; k += 4) {
+          o << "      { const uint4 t = *reinterpret_cast<const uint4*>(tp + " << k << "); s" << i << " += ((rb - t.x) >> 31)";
+          if (k + 1 < nth) o << " + ((rb - t.y) >> 31)";
+          if (k + 2 < nth) o << " + ((rb - t.z) >> 31)";
+          if (k + 3 < nth) o << " + ((rb - t.w) >> 31)";
+          o << "; }\n";
+        }
       }
       o << "    }\n";
     }
-    if (!prune) o << "    chk += s" << i << ";\n";
+    if (!prune && !has_reader[i]) o << "    chk += s" << i << ";  // nothing else reads this state\n";
   }
   // query cell
   o << "    const u32 cell = 0u";
@@ -365,6 +394,8 @@ int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* q
     k = it->second;
   } else {
     SpecShape shp;
+    if (const char* e = getenv("BN_SPEC_THREADS")) shp.threads = atoi(e);
+    if (const char* e = getenv("BN_SPEC_MINB")) shp.min_blocks = atoi(e);
     uint32_t n_live = 0;
     const std::string src = gen_lw_source(*net, prg, query, n_query, qstride, ncell, prune, shp, &n_live);
     const std::string gkey = std::to_string(net->device) + "|" + src;
