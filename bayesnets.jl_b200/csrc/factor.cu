@@ -27,21 +27,29 @@ namespace bn {
 constexpr int MAXD = 48;  // loop dims (output + summed)
 constexpr int MAXF = 6;   // operands per contraction
 constexpr int MAX_NS = 2048;
+constexpr int NTHR = 256;
+constexpr int TLEV = 3;     // tile-offset table levels
+constexpr int TLEV_MAX = 256;
 
-// Loop dims are ordered [lo | j | t | s]:
-//   lo: leading output dims, Rlo entries, one per thread (per-operand offsets live in registers)
-//   j : next output dims, H = prod(card) <= 64 entries per tile (offset table in smem, tile independent)
-//   t : remaining output dims = the tile index (decomposed once per tile by warp 0, one dim per lane)
+// Loop dims are ordered [lo | j | t0 | t1 | t2 | s]:
+//   lo: leading output dims, Rlo entries = V vector columns of W outputs; a thread owns ONE column for the
+//       whole kernel, so its per-operand lo offsets live in registers
+//   j : H rows per tile; G = NTHR / V row groups work on rows g, g+G, g+2G, ...  Output dims the LEADING operand
+//       does not have are preferred here: rows that differ only in such a dim re-read the same leading-operand
+//       bytes back to back (L1 hits) instead of once per value a whole factor later (HBM re-read)
+//   t : remaining output dims = the tile index, split into <= 3 digit groups of <= 256 values each; per-operand
+//       offsets of every digit value are tabulated once per CTA (no per-tile divisions by dim, no barriers)
 //   s : summed dims, Ns joint states (offset table in smem), accumulated first-dim-fastest
 struct ContractParams {
-  int32_t nf, nlo, nj, nt, ns;
+  int32_t nf, nlo, nj, ns;
+  int32_t nt[TLEV], L[TLEV];       // dims / values per tile-digit group (L = 1 when unused)
   int32_t card[MAXD];
-  uint32_t tdiv[MAXD];             // for t dims: product of the cards of the lower t dims
-  long long fstride[MAXF][MAXD];   // element stride of each operand along each loop dim (0 = absent)
+  long long fstride[MAXF + 1][MAXD];  // element stride of each operand along each loop dim (0 = absent);
+                                      // row nf = the OUTPUT's strides (its rows need not be consecutive)
   const double* f[MAXF];
   double* out;
   long long Rlo, n_tiles;
-  int32_t H, Ns;
+  int32_t H, Ns, V, G;
   int32_t vstride_dim;  // loop dim used for 128-bit vectors (first lo dim or first s dim)
   int32_t fmode[MAXF];  // behaviour along that dim: 0 broadcast, 1 contiguous+aligned, 2 strided
 };
@@ -49,204 +57,240 @@ struct ContractParams {
 enum { VEC_NONE = 0, VEC_LO = 1, VEC_S = 2 };
 
 __device__ __forceinline__ double2 ld2(const double* __restrict__ f, long long off, int mode, long long stride) {
-  if (mode == 1) return *reinterpret_cast<const double2*>(f + off);
+  if (mode == 1) return __ldg(reinterpret_cast<const double2*>(f + off));
   if (mode == 0) { const double v = __ldg(f + off); return make_double2(v, v); }
   return make_double2(__ldg(f + off), __ldg(f + off + stride));
 }
 
-template <int NF, int VEC, bool SUM>
-__global__ void __launch_bounds__(256) contract_kernel(const ContractParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  long long* jOff = reinterpret_cast<long long*>(smem_raw);  // [NF][H]
-  long long* sOff = jOff + NF * p.H;                          // [NF][Ns]
-  __shared__ long long tileOff[MAXF];
-  const int tid = threadIdx.x;
-  const int nthr = blockDim.x;
-  constexpr int W = (VEC == VEC_LO) ? 2 : 1;  // outputs per thread step
-  constexpr int JU = 4;                        // tile rows in flight per thread
-
-  // ---- one-time tables: j offsets and summed-dim offsets
-  for (int j = tid; j < p.H; j += nthr) {
-    uint32_t r = (uint32_t)j;
+// offsets of every joint value of loop dims [d0, d0 + nd) for each operand -> tab[k * count + e]
+template <int NF>
+__device__ __forceinline__ void fill_table(long long* tab, int count, int d0, int nd, const ContractParams& p) {
+  for (int e = threadIdx.x; e < count; e += NTHR) {
+    uint32_t r = (uint32_t)e;
     long long off[NF];
 #pragma unroll
     for (int k = 0; k < NF; ++k) off[k] = 0;
-    for (int d = 0; d < p.nj; ++d) {
-      const uint32_t c = (uint32_t)p.card[p.nlo + d];
+    for (int d = 0; d < nd; ++d) {
+      const uint32_t c = (uint32_t)p.card[d0 + d];
       const uint32_t dg = r % c;
       r /= c;
 #pragma unroll
-      for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][p.nlo + d];
+      for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][d0 + d];
     }
 #pragma unroll
-    for (int k = 0; k < NF; ++k) jOff[k * p.H + j] = off[k];
+    for (int k = 0; k < NF; ++k) tab[k * count + e] = off[k];
   }
-  if (SUM) {
-    const int sbase = p.nlo + p.nj + p.nt;
-    for (int s = tid; s < p.Ns; s += nthr) {
-      uint32_t r = (uint32_t)s;
-      long long off[NF];
-#pragma unroll
-      for (int k = 0; k < NF; ++k) off[k] = 0;
-      for (int d = 0; d < p.ns; ++d) {
-        const uint32_t c = (uint32_t)p.card[sbase + d];
-        const uint32_t dg = r % c;
-        r /= c;
-#pragma unroll
-        for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][sbase + d];
-      }
-#pragma unroll
-      for (int k = 0; k < NF; ++k) sOff[k * p.Ns + s] = off[k];
-    }
-  }
-  // ---- per-thread lo offsets (hoisted when each thread owns a single lo)
-  const bool lo_fixed = p.Rlo <= (long long)nthr * W;
-  long long loOff0[NF];
+}
+
+// rows in flight per thread: keep NF * (loads per row) * JU independent loads within the register budget
+// (<= 8 double2 or <= 16 double in flight)
+template <int NF, int VEC, int NS>
+struct RowsInFlight {
+  static constexpr int per_row = NF * (NS > 1 ? (VEC == VEC_S ? NS / 2 : NS) : 1);
+  static constexpr int budget = (VEC == VEC_NONE) ? 16 : 12;
+  static constexpr int value = per_row * 4 <= budget ? 4 : (per_row * 2 <= budget ? 2 : 1);
+};
+
+// NS: 0 = plain product (nothing summed), 1 = run-time loop over p.Ns, 2..4 = that many joint states, unrolled
+template <int NF, int VEC, int NS>
+__global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contract_kernel(const ContractParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NS1 = NF + 1;  // table slots: the operands, then the output
+  long long* jOff = reinterpret_cast<long long*>(smem_raw);  // [NF+1][H]
+  long long* sOff = jOff + NS1 * p.H;                         // [NF][Ns]
+  long long* tOff0 = sOff + NF * p.Ns;                        // [NF+1][L0]
+  long long* tOff1 = tOff0 + NS1 * p.L[0];
+  long long* tOff2 = tOff1 + NS1 * p.L[1];
+  const int tid = threadIdx.x;
+  constexpr int W = (VEC == VEC_LO) ? 2 : 1;  // outputs per thread per row
+  constexpr int JU = RowsInFlight<NF, VEC, NS>::value;
+  constexpr bool SUM = NS != 0;
+
+  // ---- one-time tables
+  const int jb = p.nlo, t0b = jb + p.nj, t1b = t0b + p.nt[0], t2b = t1b + p.nt[1], sb = t2b + p.nt[2];
+  fill_table<NS1>(jOff, p.H, jb, p.nj, p);
+  if (SUM) fill_table<NF>(sOff, p.Ns, sb, p.ns, p);
+  fill_table<NS1>(tOff0, p.L[0], t0b, p.nt[0], p);
+  fill_table<NS1>(tOff1, p.L[1], t1b, p.nt[1], p);
+  fill_table<NS1>(tOff2, p.L[2], t2b, p.nt[2], p);
+  // ---- this thread's column
+  const int V = p.V, G = p.G;
+  const int col = tid % V, g = tid / V;
+  long long loOff[NS1];
   {
-    uint32_t r = (uint32_t)tid * W;
+    uint32_t r = (uint32_t)col * W;
 #pragma unroll
-    for (int k = 0; k < NF; ++k) loOff0[k] = 0;
+    for (int k = 0; k < NS1; ++k) loOff[k] = 0;
     for (int d = 0; d < p.nlo; ++d) {
       const uint32_t c = (uint32_t)p.card[d];
       const uint32_t dg = r % c;
       r /= c;
 #pragma unroll
-      for (int k = 0; k < NF; ++k) loOff0[k] += (long long)dg * p.fstride[k][d];
+      for (int k = 0; k < NS1; ++k) loOff[k] += (long long)dg * p.fstride[k][d];
     }
   }
-  const int tb = p.nlo + p.nj;
-  const long long vst_lo = p.fstride[0][0];
+  __syncthreads();
+  if (g >= G) return;  // threads beyond G * V columns have no work (non power-of-two column counts)
+  const int sd = p.vstride_dim;
+  const int ns_rt = (NS == 1) ? p.Ns : NS;
 
+  // tiles are dealt round-robin (all CTAs sweep one moving window of memory: measured 77% vs 54% of HBM peak
+  // for contiguous per-CTA chunks, which open ~1200 DRAM streams at once); the three tile digits advance by the
+  // grid size as a mixed-radix add, so there are no divisions in the loop
+  uint32_t i0, i1, i2, s0, s1, s2;
+  {
+    uint32_t t = blockIdx.x;
+    i0 = t % (uint32_t)p.L[0]; t /= (uint32_t)p.L[0];
+    i1 = t % (uint32_t)p.L[1]; i2 = t / (uint32_t)p.L[1];
+    t = gridDim.x;
+    s0 = t % (uint32_t)p.L[0]; t /= (uint32_t)p.L[0];
+    s1 = t % (uint32_t)p.L[1]; s2 = t / (uint32_t)p.L[1];
+  }
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    __syncthreads();  // tables ready (first pass) / previous tile finished with tileOff
-    if (tid < 32) {
-      long long off[NF];
+    long long base[NS1];
 #pragma unroll
-      for (int k = 0; k < NF; ++k) off[k] = 0;
-      for (int d = tid; d < p.nt; d += 32) {
-        const uint32_t dg = ((uint32_t)tile / p.tdiv[d]) % (uint32_t)p.card[tb + d];
-#pragma unroll
-        for (int k = 0; k < NF; ++k) off[k] += (long long)dg * p.fstride[k][tb + d];
-      }
-#pragma unroll
-      for (int k = 0; k < NF; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) off[k] += __shfl_xor_sync(0xffffffffu, off[k], o);
-        if (tid == 0) tileOff[k] = off[k];
-      }
-    }
-    __syncthreads();
-    double* otile = p.out + tile * (long long)p.H * p.Rlo;
+    for (int k = 0; k < NS1; ++k)
+      base[k] = loOff[k] + tOff0[k * p.L[0] + i0] + tOff1[k * p.L[1] + i1] + tOff2[k * p.L[2] + i2];
+    i0 += s0;
+    i1 += s1;
+    if (i0 >= (uint32_t)p.L[0]) { i0 -= (uint32_t)p.L[0]; ++i1; }
+    i2 += s2;
+    if (i1 >= (uint32_t)p.L[1]) { i1 -= (uint32_t)p.L[1]; ++i2; }
+    double* ocol = p.out + base[NF];
 
-    for (long long lo = (long long)tid * W; lo < p.Rlo; lo += (long long)nthr * W) {
-      long long lt[NF];
-      if (lo_fixed) {
+    for (int j0 = g; j0 < p.H; j0 += G * JU) {
+      long long off[JU][NF], ooff[JU];
 #pragma unroll
-        for (int k = 0; k < NF; ++k) lt[k] = loOff0[k] + tileOff[k];
-      } else {
-        uint32_t r = (uint32_t)lo;
+      for (int u = 0; u < JU; ++u) {
+        const int j = (j0 + u * G < p.H) ? j0 + u * G : j0;  // clamp: redundant load, store skipped below
 #pragma unroll
-        for (int k = 0; k < NF; ++k) lt[k] = tileOff[k];
-        for (int d = 0; d < p.nlo; ++d) {
-          const uint32_t c = (uint32_t)p.card[d];
-          const uint32_t dg = r % c;
-          r /= c;
-#pragma unroll
-          for (int k = 0; k < NF; ++k) lt[k] += (long long)dg * p.fstride[k][d];
-        }
+        for (int k = 0; k < NF; ++k) off[u][k] = base[k] + jOff[k * p.H + j];
+        ooff[u] = jOff[NF * p.H + j];
       }
-      for (int j0 = 0; j0 < p.H; j0 += JU) {
-        long long base[JU][NF];
+      if constexpr (VEC == VEC_LO) {
+        double2 acc[JU];
+        if constexpr (!SUM) {
+          double2 v[JU][NF];
 #pragma unroll
-        for (int u = 0; u < JU; ++u) {
-          const int j = (j0 + u < p.H) ? j0 + u : p.H - 1;
+          for (int u = 0; u < JU; ++u)
 #pragma unroll
-          for (int k = 0; k < NF; ++k) base[u][k] = lt[k] + jOff[k * p.H + j];
-        }
-        if (VEC == VEC_LO) {
-          double2 acc[JU];
-          if (!SUM) {
-            double2 v[JU][NF];
+            for (int k = 0; k < NF; ++k) v[u][k] = ld2(p.f[k], off[u][k], p.fmode[k], p.fstride[k][0]);
+#pragma unroll
+          for (int u = 0; u < JU; ++u) {
+            acc[u] = v[u][0];
+#pragma unroll
+            for (int k = 1; k < NF; ++k) { acc[u].x *= v[u][k].x; acc[u].y *= v[u][k].y; }
+          }
+        } else if constexpr (NS > 1) {
+          double2 v[NS][JU][NF];
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int u = 0; u < JU; ++u)
 #pragma unroll
-              for (int k = 0; k < NF; ++k) v[u][k] = ld2(p.f[k], base[u][k], p.fmode[k], p.fstride[k][0]);
-#pragma unroll
-            for (int u = 0; u < JU; ++u) {
-              acc[u] = v[u][0];
-#pragma unroll
-              for (int k = 1; k < NF; ++k) { acc[u].x *= v[u][k].x; acc[u].y *= v[u][k].y; }
-            }
-          } else {
-            for (int s = 0; s < p.Ns; ++s) {
-#pragma unroll
-              for (int u = 0; u < JU; ++u) {
-                double2 pr = ld2(p.f[0], base[u][0] + sOff[s], p.fmode[0], p.fstride[0][0]);
-#pragma unroll
-                for (int k = 1; k < NF; ++k) {
-                  const double2 x = ld2(p.f[k], base[u][k] + sOff[k * p.Ns + s], p.fmode[k], p.fstride[k][0]);
-                  pr.x *= x.x; pr.y *= x.y;
-                }
-                if (s == 0) acc[u] = pr; else { acc[u].x += pr.x; acc[u].y += pr.y; }
-              }
-            }
-          }
+              for (int k = 0; k < NF; ++k)
+                v[s][u][k] = ld2(p.f[k], off[u][k] + sOff[k * NS + s], p.fmode[k], p.fstride[k][0]);
 #pragma unroll
           for (int u = 0; u < JU; ++u)
-            if (j0 + u < p.H) *reinterpret_cast<double2*>(otile + (long long)(j0 + u) * p.Rlo + lo) = acc[u];
-        } else if (VEC == VEC_S) {
-          // SUM is implied; pairs run along the first summed dim
-          const int sd = p.vstride_dim;
-          double acc[JU];
-          for (int s = 0; s < p.Ns; s += 2) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+              double2 pr = v[s][u][0];
+#pragma unroll
+              for (int k = 1; k < NF; ++k) { pr.x *= v[s][u][k].x; pr.y *= v[s][u][k].y; }
+              if (s == 0) acc[u] = pr; else { acc[u].x += pr.x; acc[u].y += pr.y; }
+            }
+        } else {
+#pragma unroll 4
+          for (int s = 0; s < ns_rt; ++s) {
 #pragma unroll
             for (int u = 0; u < JU; ++u) {
-              double2 pr = ld2(p.f[0], base[u][0] + sOff[s], p.fmode[0], p.fstride[0][sd]);
+              double2 pr = ld2(p.f[0], off[u][0] + sOff[s], p.fmode[0], p.fstride[0][0]);
 #pragma unroll
               for (int k = 1; k < NF; ++k) {
-                const double2 x = ld2(p.f[k], base[u][k] + sOff[k * p.Ns + s], p.fmode[k], p.fstride[k][sd]);
+                const double2 x = ld2(p.f[k], off[u][k] + sOff[k * ns_rt + s], p.fmode[k], p.fstride[k][0]);
+                pr.x *= x.x; pr.y *= x.y;
+              }
+              if (s == 0) acc[u] = pr; else { acc[u].x += pr.x; acc[u].y += pr.y; }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < JU; ++u)
+          if (j0 + u * G < p.H) *reinterpret_cast<double2*>(ocol + ooff[u]) = acc[u];
+      } else if constexpr (VEC == VEC_S) {
+        // pairs run along the first summed dim (contiguous in the leading operand); Ns is even
+        double acc[JU];
+        if constexpr (NS > 1) {
+          constexpr int NP = NS / 2;
+          double2 v[NP][JU][NF];
+#pragma unroll
+          for (int s = 0; s < NP; ++s)
+#pragma unroll
+            for (int u = 0; u < JU; ++u)
+#pragma unroll
+              for (int k = 0; k < NF; ++k)
+                v[s][u][k] = ld2(p.f[k], off[u][k] + sOff[k * NS + 2 * s], p.fmode[k], p.fstride[k][sd]);
+#pragma unroll
+          for (int u = 0; u < JU; ++u)
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+              double2 pr = v[s][u][0];
+#pragma unroll
+              for (int k = 1; k < NF; ++k) { pr.x *= v[s][u][k].x; pr.y *= v[s][u][k].y; }
+              acc[u] = (s == 0) ? pr.x : acc[u] + pr.x;
+              acc[u] += pr.y;
+            }
+        } else {
+#pragma unroll 4
+          for (int s = 0; s < ns_rt; s += 2) {
+#pragma unroll
+            for (int u = 0; u < JU; ++u) {
+              double2 pr = ld2(p.f[0], off[u][0] + sOff[s], p.fmode[0], p.fstride[0][sd]);
+#pragma unroll
+              for (int k = 1; k < NF; ++k) {
+                const double2 x = ld2(p.f[k], off[u][k] + sOff[k * ns_rt + s], p.fmode[k], p.fstride[k][sd]);
                 pr.x *= x.x; pr.y *= x.y;
               }
               acc[u] = (s == 0) ? pr.x : acc[u] + pr.x;
               acc[u] += pr.y;
             }
           }
+        }
+#pragma unroll
+        for (int u = 0; u < JU; ++u)
+          if (j0 + u * G < p.H) ocol[ooff[u]] = acc[u];
+      } else {
+        double acc[JU];
+        if constexpr (!SUM) {
+          double v[JU][NF];
 #pragma unroll
           for (int u = 0; u < JU; ++u)
-            if (j0 + u < p.H) otile[(long long)(j0 + u) * p.Rlo + lo] = acc[u];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) v[u][k] = __ldg(p.f[k] + off[u][k]);
+#pragma unroll
+          for (int u = 0; u < JU; ++u) {
+            acc[u] = v[u][0];
+#pragma unroll
+            for (int k = 1; k < NF; ++k) acc[u] *= v[u][k];
+          }
         } else {
-          double acc[JU];
-          if (!SUM) {
-            double v[JU][NF];
-#pragma unroll
-            for (int u = 0; u < JU; ++u)
-#pragma unroll
-              for (int k = 0; k < NF; ++k) v[u][k] = __ldg(p.f[k] + base[u][k]);
+#pragma unroll 4
+          for (int s = 0; s < ns_rt; ++s) {
 #pragma unroll
             for (int u = 0; u < JU; ++u) {
-              acc[u] = v[u][0];
+              double pr = __ldg(p.f[0] + off[u][0] + sOff[s]);
 #pragma unroll
-              for (int k = 1; k < NF; ++k) acc[u] *= v[u][k];
-            }
-          } else {
-            for (int s = 0; s < p.Ns; ++s) {
-#pragma unroll
-              for (int u = 0; u < JU; ++u) {
-                double pr = __ldg(p.f[0] + base[u][0] + sOff[s]);
-#pragma unroll
-                for (int k = 1; k < NF; ++k) pr *= __ldg(p.f[k] + base[u][k] + sOff[k * p.Ns + s]);
-                acc[u] = (s == 0) ? pr : acc[u] + pr;
-              }
+              for (int k = 1; k < NF; ++k) pr *= __ldg(p.f[k] + off[u][k] + sOff[k * ns_rt + s]);
+              acc[u] = (s == 0) ? pr : acc[u] + pr;
             }
           }
-#pragma unroll
-          for (int u = 0; u < JU; ++u)
-            if (j0 + u < p.H) otile[(long long)(j0 + u) * p.Rlo + lo] = acc[u];
         }
+#pragma unroll
+        for (int u = 0; u < JU; ++u)
+          if (j0 + u * G < p.H) ocol[ooff[u]] = acc[u];
       }
     }
   }
-  (void)vst_lo;
 }
 
 // ---- normalize!: two launches -- (1) per-CTA partial sums, last CTA folds them in a fixed order,
@@ -314,22 +358,46 @@ static int find_dim(const std::vector<int32_t>& dims, int32_t d) {
   return -1;
 }
 
-template <int NF, int VEC, bool SUM>
-static int32_t launch_contract_v(const ContractParams& p, int grid, size_t smem, cudaStream_t s) {
-  BN_CUDA_TRY(cudaFuncSetAttribute(contract_kernel<NF, VEC, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  contract_kernel<NF, VEC, SUM><<<grid, 256, smem, s>>>(p);
+template <int NF, int VEC, int NS>
+static int32_t launch_contract_v(const ContractParams& p, int sm_count, size_t smem, cudaStream_t s) {
+  static thread_local int occ = 0;  // resident CTAs per SM of this instantiation (per host thread)
+  if (occ == 0) {
+    BN_CUDA_TRY(cudaFuncSetAttribute(contract_kernel<NF, VEC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    BN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, contract_kernel<NF, VEC, NS>, NTHR, 16 * 1024));
+    if (occ < 1) occ = 1;
+  }
+  BN_REQUIRE(smem <= 64 * 1024, BN_UNSUPPORTED, "contraction offset tables need %zu bytes of shared memory", smem);
+  // persistent grid: every resident CTA slot gets tiles round-robin
+  const int grid = (int)std::min<long long>(p.n_tiles, (long long)sm_count * occ);
+  contract_kernel<NF, VEC, NS><<<grid, NTHR, smem, s>>>(p);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   return BN_OK;
 }
 
+template <int NF, int VEC>
+static int32_t launch_contract_ns(const ContractParams& p, int ns_mode, int sm_count, size_t smem, cudaStream_t s) {
+  if constexpr (VEC == VEC_S) {  // Ns is even here; 3 cannot occur
+    if (ns_mode == 2) return launch_contract_v<NF, VEC, 2>(p, sm_count, smem, s);
+    if constexpr (NF <= 3) {
+      if (ns_mode == 4) return launch_contract_v<NF, VEC, 4>(p, sm_count, smem, s);
+    }
+    return launch_contract_v<NF, VEC, 1>(p, sm_count, smem, s);
+  }
+  if (ns_mode == 0) return launch_contract_v<NF, VEC, 0>(p, sm_count, smem, s);
+  if constexpr (NF <= 3) {
+    if (ns_mode == 2) return launch_contract_v<NF, VEC, 2>(p, sm_count, smem, s);
+    if (ns_mode == 3) return launch_contract_v<NF, VEC, 3>(p, sm_count, smem, s);
+    if (ns_mode == 4) return launch_contract_v<NF, VEC, 4>(p, sm_count, smem, s);
+  }
+  return launch_contract_v<NF, VEC, 1>(p, sm_count, smem, s);
+}
+
 template <int NF>
-static int32_t launch_contract_nf(const ContractParams& p, int vec, bool sum, int grid, size_t smem, cudaStream_t s) {
-  if (vec == VEC_S) return launch_contract_v<NF, VEC_S, true>(p, grid, smem, s);
-  if (vec == VEC_LO) return sum ? launch_contract_v<NF, VEC_LO, true>(p, grid, smem, s)
-                                : launch_contract_v<NF, VEC_LO, false>(p, grid, smem, s);
-  return sum ? launch_contract_v<NF, VEC_NONE, true>(p, grid, smem, s)
-             : launch_contract_v<NF, VEC_NONE, false>(p, grid, smem, s);
+static int32_t launch_contract_nf(const ContractParams& p, int vec, int ns_mode, int sm_count, size_t smem, cudaStream_t s) {
+  if (vec == VEC_S) return launch_contract_ns<NF, VEC_S>(p, ns_mode, sm_count, smem, s);
+  if (vec == VEC_LO) return launch_contract_ns<NF, VEC_LO>(p, ns_mode, sm_count, smem, s);
+  return launch_contract_ns<NF, VEC_NONE>(p, ns_mode, sm_count, smem, s);
 }
 
 // out[out_dims] = sum_{sum_dims} prod_k ops[k]; out_dims/out_card give the output layout (column-major),
@@ -350,36 +418,14 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
   for (int c : sum_card) Ns *= c;
   BN_REQUIRE(Ns <= MAX_NS, BN_UNSUPPORTED, "summing out %lld joint states at once (max %d)", Ns, MAX_NS);
   const DevProps& dp = dev_props(device);
-  // lo = shortest prefix of the output dims with >= 256 entries
-  int nlo = 0;
-  long long Rlo = 1;
-  while (nlo < no && Rlo < 256) { Rlo *= out_card[nlo]; ++nlo; }
-  BN_REQUIRE(Rlo < (1ll << 31), BN_UNSUPPORTED, "leading output dims too large");
-  // j = following dims while the tile stays <= 64 rows and >= 8 tiles per SM remain
-  int nj = 0;
-  long long H = 1;
-  const long long rest = Nout / Rlo;
-  while (nlo + nj < no) {
-    const long long h2 = H * out_card[nlo + nj];
-    if (h2 > 64 || rest / h2 < (long long)dp.sm_count * 8) break;
-    H = h2; ++nj;
-  }
-  const int nt = no - nlo - nj;
-  const long long n_tiles = rest / H;
-  BN_REQUIRE(n_tiles < (1ll << 31), BN_UNSUPPORTED, "too many tiles");
-  p.nlo = nlo; p.nj = nj; p.nt = nt;
-  p.Rlo = Rlo; p.H = (int)H; p.n_tiles = n_tiles; p.Ns = (int)Ns;
-  for (int d = 0; d < no; ++d) p.card[d] = out_card[d];
-  for (int d = 0; d < ns; ++d) p.card[no + d] = sum_card[d];
-  {
-    long long pr = 1;
-    for (int d = 0; d < nt; ++d) { p.tdiv[d] = (uint32_t)pr; pr *= out_card[nlo + nj + d]; }
-  }
+
+  // strides of every operand along the output dims and the summed dims; the largest operand leads
+  std::vector<std::vector<long long>> st(nf, std::vector<long long>(no + ns, 0));
   int lead = 0;
   long long lead_len = -1;
   for (int k = 0; k < nf; ++k) {
     p.f[k] = ops[k].ptr;
-    long long st = 1;
+    long long acc = 1;
     for (size_t i = 0; i < ops[k].dims.size(); ++i) {
       int pos = find_dim(out_dims, ops[k].dims[i]);
       if (pos < 0) {
@@ -387,34 +433,88 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
         BN_REQUIRE(pos >= 0, BN_BAD_ARG, "operand dim %d is neither kept nor summed", ops[k].dims[i]);
         pos += no;
       }
-      p.fstride[k][pos] = st;
-      st *= ops[k].card[i];
+      st[k][pos] = acc;
+      acc *= ops[k].card[i];
     }
-    if (st > lead_len) { lead_len = st; lead = k; }
+    if (acc > lead_len) { lead_len = acc; lead = k; }
   }
   // vector dim: the first summed dim if the largest operand is contiguous there, else the first output dim
-  int vec = VEC_NONE, vdim = 0;
-  if (ns >= 1 && (sum_card[0] % 2) == 0 && p.fstride[lead][no] == 1) { vec = VEC_S; vdim = no; }
-  else if (no >= 1 && (out_card[0] % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0) { vec = VEC_LO; vdim = 0; }
+  int vec = VEC_NONE;
+  if (ns >= 1 && (sum_card[0] % 2) == 0 && st[lead][no] == 1) vec = VEC_S;
+  else if (no >= 1 && (out_card[0] % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0) vec = VEC_LO;
+  const int W = vec == VEC_LO ? 2 : 1;
+
+  // lo = longest prefix of the output dims whose vector columns fit one CTA pass
+  int nlo = 0;
+  long long Rlo = 1;
+  while (nlo < no && Rlo * out_card[nlo] / W <= NTHR) { Rlo *= out_card[nlo]; ++nlo; }
+  if (nlo == 0 && no > 0) {  // first dim alone is wider than a CTA pass: cannot happen for card <= 255 with W >= 1
+    Rlo = out_card[0]; nlo = 1;
+  }
+  BN_REQUIRE(Rlo / W <= NTHR, BN_UNSUPPORTED, "leading output dim too large (%lld)", Rlo);
+  const int V = (int)std::max<long long>(1, Rlo / W);
+  const int G = NTHR / V;
+  // loop-dim order [lo | j | t | s] as positions into out_dims.  j: first the output dims the leading operand
+  // lacks (see the kernel comment), then the dims right after lo, until every row group has ~4 rows per tile.
+  std::vector<int> order;
+  for (int i = 0; i < nlo; ++i) order.push_back(i);
+  std::vector<char> taken(no, 0);
+  long long H = 1;
+  int nj = 0;
+  const long long h_target = 4ll * G;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = nlo; i < no; ++i) {
+      if (taken[i] || (pass == 0 && st[lead][i] != 0)) continue;
+      if (H >= h_target || H * out_card[i] > 1024) continue;
+      taken[i] = 1; order.push_back(i); H *= out_card[i]; ++nj;
+    }
+  // t = the rest in ascending order, in <= 3 digit groups of <= 256 values
+  std::vector<int> rest;
+  for (int i = nlo; i < no; ++i) if (!taken[i]) rest.push_back(i);
+  size_t ri = 0;
+  long long n_tiles = 1;
+  for (int l = 0; l < TLEV; ++l) {
+    p.nt[l] = 0; p.L[l] = 1;
+    while (ri < rest.size() && (long long)p.L[l] * out_card[rest[ri]] <= TLEV_MAX) {
+      p.L[l] *= out_card[rest[ri]]; ++p.nt[l]; order.push_back(rest[ri]); ++ri;
+    }
+    n_tiles *= p.L[l];
+  }
+  BN_REQUIRE(ri == rest.size(), BN_UNSUPPORTED, "output too large for the tile tables (%lld entries)", Nout);
+  BN_REQUIRE(n_tiles < (1ll << 31), BN_UNSUPPORTED, "too many tiles");
+  p.nlo = nlo; p.nj = nj;
+  p.Rlo = Rlo; p.H = (int)H; p.n_tiles = n_tiles; p.Ns = (int)Ns; p.V = V; p.G = G;
+  std::vector<long long> ost(no, 1);  // column-major strides of the output
+  for (int i = 1; i < no; ++i) ost[i] = ost[i - 1] * out_card[i - 1];
+  for (int i = 0; i < no; ++i) {
+    p.card[i] = out_card[order[i]];
+    for (int k = 0; k < nf; ++k) p.fstride[k][i] = st[k][order[i]];
+    p.fstride[nf][i] = ost[order[i]];
+  }
+  for (int i = 0; i < ns; ++i) {
+    p.card[no + i] = sum_card[i];
+    for (int k = 0; k < nf; ++k) p.fstride[k][no + i] = st[k][no + i];
+    p.fstride[nf][no + i] = 0;
+  }
+  const int vdim = vec == VEC_S ? no : 0;
   p.vstride_dim = vdim;
   if (vec != VEC_NONE) {
     for (int k = 0; k < nf; ++k) {
-      const long long st = p.fstride[k][vdim];
+      const long long sv = p.fstride[k][vdim];
       const bool aligned = (reinterpret_cast<uintptr_t>(p.f[k]) % 16) == 0;
-      p.fmode[k] = st == 0 ? 0 : ((st == 1 && aligned) ? 1 : 2);
+      p.fmode[k] = sv == 0 ? 0 : ((sv == 1 && aligned) ? 1 : 2);
     }
   }
-  const int grid = (int)std::min<long long>(n_tiles, (long long)dp.sm_count * 8);
-  const size_t smem = (size_t)nf * ((size_t)H + (size_t)Ns) * sizeof(long long);
+  const size_t smem = ((size_t)(nf + 1) * ((size_t)H + (size_t)p.L[0] + p.L[1] + p.L[2]) + (size_t)nf * (size_t)Ns) * sizeof(long long);
   cudaStream_t s = tl_stream;
-  const bool sum = ns > 0;
+  const int ns_mode = ns == 0 ? 0 : ((Ns >= 2 && Ns <= 4) ? (int)Ns : 1);
   switch (nf) {
-    case 1: return launch_contract_nf<1>(p, vec, sum, grid, smem, s);
-    case 2: return launch_contract_nf<2>(p, vec, sum, grid, smem, s);
-    case 3: return launch_contract_nf<3>(p, vec, sum, grid, smem, s);
-    case 4: return launch_contract_nf<4>(p, vec, sum, grid, smem, s);
-    case 5: return launch_contract_nf<5>(p, vec, sum, grid, smem, s);
-    default: return launch_contract_nf<6>(p, vec, sum, grid, smem, s);
+    case 1: return launch_contract_nf<1>(p, vec, ns_mode, dp.sm_count, smem, s);
+    case 2: return launch_contract_nf<2>(p, vec, ns_mode, dp.sm_count, smem, s);
+    case 3: return launch_contract_nf<3>(p, vec, ns_mode, dp.sm_count, smem, s);
+    case 4: return launch_contract_nf<4>(p, vec, ns_mode, dp.sm_count, smem, s);
+    case 5: return launch_contract_nf<5>(p, vec, ns_mode, dp.sm_count, smem, s);
+    default: return launch_contract_nf<6>(p, vec, ns_mode, dp.sm_count, smem, s);
   }
 }
 
