@@ -30,22 +30,63 @@ def build_cases(bn, k, nrot, rng):
             "A": mk(range(k)), "B12": mk(range(0, k, 2)), "A23": mk(range(k - 1)), "B23": mk(range(1, k)),
             "Bp": mk(perm), "Eb": mk([0] + list(range(k - 12, k - 1))), "Ec": mk([0] + list(range(1, 12))),
         })
+    # ops go straight through the C ABI on handles (what a `ccall` does); wrapping every result in a Python Factor
+    # costs ~20 us of interpreter time per op, which at 35-60 us per kernel would make the HOST the bottleneck
+    from bayesnets_jl_b200 import _lib
+    import ctypes as C
+    L = _lib.lib()
+
+    class Raw:
+        """owns one bn_factor_t; freed (stream-ordered) when dropped"""
+        __slots__ = ("h",)
+
+        def __init__(self, h):
+            self.h = h
+
+        def __del__(self):
+            L.bn_factor_free(self.h)
+
+    def ids(*dd):
+        a = np.array([bn.factors.var_id(names[i]) for i in dd], np.int32)
+        return a, _lib.ptr(a, _lib.i32p), C.c_int32(len(dd))
+
+    def product(a, b):
+        out = _lib.h64(0)
+        _lib.check(L.bn_factor_product(_lib.h64(a.handle), _lib.h64(b.handle), C.byref(out)))
+        return Raw(out)
+
+    def fsum(a, idp):
+        out = _lib.h64(0)
+        _lib.check(L.bn_factor_sum(_lib.h64(a.handle), idp[1], idp[2], C.byref(out)))
+        return Raw(out)
+
+    def elim(fs, idp):
+        hs = (_lib.h64 * len(fs))(*[f.handle for f in fs])
+        out = _lib.h64(0)
+        _lib.check(L.bn_factor_eliminate(hs, C.c_int32(len(fs)), idp[1], idp[2], C.byref(out)))
+        return Raw(out)
+
+    def norm(a):
+        _lib.check(L.bn_factor_normalize(_lib.h64(a.handle), C.c_int32(1)))
+        return None
+
+    d0, dk, dm, d4 = ids(0), ids(k - 1), ids(k // 2), ids(1, 5, 11, k - 2)
     cases = [
-        ("P1 2^%d x 2^%d interleaved" % (k, k // 2), lambda s: s["A"] * s["B12"], 8 * (2 * N + (1 << (k // 2)))),
-        ("P2 dims1..k-1 x dims2..k", lambda s: s["A23"] * s["B23"], 8 * (N + N)),
-        ("P3 2^%d x 2^%d permuted" % (k, k), lambda s: s["A"] * s["Bp"], 8 * 3 * N),
-        ("S1 sum innermost", lambda s: s["A"].sum(names[0]), 8 * (N + N // 2)),
-        ("S2 sum outermost", lambda s: s["A"].sum(names[k - 1]), 8 * (N + N // 2)),
-        ("S3 sum middle", lambda s: s["A"].sum(names[k // 2]), 8 * (N + N // 2)),
-        ("S4 sum 4 dims", lambda s: s["A"].sum([names[1], names[5], names[11], names[k - 2]]), 8 * (N + N // 16)),
-        ("N1 normalize", lambda s: s["A"].normalize_(), 8 * 3 * N),
-        ("E1 fused eliminate 3 factors", lambda s: bn.eliminate([s["A"], s["Eb"], s["Ec"]], names[0]),
+        ("P1 2^%d x 2^%d interleaved" % (k, k // 2), lambda s: product(s["A"], s["B12"]), 8 * (2 * N + (1 << (k // 2)))),
+        ("P2 dims1..k-1 x dims2..k", lambda s: product(s["A23"], s["B23"]), 8 * (N + N)),
+        ("P3 2^%d x 2^%d permuted" % (k, k), lambda s: product(s["A"], s["Bp"]), 8 * 3 * N),
+        ("S1 sum innermost", lambda s: fsum(s["A"], d0), 8 * (N + N // 2)),
+        ("S2 sum outermost", lambda s: fsum(s["A"], dk), 8 * (N + N // 2)),
+        ("S3 sum middle", lambda s: fsum(s["A"], dm), 8 * (N + N // 2)),
+        ("S4 sum 4 dims", lambda s: fsum(s["A"], d4), 8 * (N + N // 16)),
+        ("N1 normalize", lambda s: norm(s["A"]), 8 * 3 * N),
+        ("E1 fused eliminate 3 factors", lambda s: elim([s["A"], s["Eb"], s["Ec"]], d0),
          8 * (N + 2 * (1 << 12) + N // 2)),
     ]
     return sets, cases
 
 
-def run(bn, torch, device=0, k=24, reps=12, nrot=3, only=None):
+def run(bn, torch, device=0, k=24, reps=24, nrot=3, only=None):
     from bayesnets_jl_b200 import _lib
     rng = np.random.default_rng(0)
     sets, cases = build_cases(bn, k, nrot, rng)
@@ -75,25 +116,28 @@ def run(bn, torch, device=0, k=24, reps=12, nrot=3, only=None):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         keep = []
+        import time
+        t0 = time.perf_counter()
         e0.record()
         for it in range(reps):
             keep.append(fn(sets[it % nrot]))
             if len(keep) > 2:
                 keep.pop(0)  # frees go back to the stream-ordered pool; no sync
         e1.record()
+        host_ms = (time.perf_counter() - t0) * 1e3 / reps
         torch.cuda.synchronize()
         del keep
         batch_ms = e0.elapsed_time(e1) / reps
         out.append({"case": name, "bytes": nbytes, "call_ms": round(float(np.mean(call)), 4),
                     "call_GBs": round(nbytes / np.mean(call) / 1e6, 1), "batch_ms": round(batch_ms, 4),
-                    "batch_GBs": round(nbytes / batch_ms / 1e6, 1)})
+                    "batch_GBs": round(nbytes / batch_ms / 1e6, 1), "host_ms_per_op": round(host_ms, 4)})
     return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--k", type=int, default=24)
-    ap.add_argument("--reps", type=int, default=12)
+    ap.add_argument("--reps", type=int, default=24)
     ap.add_argument("--only", default=None)
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
@@ -107,6 +151,6 @@ if __name__ == "__main__":
     for r in res:
         r["batch_frac"] = round(r["batch_GBs"] / peak, 3)
         print(f"{r['case']:34s} call {r['call_ms']:.4f} ms {r['call_GBs']:8.1f} GB/s | batch {r['batch_ms']:.4f} ms "
-              f"{r['batch_GBs']:8.1f} GB/s  ({r['batch_frac']:.3f} of {peak:.0f})")
+              f"{r['batch_GBs']:8.1f} GB/s  ({r['batch_frac']:.3f} of {peak:.0f})  host {r['host_ms_per_op']:.4f} ms/op")
     if a.json:
         json.dump(res, open(a.json, "w"), indent=1)
