@@ -1,0 +1,89 @@
+"""World-size-2 `gloo` test of the multi-GPU plumbing on CPU.
+
+The sharding contract is host logic: rank g runs particle ids [g*N//G, (g+1)*N//G) of ONE global Philox counter space
+and the ranks all-reduce the (cells + 2) doubles.  Here each rank's shard is computed by the oracle (the GPU kernels are
+bit-identical to it per tests/test_gpu_sampling.py), reduced with the product's own `allreduce_sum_` over gloo, and
+compared with the single-process result: integer (unweighted) counts must match exactly, weighted sums to 1e-12.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch
+        import torch.distributed as dist
+        import bayesnets_jl_b200 as bn
+        from bayesnets_jl_b200.distributed import allreduce_sum_, shard_range
+        from oracle import capi
+        from oracle.factors_np import FlatNet
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        net = bn.rand_discrete_bn(40, 3, 4, seed=5)
+        lay = bn.flatten(net)
+        on = FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
+        evidence, query = {"N3": 1, "N20": 2}, ["N7", "N33"]
+        ev, qi = lay.evidence_vector(evidence), lay.query_indices(query)
+        first, count = shard_range(n_total, rank, world)
+        c, sw, sw2 = capi.lw_infer(on, ev, qi, count, seed=9, first=first, mode=capi.DEVICE_SPEC)
+        t = torch.from_numpy(np.concatenate([c.ravel(order="F"), [sw, sw2]]))
+        allreduce_sum_(t)
+        # Gibbs: chains sharded the same way, integer counts
+        gfirst, gcount = shard_range(64, rank, world)
+        gc, _ = capi.gibbs_infer(on, ev, qi, gcount, 300, 100, 3, seed=4, first_chain=gfirst)
+        g = torch.from_numpy(gc.astype(np.float64).ravel(order="F").copy())
+        allreduce_sum_(g)
+        if rank == 0:
+            q.put((t.numpy().copy(), g.numpy().copy()))
+        dist.destroy_process_group()
+    except Exception as e:  # surface worker failures in the parent
+        if rank == 0:
+            q.put(e)
+        raise
+
+
+def test_two_rank_gloo_allreduce_equals_single_stream():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import bayesnets_jl_b200 as bn
+    from oracle import capi
+    from oracle.factors_np import FlatNet
+    capi.build()
+    n_total = 100_001  # odd: ragged shards
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if isinstance(got, Exception):
+        raise got
+    lw2, g2 = got
+    net = bn.rand_discrete_bn(40, 3, 4, seed=5)
+    lay = bn.flatten(net)
+    on = FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
+    ev, qi = lay.evidence_vector({"N3": 1, "N20": 2}), lay.query_indices(["N7", "N33"])
+    c, sw, sw2 = capi.lw_infer(on, ev, qi, n_total, seed=9, mode=capi.DEVICE_SPEC)
+    np.testing.assert_allclose(lw2[:-2], c.ravel(order="F"), rtol=1e-12)
+    assert lw2[-2] == pytest.approx(sw, rel=1e-12) and lw2[-1] == pytest.approx(sw2, rel=1e-12)
+    gc, _ = capi.gibbs_infer(on, ev, qi, 64, 300, 100, 3, seed=4)
+    assert np.array_equal(g2, gc.astype(np.float64).ravel(order="F"))
