@@ -25,6 +25,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# from the committed ncu capture of the headline kernel (profiles/r1c_lw_spec_ncu_full.txt): 5.179e9 warp
+# instructions for 1e8 particles (3.125e6 warps), DRAM bytes per launch, pipe utilisation
+NCU_LW = {"inst_per_warp_particle": 5178894080 / (1e8 / 32), "dram_bytes_per_launch": 45312,
+          "fmaheavy_pct": 80.2, "alu_pct": 61.7, "issue_active_pct": 61.7}
 METRIC = "lw_samples_per_s"
 UNIT = "samples/s"
 
@@ -122,8 +126,8 @@ def cpu_lw(lay, query, evidence, n, seed, threads=None):
     from oracle import capi
     from oracle.factors_np import FlatNet
     capi.build()
-    if threads:
-        capi.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core it is allowed to run on
+    capi.set_num_threads(threads or len(os.sched_getaffinity(0)))
     on = FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
     evv, qi = lay.evidence_vector(evidence), lay.query_indices(query)
     t0 = time.perf_counter()
@@ -325,6 +329,18 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     hbm, src = peaks()
+    # the bound that actually applies: issue slots of the busiest pipe.  Instructions per warp-particle are a static
+    # property of the generated kernel (ncu smsp__inst_executed.sum / warps, profiles/r1c_lw_spec_ncu_full.txt);
+    # the live fraction below is that count x warps launched / (SMs x 4 schedulers x clock x measured duration)
+    sm_clock = (line_clock := clk.summary()).get("sm_mhz") or 1965.0
+    warp_instr = NCU_LW["inst_per_warp_particle"] * per_gpu / 32.0
+    pipe = {"bound": "issue slots; busiest pipe = fmaheavy (IMAD.WIDE of Philox4x32-10) then alu",
+            "issue_slot_frac_live": warp_instr / (148 * 4 * sm_clock * 1e6 * kern_ms * 1e-3),
+            "ncu_fmaheavy_pct": NCU_LW["fmaheavy_pct"], "ncu_alu_pct": NCU_LW["alu_pct"],
+            "ncu_issue_active_pct": NCU_LW["issue_active_pct"], "inst_per_node_sample": NCU_LW["inst_per_warp_particle"] / lay.n,
+            "source": "profiles/r1c_lw_spec_ncu_full.txt (ncu --set full, same command at 1e8 particles)"}
+    if args.lw_kernel != "specialized_all":
+        pipe = None
     bpp = algorithmic_bytes_per_particle(lay)
     achieved = bpp * per_gpu / (kern_ms * 1e-3) / 1e9
     line = {
@@ -332,14 +348,15 @@ def run_gpu(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 thresholds / f64 weights",
         "data": "synthetic", "config": workload_config(lay, query, evidence, per_gpu, world),
-        "clocks": clk.summary(),
+        "clocks": line_clock,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "infer(LikelihoodWeightingInference(nsamples), bn, query; evidence)"},
         "gpu_launches": int(launches),
         "lw_kernel": args.lw_kernel, "nodes_sampled_per_particle": int(lay.n) if args.lw_kernel != "specialized_pruned" else live,
         "variants": variants, "jit_compiles": int(_lib.lib().bn_lw_spec_compile_count()),
         "roofline": {"kernel": {"generic": "bn::particle_kernel<MODE_INFER>"}.get(args.lw_kernel, "lw_spec (NVRTC, network-specialised)"), "bound": "hbm", "achieved": achieved, "peak": hbm,
-                     "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": f"of {src}",
+                     "unit": "GB/s", "frac": achieved / hbm, "traffic": NCU_LW["dram_bytes_per_launch"], "peak_source": f"of {src}",
+                     "pipe_roofline": pipe,
                      "algorithmic_bytes_per_particle": bpp, "kernel_ms": kern_ms,
                      "note": "HBM-EQUIVALENT figure required by SURVEY.md 8(d): the CPT rows a particle touches, "
                              "counted as fp64 bytes.  The tables are shared-memory resident, so this kernel is "
