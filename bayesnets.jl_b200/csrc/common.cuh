@@ -169,6 +169,9 @@ int32_t compile_program(const Net& net, const int8_t* evidence, bool treat_all_f
 int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
                               const std::vector<int64_t>& qstride, uint32_t ncell, uint64_t first, uint64_t n,
                               uint64_t seed, double* out_dev, bool* used);
+int32_t launch_table_specialized(Net* net, const int8_t* evidence, int32_t kind, uint32_t max_attempts, uint64_t first,
+                                 uint64_t n, uint64_t seed, uint8_t* out_states, double* out_w, uint8_t* out_ok,
+                                 bool* used);
 
 // ---------------------------------------------------------------------------- Philox4x32-10
 // Salmon et al. SC'11.  key bumps are warp-uniform so only 2 IMAD.WIDE + 2 LOP3 per round are

@@ -452,6 +452,12 @@ int32_t bn_sample_dev(bn_net_t h, const int8_t* evidence, int32_t kind, int32_t 
   BN_REQUIRE(kind != BN_SAMPLE_REJECTION || max_attempts >= 1, BN_BAD_ARG, "bn_sample: max_attempts must be >= 1");
   BN_CUDA_TRY(cudaSetDevice(net->device));
   if (n_rows == 0) return BN_OK;
+  {  // network-specialised kernel first (specialize.cu); same rows bit for bit
+    bool used = false;
+    BN_TRY(launch_table_specialized(net, evidence, kind, (uint32_t)(max_attempts > 0 ? max_attempts : 1), first_row, n_rows,
+                                    seed, out_states_dev, out_w_dev, out_ok_dev, &used));
+    if (used) return BN_OK;
+  }
   SampleArgs a{};
   a.first = first_row;
   a.n = n_rows;

@@ -176,45 +176,62 @@ __device__ __forceinline__ void stage_tables(void* dst, const void* src, u32 byt
 }
 )BNSRC";
 
-// Emit the kernel for this (net, evidence mask, query).
-static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const int32_t* query, uint32_t n_query,
-                                 const std::vector<int64_t>& qstride, uint32_t ncell, bool prune, const SpecShape& shp,
-                                 uint32_t* n_live_out) {
+enum SpecMode { SPEC_INFER = 0, SPEC_TABLE = 1, SPEC_REJECT = 2 };
+
+// Emit the kernel for this (net structure, evidence mask, query | table mode).
+//   SPEC_INFER : weighted counts of the query cell (bn_lw_infer)
+//   SPEC_TABLE : one row of states (+ weight) per particle; evidence columns are clamped (bn_sample ancestral/weighted)
+//   SPEC_REJECT: ancestral rows retried (Philox counter word 3 = attempt << 8) until consistent with the evidence
+static std::string gen_source(SpecMode mode, const Net& net, const SampleProgram& prg, const std::vector<char>& ev_mask,
+                              const int32_t* query, uint32_t n_query, const std::vector<int64_t>& qstride,
+                              uint32_t ncell, bool prune, const SpecShape& shp, uint32_t* n_live_out) {
   const int n = net.n;
+  const bool infer = mode == SPEC_INFER;
   std::vector<char> live;
-  live_nodes(net, prg, query, n_query, prune, &live);
+  live_nodes(net, prg, query, n_query, prune && infer, &live);
   const bool reg_bins = ncell <= (uint32_t)SPEC_MAX_REG_CELLS;
-  const uint32_t tab_words = prg.table_words;
-  const char* style_env = getenv("BN_SPEC_STYLE");
-  const int style = style_env ? atoi(style_env) : 1;
   std::ostringstream o;
-  o << "// generated by libbn_cuda (specialize.cu): " << n << " nodes, " << prg.n_free << " free, query cells " << ncell
-    << (prune ? ", barren nodes pruned" : ", all nodes kept alive") << "\n";
-  o << kPrelude;
-  o << "#define NT " << shp.threads << "\n#define TAB_WORDS " << tab_words << "u\n#define NCELL " << ncell << "u\n";
-  o << "extern \"C\" __global__ void __launch_bounds__(NT, " << shp.min_blocks
-    << ") lw_spec(const u32* __restrict__ tab_g, u64 first, u64 n, u32 k0, u32 k1, u32 never, double* __restrict__ out) {\n";
+  o << "// generated by libbn_cuda (specialize.cu): " << n << " nodes, " << prg.n_free << " free, mode " << (int)mode;
+  if (infer) o << ", query cells " << ncell << (prune ? ", barren nodes pruned" : ", all nodes kept alive");
+  o << "\n" << kPrelude;
+  o << "#define NT " << shp.threads << "\n#define TAB_WORDS " << prg.table_words << "u\n#define NCELL " << (infer ? ncell : 0u) << "u\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(NT, " << shp.min_blocks << ") lw_spec(const u32* __restrict__ tab_g, "
+       "u64 first, u64 n, u32 k0, u32 k1, u32 never, double* __restrict__ out, const signed char* __restrict__ ev, "
+       "unsigned char* __restrict__ out_states, double* __restrict__ out_w, unsigned char* __restrict__ out_ok, u32 max_att) {\n";
   o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
   o << "  __shared__ __align__(8) u64 bar;\n";
   o << "  const u32* __restrict__ tab = reinterpret_cast<const u32*>(smem_raw);\n";
-  o << "  double* bins = reinterpret_cast<double*>(smem_raw + TAB_WORDS * 4u);\n";
   o << "  const u32 tid = threadIdx.x;\n";
   o << "  stage_tables(smem_raw, tab_g, TAB_WORDS * 4u, &bar);\n";
-  o << "  for (u32 c = tid; c < NCELL + 2u; c += NT) bins[c] = 0.0;\n";
+  if (infer) {
+    o << "  double* bins = reinterpret_cast<double*>(smem_raw + TAB_WORDS * 4u);\n";
+    o << "  for (u32 c = tid; c < NCELL + 2u; c += NT) bins[c] = 0.0;\n";
+  }
   o << "  __syncthreads();\n";
-  o << "  double sw = 0.0, sw2 = 0.0;\n";
-  if (reg_bins)
-    for (uint32_t c = 0; c < ncell; ++c) o << "  double a" << c << " = 0.0;\n";
-  o << "  for (u64 row = (u64)blockIdx.x * NT + tid; row < n; row += (u64)gridDim.x * NT) {\n";
-  o << "    const u64 pid = first + row;\n";
-  o << "    const u32 c0 = (u32)pid, c1 = (u32)(pid >> 32);\n";
-  o << "    double w = 1.0;\n";
-  if (!prune) o << "    u32 chk = 0u;\n";
+  if (infer) {
+    o << "  double sw = 0.0, sw2 = 0.0;\n";
+    if (reg_bins)
+      for (uint32_t c = 0; c < ncell; ++c) o << "  double a" << c << " = 0.0;\n";
+  }
   // states that no child, query cell or weight reads (only matters when every node is kept alive)
   std::vector<char> has_reader(n, 0);
   for (int i = 0; i < n; ++i)
     for (auto& pr : prg.plan[i].parents) has_reader[pr.first] = 1;
   for (uint32_t j = 0; j < n_query; ++j) has_reader[query[j]] = 1;
+
+  o << "  for (u64 row = (u64)blockIdx.x * NT + tid; row < n; row += (u64)gridDim.x * NT) {\n";
+  o << "    const u64 pid = first + row;\n";
+  o << "    const u32 c0 = (u32)pid, c1 = (u32)(pid >> 32);\n";
+  o << "    double w = 1.0;\n";
+  if (infer && !prune) o << "    u32 chk = 0u;\n";
+  if (mode == SPEC_REJECT) {
+    for (int i = 0; i < n; ++i) o << "    u32 s" << i << " = 0u;\n";
+    o << "    u32 ok = 0u;\n";
+    o << "    for (u32 att = 0u; att < max_att && !ok; ++att) {\n";
+    o << "    const u32 c3 = att << 8;\n";
+  }
+  const char* c3 = mode == SPEC_REJECT ? "c3" : "0u";
+  const char* decl = mode == SPEC_REJECT ? "" : "u32 ";
   uint32_t d = 0, n_live = 0;
   int cur_blk = -1;
   for (int i = 0; i < n; ++i) {
@@ -223,8 +240,7 @@ static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const
     if (!np.is_evidence) ++d;
     if (!live[i]) continue;
     ++n_live;
-    // row address (words)
-    std::ostringstream addr;
+    std::ostringstream addr;  // row address (words)
     addr << np.toff << "u";
     for (auto& pr : np.parents) addr << " + s" << pr.first << " * " << (pr.second * np.row_words) << "u";
     if (np.is_evidence) {
@@ -235,34 +251,20 @@ static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const
     if (blk != cur_blk) {
       cur_blk = blk;
       o << "    u32 r" << blk << "_0, r" << blk << "_1, r" << blk << "_2, r" << blk << "_3;\n";
-      o << "    px(c0, c1, " << blk << "u, 0u, k0, k1, r" << blk << "_0, r" << blk << "_1, r" << blk << "_2, r" << blk
-        << "_3);\n";
+      o << "    px(c0, c1, " << blk << "u, " << c3 << ", k0, k1, r" << blk << "_0, r" << blk << "_1, r" << blk << "_2, r"
+        << blk << "_3);\n";
     }
     std::ostringstream rw;
     rw << "r" << blk << "_" << (my_d & 3u);
-    const std::string rword = rw.str();
-    o << "    u32 s" << i << ";  // node " << i << ": card " << np.card << ", " << np.parents.size() << " free parents\n";
     const int nth = np.card - 1;  // real thresholds (row padding is never compared)
+    o << "    // node " << i << ": card " << np.card << ", " << np.parents.size() << " free parents\n";
     if (np.card <= 1) {
-      o << "    s" << i << " = 0u;\n";
-    } else if (style == 0) {
-      // plain compares; the compiler picks ISETP + SEL/IMAD.MOV sequences
-      o << "    { const u32 r = " << rword << " >> 1; const u32* tp = tab + (" << addr.str() << "); s" << i << " = 0u;\n";
-      if (nth == 1) o << "      s" << i << " = (u32)(r >= tp[0]);\n";
-      else if (nth == 2) o << "      { const uint2 t = *reinterpret_cast<const uint2*>(tp); s" << i << " = (u32)(r >= t.x) + (u32)(r >= t.y); }\n";
-      else
-        for (int k = 0; k < nth; k += 4) {
-          o << "      { const uint4 t = *reinterpret_cast<const uint4*>(tp + " << k << "); s" << i << " += (u32)(r >= t.x)";
-          if (k + 1 < nth) o << " + (u32)(r >= t.y)";
-          if (k + 2 < nth) o << " + (u32)(r >= t.z)";
-          if (k + 3 < nth) o << " + (u32)(r >= t.w)";
-          o << "; }\n";
-        }
-      o << "    }\n";
+      o << "    " << decl << "s" << i << " = 0u;\n";
     } else {
       // sign-bit form: rb = (r >> 1) | 2^31 (one funnel shift); rb - T has bit 31 set iff (r >> 1) >= T for every
       // T in [0, 2^31]; two ALU ops per threshold (IADD + LEA.HI / SHF), no predicates, no moves
-      o << "    { const u32 rb = __funnelshift_r(" << rword << ", 1u, 1); const u32* tp = tab + (" << addr.str() << ");\n";
+      o << "    " << decl << "s" << i << ";\n";
+      o << "    { const u32 rb = __funnelshift_r(" << rw.str() << ", 1u, 1); const u32* tp = tab + (" << addr.str() << ");\n";
       if (nth == 1) o << "      s" << i << " = (rb - tp[0]) >> 31;\n";
       else if (nth == 2) o << "      { const uint2 t = *reinterpret_cast<const uint2*>(tp); s" << i << " = ((rb - t.x) >> 31) + ((rb - t.y) >> 31); }\n";
       else {
@@ -277,31 +279,52 @@ static std::string gen_lw_source(const Net& net, const SampleProgram& prg, const
       }
       o << "    }\n";
     }
-    if (!prune && !has_reader[i]) o << "    chk += s" << i << ";  // nothing else reads this state\n";
+    if (infer && !prune && !has_reader[i]) o << "    chk += s" << i << ";  // nothing else reads this state\n";
   }
-  // query cell
-  o << "    const u32 cell = 0u";
-  for (uint32_t j = 0; j < n_query; ++j) o << " + s" << query[j] << " * " << (uint32_t)qstride[j] << "u";
-  o << ";\n";
-  if (!prune) o << "    if (chk == never) w = 0.0;  // keeps every state live; never true (host passes 0xFFFFFFFF)\n";
-  if (reg_bins) {
-    for (uint32_t c = 0; c < ncell; ++c) o << "    a" << c << " += (cell == " << c << "u) ? w : 0.0;\n";
+  if (mode == SPEC_REJECT) {
+    // consistent(a, evidence): src/ProbabilisticGraphicalModels/assignments.jl:13-22
+    o << "    ok = 1u;\n";
+    for (int i = 0; i < n; ++i)
+      if (ev_mask[i]) o << "    ok &= (u32)(s" << i << " == (u32)ev[" << i << "]);\n";
+    o << "    }\n";
+  }
+  if (infer) {
+    o << "    const u32 cell = 0u";
+    for (uint32_t j = 0; j < n_query; ++j) o << " + s" << query[j] << " * " << (uint32_t)qstride[j] << "u";
+    o << ";\n";
+    if (!prune) o << "    if (chk == never) w = 0.0;  // keeps every state live; never true (host passes 0xFFFFFFFF)\n";
+    if (reg_bins) {
+      for (uint32_t c = 0; c < ncell; ++c) o << "    a" << c << " += (cell == " << c << "u) ? w : 0.0;\n";
+    } else {
+      o << "    atomicAdd(&bins[cell], w);\n";
+    }
+    o << "    sw += w; sw2 += w * w;\n";
   } else {
-    o << "    atomicAdd(&bins[cell], w);\n";
+    // one DataFrame column per node: node-major uint8, 32 consecutive bytes per warp store
+    for (int i = 0; i < n; ++i) {
+      o << "    out_states[" << i << "ull * n + row] = (unsigned char)(";
+      if (mode == SPEC_REJECT) o << "ok ? s" << i << " : 0xFFu";
+      else if (prg.plan[i].is_evidence) o << "ev[" << i << "]";
+      else o << "s" << i;
+      o << ");\n";
+    }
+    o << "    if (out_w) out_w[row] = w;\n";
+    o << "    if (out_ok) out_ok[row] = (unsigned char)" << (mode == SPEC_REJECT ? "ok" : "1u") << ";\n";
   }
-  o << "    sw += w; sw2 += w * w;\n";
   o << "  }\n";
-  // reductions: warp shuffle, one smem atomic per warp, then one global atomic per (CTA, cell)
-  o << "#pragma unroll\n  for (int of = 16; of > 0; of >>= 1) {\n";
-  o << "    sw += __shfl_xor_sync(0xffffffffu, sw, of); sw2 += __shfl_xor_sync(0xffffffffu, sw2, of);\n";
-  if (reg_bins)
-    for (uint32_t c = 0; c < ncell; ++c) o << "    a" << c << " += __shfl_xor_sync(0xffffffffu, a" << c << ", of);\n";
-  o << "  }\n";
-  o << "  if ((tid & 31u) == 0u) {\n    atomicAdd(&bins[NCELL], sw); atomicAdd(&bins[NCELL + 1u], sw2);\n";
-  if (reg_bins)
-    for (uint32_t c = 0; c < ncell; ++c) o << "    if (a" << c << " != 0.0) atomicAdd(&bins[" << c << "], a" << c << ");\n";
-  o << "  }\n  __syncthreads();\n";
-  o << "  for (u32 c = tid; c < NCELL + 2u; c += NT) if (bins[c] != 0.0) atomicAdd(&out[c], bins[c]);\n";
+  if (infer) {
+    // reductions: warp shuffle, one smem atomic per warp, then one global atomic per (CTA, cell)
+    o << "#pragma unroll\n  for (int of = 16; of > 0; of >>= 1) {\n";
+    o << "    sw += __shfl_xor_sync(0xffffffffu, sw, of); sw2 += __shfl_xor_sync(0xffffffffu, sw2, of);\n";
+    if (reg_bins)
+      for (uint32_t c = 0; c < ncell; ++c) o << "    a" << c << " += __shfl_xor_sync(0xffffffffu, a" << c << ", of);\n";
+    o << "  }\n";
+    o << "  if ((tid & 31u) == 0u) {\n    atomicAdd(&bins[NCELL], sw); atomicAdd(&bins[NCELL + 1u], sw2);\n";
+    if (reg_bins)
+      for (uint32_t c = 0; c < ncell; ++c) o << "    if (a" << c << " != 0.0) atomicAdd(&bins[" << c << "], a" << c << ");\n";
+    o << "  }\n  __syncthreads();\n";
+    o << "  for (u32 c = tid; c < NCELL + 2u; c += NT) if (bins[c] != 0.0) atomicAdd(&out[c], bins[c]);\n";
+  }
   o << "}\n";
   if (n_live_out) *n_live_out = n_live;
   return o.str();
@@ -349,14 +372,6 @@ static std::atomic<uint64_t> g_spec_compiles{0};
 
 void spec_cache_clear(Net* net) { net->spec_cache.clear(); }
 
-static std::string spec_key(const Net& net, const int8_t* evidence, const int32_t* query, uint32_t n_query, bool prune) {
-  std::string k((size_t)net.n, '0');
-  for (int i = 0; i < net.n; ++i) k[i] = (evidence && evidence[i] >= 0) ? '1' : '0';
-  k += prune ? "|p" : "|a";
-  for (uint32_t j = 0; j < n_query; ++j) k += "," + std::to_string(query[j]);
-  return k;
-}
-
 static int32_t cu_fail(const char* what, CUresult r) {
   const char* s = nullptr;
   driver().GetErrorString(r, &s);
@@ -367,27 +382,46 @@ static int32_t cu_fail(const char* what, CUresult r) {
 thread_local int tl_lw_mode = 0;   // 0 auto, 1 generic only, 2 specialised required
 thread_local int tl_lw_prune = 1;  // barren-node elimination in the specialised kernel
 
-int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
-                              const std::vector<int64_t>& qstride, uint32_t ncell, uint64_t first, uint64_t n,
-                              uint64_t seed, double* out_dev, bool* used) {
+struct SpecLaunch {
+  SpecMode mode = SPEC_INFER;
+  const int8_t* evidence = nullptr;  // host, n entries or NULL
+  bool all_free = false;             // ancestral / rejection: evidence is ignored while sampling
+  const int32_t* query = nullptr;
+  uint32_t n_query = 0, ncell = 1;
+  const std::vector<int64_t>* qstride = nullptr;
+  uint64_t first = 0, n = 0, seed = 0;
+  double* out = nullptr;             // SPEC_INFER
+  uint8_t* out_states = nullptr;     // table modes
+  double* out_w = nullptr;
+  uint8_t* out_ok = nullptr;
+  uint32_t max_attempts = 1;
+};
+
+static int32_t launch_specialized(Net* net, const SpecLaunch& a, bool* used) {
   *used = false;
   if (tl_lw_mode == 1) return BN_OK;
   const bool must = tl_lw_mode == 2;
   Driver& drv = driver();
   if (!nvrtc().ok || !drv.ok) {
-    BN_REQUIRE(!must, BN_UNSUPPORTED, "specialised LW kernel unavailable: NVRTC / driver entry points missing");
+    BN_REQUIRE(!must, BN_UNSUPPORTED, "specialised sampling kernel unavailable: NVRTC / driver entry points missing");
     return BN_OK;
   }
   const DevProps& dp = dev_props(net->device);
   SampleProgram prg;
-  BN_TRY(compile_program(*net, evidence, false, 1, &prg));
-  const size_t smem = (size_t)prg.table_words * 4 + (size_t)(ncell + 2) * 8;
-  if (smem + 1024 > (size_t)dp.max_smem_optin || net->n > 4096 || prg.table_words > (1u << 22)) {
-    BN_REQUIRE(!must, BN_UNSUPPORTED, "network too large for the specialised LW kernel");
+  BN_TRY(compile_program(*net, a.evidence, a.all_free, 1, &prg));
+  const bool infer = a.mode == SPEC_INFER;
+  const size_t smem = (size_t)prg.table_words * 4 + (infer ? (size_t)(a.ncell + 2) * 8 : 0);
+  if (smem + 1024 > (size_t)dp.max_smem_optin || net->n > 2048 || prg.table_words > (1u << 22)) {
+    BN_REQUIRE(!must, BN_UNSUPPORTED, "network too large for the specialised sampling kernel");
     return BN_OK;
   }
-  const bool prune = tl_lw_prune != 0;
-  const std::string key = spec_key(*net, evidence, query, n_query, prune);
+  const bool prune = tl_lw_prune != 0 && infer;
+  std::vector<char> ev_mask((size_t)net->n, 0);
+  for (int i = 0; i < net->n; ++i) ev_mask[i] = (a.evidence && a.evidence[i] >= 0) ? 1 : 0;
+  std::string key((size_t)net->n, '0');
+  for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
+  key += "|m" + std::to_string((int)a.mode) + (a.all_free ? "f" : "e") + (prune ? "p" : "a");
+  for (uint32_t j = 0; j < a.n_query; ++j) key += "," + std::to_string(a.query[j]);
   SpecKernel* k = nullptr;
   auto it = net->spec_cache.find(key);
   if (it != net->spec_cache.end()) {
@@ -397,7 +431,9 @@ int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* q
     if (const char* e = getenv("BN_SPEC_THREADS")) shp.threads = atoi(e);
     if (const char* e = getenv("BN_SPEC_MINB")) shp.min_blocks = atoi(e);
     uint32_t n_live = 0;
-    const std::string src = gen_lw_source(*net, prg, query, n_query, qstride, ncell, prune, shp, &n_live);
+    static const std::vector<int64_t> no_stride;
+    const std::string src = gen_source(a.mode, *net, prg, ev_mask, a.query, a.n_query, a.qstride ? *a.qstride : no_stride,
+                                       a.ncell, prune, shp, &n_live);
     const std::string gkey = std::to_string(net->device) + "|" + src;
     std::lock_guard<std::mutex> lk(g_spec_mu);
     auto git = g_spec.find(gkey);
@@ -435,27 +471,63 @@ int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* q
     net->spec_cache[key] = k;
   }
   if (!k) {
-    BN_REQUIRE(!must, BN_CUDA_ERR, "specialised LW kernel failed to compile earlier for this (net, evidence, query)");
+    BN_REQUIRE(!must, BN_CUDA_ERR, "specialised kernel failed to compile earlier for this (net, evidence, query)");
     return BN_OK;
   }
   BN_REQUIRE(k->table_words == prg.table_words, BN_CUDA_ERR, "specialised kernel/table mismatch");
-  // tables -> device scratch (evidence values live only here)
+  // tables (+ evidence values) -> device scratch: evidence VALUES live only here
   cudaStream_t s = tl_stream;
-  const size_t bytes = (size_t)prg.table_words * 4;
-  if (net->scratch.n < bytes + 16) BN_CUDA_TRY(net->scratch.alloc((bytes + 16) * 2));
-  const uint32_t* tab_host = prg.words.data() + prg.prog_words;
-  if (bytes) BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, tab_host, bytes, cudaMemcpyHostToDevice, s));
-  long want = (long)((n + k->threads - 1) / k->threads);
+  const size_t tbytes = (size_t)prg.table_words * 4;
+  const size_t ev_off = (tbytes + 15) / 16 * 16;
+  const size_t total = ev_off + (size_t)net->n + 16;
+  if (net->scratch.n < total) BN_CUDA_TRY(net->scratch.alloc(total * 2));
+  std::vector<unsigned char> host(total, 0);
+  if (tbytes) memcpy(host.data(), prg.words.data() + prg.prog_words, tbytes);
+  for (int i = 0; i < net->n; ++i) host[ev_off + i] = (unsigned char)(a.evidence ? a.evidence[i] : -1);
+  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, host.data(), total, cudaMemcpyHostToDevice, s));
+  long want = (long)((a.n + k->threads - 1) / k->threads);
   long full = (long)dp.sm_count * k->blocks_per_sm;
   unsigned grid = (unsigned)(want < full ? (want > 0 ? want : 1) : full);
   const uint32_t* tab_dev = reinterpret_cast<const uint32_t*>(net->scratch.p);
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), never = 0xFFFFFFFFu;
-  void* args[] = {(void*)&tab_dev, (void*)&first, (void*)&n, (void*)&k0, (void*)&k1, (void*)&never, (void*)&out_dev};
+  const signed char* ev_dev = reinterpret_cast<const signed char*>(net->scratch.p + ev_off);
+  uint64_t first = a.first, n = a.n;
+  uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), never = 0xFFFFFFFFu, max_att = a.max_attempts;
+  double* out = a.out;
+  uint8_t* out_states = a.out_states;
+  double* out_w = a.out_w;
+  uint8_t* out_ok = a.out_ok;
+  void* args[] = {(void*)&tab_dev, (void*)&first, (void*)&n, (void*)&k0, (void*)&k1, (void*)&never, (void*)&out,
+                  (void*)&ev_dev, (void*)&out_states, (void*)&out_w, (void*)&out_ok, (void*)&max_att};
   CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)s, args, nullptr);
   if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(lw_spec)", r);
   count_launch();
   *used = true;
   return BN_OK;
+}
+
+int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
+                              const std::vector<int64_t>& qstride, uint32_t ncell, uint64_t first, uint64_t n,
+                              uint64_t seed, double* out_dev, bool* used) {
+  SpecLaunch a;
+  a.mode = SPEC_INFER;
+  a.evidence = evidence;
+  a.query = query; a.n_query = n_query; a.ncell = ncell; a.qstride = &qstride;
+  a.first = first; a.n = n; a.seed = seed; a.out = out_dev;
+  return launch_specialized(net, a, used);
+}
+
+// kind: BN_SAMPLE_ANCESTRAL / _REJECTION / _WEIGHTED (include/bn_cuda.h)
+int32_t launch_table_specialized(Net* net, const int8_t* evidence, int32_t kind, uint32_t max_attempts, uint64_t first,
+                                 uint64_t n, uint64_t seed, uint8_t* out_states, double* out_w, uint8_t* out_ok,
+                                 bool* used) {
+  SpecLaunch a;
+  a.mode = kind == BN_SAMPLE_REJECTION ? SPEC_REJECT : SPEC_TABLE;
+  a.evidence = kind == BN_SAMPLE_ANCESTRAL ? nullptr : evidence;
+  a.all_free = kind != BN_SAMPLE_WEIGHTED;
+  a.first = first; a.n = n; a.seed = seed;
+  a.out_states = out_states; a.out_w = out_w; a.out_ok = out_ok;
+  a.max_attempts = max_attempts;
+  return launch_specialized(net, a, used);
 }
 
 }  // namespace bn
@@ -498,7 +570,9 @@ int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* p
   }
   SpecShape shp;
   uint32_t nl = 0;
-  const std::string src = gen_lw_source(net, prg, query, (uint32_t)n_query, qstride, (uint32_t)cells, prune != 0, shp, &nl);
+  std::vector<char> ev_mask((size_t)n_nodes, 0);
+  for (int i = 0; i < n_nodes; ++i) ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0;
+  const std::string src = gen_source(SPEC_INFER, net, prg, ev_mask, query, (uint32_t)n_query, qstride, (uint32_t)cells, prune != 0, shp, &nl);
   if (n_live) *n_live = (int32_t)nl;
   *out_len = (int64_t)src.size();
   if (out_src && cap > 0) {

@@ -24,6 +24,12 @@ def lw_raw(bn, net, query, evidence, n, seed=0, first=0):
     return counts, im.last_stats
 
 
+@pytest.fixture
+def lw_mode(bn):
+    yield bn.set_lw_mode
+    bn.set_lw_mode("auto", True)
+
+
 def random_case(bn, n_nodes, seed, n_ev, n_q=2):
     net = bn.rand_discrete_bn(n_nodes, 3, 4, seed=seed)
     lay = bn.flatten(net)
@@ -129,11 +135,15 @@ def test_xdsl_config_c1(bn, golden, tmp_path):
                                    ex, rtol=1e-12)
 
 
+@pytest.mark.parametrize("mode", ["generic", "specialized"])
 @pytest.mark.parametrize("kind", ["ancestral", "weighted", "rejection"])
-def test_sample_tables_match_oracle(bn, kind):
+def test_sample_tables_match_oracle(bn, lw_mode, kind, mode):
+    """rand(bn, n) / weighted rows / rejection rows from the interpreter kernel and from the network-specialised
+    NVRTC kernel are the same bytes as the oracle's."""
     net, lay, on, query, evidence = random_case(bn, 40, 7, 2)
     from bayesnets_jl_b200.sampling import _sample
-    n = 50_000
+    lw_mode(mode, True)
+    n = 50_001
     k = {"ancestral": 0, "rejection": 1, "weighted": 2}[kind]
     _, st, w, ok = _sample(net, n, evidence, k, 100, 21, None)
     ost, ow, ook = capi.sample(on, n, evidence=lay.evidence_vector(evidence), kind=k, seed=21, max_attempts=100)
@@ -187,12 +197,6 @@ def test_error_paths(bn):
         bn.infer(bn.LikelihoodWeightingInference(10), net, "T", evidence={"T": 1})
     with pytest.raises(IndexError):
         bn.infer(bn.LikelihoodWeightingInference(10), net, "T", evidence={"A": 3})
-
-
-@pytest.fixture
-def lw_mode(bn):
-    yield bn.set_lw_mode
-    bn.set_lw_mode("auto", True)
 
 
 @pytest.mark.parametrize("mode,prune", [("generic", True), ("specialized", True), ("specialized", False)])
