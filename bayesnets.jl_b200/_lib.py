@@ -38,8 +38,11 @@ _SIGS = {
     "bn_lw_infer_dev": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "bn_set_lw_mode": (C.c_int32, [C.c_int32, C.c_int32]),
     "bn_lw_spec_compile_count": (C.c_uint64, []),
+    "bn_set_gibbs_mode": (C.c_int32, [C.c_int32]),
     "bn_lw_spec_source": (C.c_int32, [C.c_int32, i32p, i32p, i32p, i64p, f64p, i8p, i32p, C.c_int32, C.c_int32,
                                       C.c_char_p, C.c_int64, i64p, i64p, i32p]),
+    "bn_gibbs_spec_source": (C.c_int32, [C.c_int32, i32p, i32p, i32p, i64p, f64p, i8p, i32p, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_char_p, C.c_int64, i64p, i64p]),
     "bn_sample": (C.c_int32, [h64, i8p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, u8p, f64p, u8p]),
     "bn_sample_dev": (C.c_int32, [h64, i8p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -124,6 +127,11 @@ def set_lw_mode(mode: str = "auto", prune: bool = True) -> None:
     interpreter otherwise), "generic", or "specialized" (raise if unavailable).  `prune` lets the specialised kernel
     skip barren nodes (never changes a count bit; see csrc/specialize.cu)."""
     check(lib().bn_set_lw_mode(C.c_int32(_LW_MODES[mode]), C.c_int32(1 if prune else 0)))
+
+
+def set_gibbs_mode(mode: str = "auto") -> None:
+    """Pick the Gibbs inference kernel for this thread: "auto", "generic" or "specialized" (csrc/specialize.cu)."""
+    check(lib().bn_set_gibbs_mode(C.c_int32(_LW_MODES[mode])))
 
 
 def launch_count() -> int:

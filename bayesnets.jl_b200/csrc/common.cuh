@@ -140,6 +140,7 @@ struct Factor {
 };
 
 Net* get_net(bn_net_t h);
+void build_children(Net* net);
 Factor* get_factor(bn_factor_t h);
 bn_factor_t register_factor(Factor* f);
 Factor* take_factor(bn_factor_t h);  // removes the handle, caller deletes
@@ -171,6 +172,13 @@ int32_t launch_lw_specialized(Net* net, const int8_t* evidence, const int32_t* q
                               uint64_t seed, double* out_dev, bool* used);
 int32_t launch_table_specialized(Net* net, const int8_t* evidence, int32_t kind, uint32_t max_attempts, uint64_t first,
                                  uint64_t n, uint64_t seed, uint8_t* out_states, double* out_w, uint8_t* out_ok,
+                                 bool* used);
+
+// specialize.cu: network-specialised Gibbs inference (same counts as gibbs_infer_kernel)
+int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
+                                 const std::vector<int64_t>& qstride, uint32_t ncell, bool full, uint64_t first_chain,
+                                 uint64_t n_chains, int64_t burn_in, int64_t thin, int64_t total, uint64_t seed,
+                                 double* out_dev, double* chain_counts_dev, uint8_t* state_dev, int32_t init_from_state,
                                  bool* used);
 
 // ---------------------------------------------------------------------------- Philox4x32-10

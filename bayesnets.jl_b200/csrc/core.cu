@@ -69,6 +69,23 @@ bn_factor_t register_factor(Factor* f) {
   return h;
 }
 
+// children CSR, ascending child index (Graphs.outneighbors order, src/bayes_nets.jl:96-99)
+void build_children(Net* net) {
+  const int n = net->n;
+  const int32_t n_par = net->par_ptr[n];
+  net->child_ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i)
+    for (int k = net->par_ptr[i]; k < net->par_ptr[i + 1]; ++k) net->child_ptr[net->par_idx[k] + 1]++;
+  for (int i = 0; i < n; ++i) net->child_ptr[i + 1] += net->child_ptr[i];
+  net->child_idx.assign(n_par, 0);
+  std::vector<int32_t> fill(n, 0);
+  for (int i = 0; i < n; ++i)
+    for (int k = net->par_ptr[i]; k < net->par_ptr[i + 1]; ++k) {
+      int p = net->par_idx[k];
+      net->child_idx[net->child_ptr[p] + fill[p]++] = i;
+    }
+}
+
 int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>& card, int device,
                    Factor** out) {
   Factor* f = new Factor();
@@ -150,20 +167,7 @@ int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_p
   net->par_idx.assign(par_idx, par_idx + n_par);
   net->cpt_off.assign(cpt_off, cpt_off + n_nodes + 1);
   net->cpt.assign(cpt, cpt + cpt_off[n_nodes]);
-  // children CSR, ascending child index (Graphs.outneighbors order, src/bayes_nets.jl:96-99)
-  net->child_ptr.assign(n_nodes + 1, 0);
-  for (int i = 0; i < n_nodes; ++i)
-    for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) net->child_ptr[par_idx[k] + 1]++;
-  for (int i = 0; i < n_nodes; ++i) net->child_ptr[i + 1] += net->child_ptr[i];
-  net->child_idx.assign(n_par, 0);
-  {
-    std::vector<int32_t> fill(n_nodes, 0);
-    for (int i = 0; i < n_nodes; ++i)
-      for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) {
-        int p = par_idx[k];
-        net->child_idx[net->child_ptr[p] + fill[p]++] = i;
-      }
-  }
+  build_children(net);
   cudaStream_t s = bn::tl_stream;
   std::vector<int32_t> off32(n_nodes + 1);
   bool fits32 = cpt_off[n_nodes] < (int64_t)0x7fffffff;

@@ -385,6 +385,17 @@ static int32_t gibbs_infer_impl(bn_net_t h, const int8_t* evidence, const int32_
   }
   BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)ncell * 8, tl_stream));
   if (n_chains == 0) return BN_OK;
+  {  // network-specialised kernel first (specialize.cu); identical counts
+    bool used = false;
+    BN_TRY(launch_gibbs_specialized(net, evidence, query, (uint32_t)n_query, qstride, (uint32_t)ncell,
+                                    mode == BN_GIBBS_FULL, first_chain, n_chains, burn_in, thin,
+                                    (nsamples - burn_in + thin - 1) / thin, seed, out_dev, d_chain_counts, d_state,
+                                    init_from_state, &used));
+    if (used) {
+      BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+      return BN_OK;
+    }
+  }
   const DevProps& dp = dev_props(net->device);
   const int T = gibbs_threads(dp, net->n, (size_t)ncell * 8);
   BN_REQUIRE(T > 0, BN_UNSUPPORTED, "network too large for the Gibbs kernel (%d nodes)", net->n);

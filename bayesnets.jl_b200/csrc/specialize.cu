@@ -530,6 +530,265 @@ int32_t launch_table_specialized(Net* net, const int8_t* evidence, int32_t kind,
   return launch_specialized(net, a, used);
 }
 
+// ------------------------------------------------------------------------------------------ Gibbs
+// Network-specialised batched Gibbs inference (src/Inference/gibbs.jl:66-145 Nodewise, :161-234 Full): one chain per
+// thread, states u8 [node][thread] in shared memory (offsets are immediates), one straight-line block per free
+// node with its Markov blanket unrolled: p[v] = prod_children P(x_c | pa_c, x_n = v) * P(v | pa_n) in fp64, children
+// first and own CPD last exactly like the reference's foldl, then StatsBase's cumulative scan.  Same Philox stream
+// and arithmetic as gibbs_infer_kernel / oracle -> identical integer counts.  burn-in / thinning bookkeeping is
+// chain-independent (a countdown in uniform registers).
+constexpr int GIBBS_SPEC_MAX_CARD = 8;
+
+// The sweep is one long straight-line block (~55 instructions per node, > 100 KB for 200 nodes).  Everything that
+// is not per-node arithmetic stays out of line or out of the loop: the Philox refill every 4th update is a call, the
+// thinned record step counts in registers (<= 16 query cells) or through one MATCH.ANY-grouped atomic per cell.
+static const char* kGibbsPrelude = R"BNSRC(
+__device__ __noinline__ void refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1, u32& b0, u32& b1, u32& b2, u32& b3) {
+  px(c0, c1, blk, 2u, k0, k1, b0, b1, b2, b3);
+}
+#define NEXT_R(r) { if ((d & 3u) == 0u) refill(c0, c1, d >> 2, k0, k1, b0, b1, b2, b3); \
+                    r = (d & 2u) ? ((d & 1u) ? b3 : b2) : ((d & 1u) ? b1 : b0); ++d; }
+)BNSRC";
+
+static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_mask, const int32_t* query,
+                                    uint32_t n_query, const std::vector<int64_t>& qstride, uint32_t ncell, bool full,
+                                    int threads, int min_blocks, uint32_t* n_free_out) {
+  const int n = net.n;
+  std::ostringstream o;
+  uint32_t n_free = 0;
+  for (int i = 0; i < n; ++i) n_free += ev_mask[i] ? 0 : 1;
+  o << "// generated by libbn_cuda (specialize.cu): Gibbs " << (full ? "Full" : "Nodewise") << ", " << n << " nodes, "
+    << n_free << " free, query cells " << ncell << "\n";
+  o << kPrelude << kGibbsPrelude;
+  o << "#define NT " << threads << "\n#define NN " << n << "u\n#define NCELL " << ncell << "u\n";
+  // record step: <= 16 query cells count in per-thread registers (no atomics until the end); larger tables group the
+  // warp's lanes by cell (MATCH.ANY) and the group leader adds the group size to the CTA's shared-memory bins
+  const bool reg_bins = ncell <= (uint32_t)SPEC_MAX_REG_CELLS;
+  o << "#define CELL (0u";
+  for (uint32_t j = 0; j < n_query; ++j) o << " + (u32)st[" << query[j] << " * NT] * " << (uint32_t)qstride[j] << "u";
+  o << ")\n";
+  if (reg_bins) {
+    o << "#define RECORD { const u32 cell = CELL;";
+    for (uint32_t c = 0; c < ncell; ++c) o << " n" << c << " += (u32)(cell == " << c << "u);";
+    o << " if (cc && live) cc[ci * NCELL + cell] += 1.0; }\n";
+  } else {
+    o << "__device__ __noinline__ void record(const unsigned char* st, unsigned long long* bins, double* cc, u64 ci, bool live) {\n";
+    o << "  const u32 cell = live ? CELL : 0xFFFFFFFFu;\n";
+    o << "  const u32 grp = __match_any_sync(0xffffffffu, cell);\n";
+    o << "  if (live) { if ((u32)(__ffs(grp) - 1) == (threadIdx.x & 31u)) atomicAdd(&bins[cell], (unsigned long long)__popc(grp));\n";
+    o << "              if (cc) cc[ci * NCELL + cell] += 1.0; }\n}\n";
+    o << "#define RECORD record(st, bins, cc, ci, live);\n";
+  }
+  o << "#define TICK { if (--until == 0) { until = thin; RECORD; if (++smp >= total) goto finished; } }\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(NT, " << min_blocks << ") gibbs_spec(const double* __restrict__ cpt, "
+       "const signed char* __restrict__ ev, u64 first_chain, u64 n_chains, u32 k0, u32 k1, long long burn_in, long long thin, "
+       "long long total, double* __restrict__ out, double* __restrict__ cc, unsigned char* __restrict__ state_io, "
+       "int init_from_state) {\n";
+  o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
+  o << "  unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem_raw);\n";
+  o << "  const u32 tid = threadIdx.x;\n";
+  o << "  unsigned char* st = smem_raw + NCELL * 8u + tid;\n";
+  o << "  for (u32 c = tid; c < NCELL; c += NT) bins[c] = 0ull;\n";
+  o << "  __syncthreads();\n";
+  o << "  const u64 ci = (u64)blockIdx.x * NT + tid;\n";
+  o << "  const bool live = ci < n_chains;  // surplus threads of the last CTA run a dummy chain (barriers need them)\n";
+  if (reg_bins)
+    for (uint32_t c = 0; c < ncell; ++c) o << "  u32 n" << c << " = 0u;\n";
+  o << "  {\n";
+  o << "    const u64 chain = first_chain + ci;\n";
+  o << "    const u32 c0 = (u32)chain, c1 = (u32)(chain >> 32);\n";
+  // ---- initial state: resume (im.state) or uniform (src/Inference/gibbs.jl:6-20), stream 1, static draw indices
+  o << "    if (state_io && init_from_state) {\n";
+  o << "      for (u32 i = 0; i < NN; ++i) st[i * NT] = live ? state_io[ci * NN + i] : (unsigned char)0;\n";
+  o << "    } else {\n";
+  {
+    uint32_t d = 0;
+    int cur = -1;
+    for (int i = 0; i < n; ++i) {
+      if (ev_mask[i]) { o << "      st[" << i << " * NT] = (unsigned char)ev[" << i << "];\n"; continue; }
+      const int blk = (int)(d >> 2);
+      if (blk != cur) {
+        cur = blk;
+        o << "      u32 i" << blk << "_0, i" << blk << "_1, i" << blk << "_2, i" << blk << "_3; px(c0, c1, " << blk
+          << "u, 1u, k0, k1, i" << blk << "_0, i" << blk << "_1, i" << blk << "_2, i" << blk << "_3);\n";
+      }
+      o << "      st[" << i << " * NT] = (unsigned char)__umulhi(i" << blk << "_" << (d & 3u) << ", " << net.card[i] << "u);\n";
+      ++d;
+    }
+  }
+  o << "    }\n";
+  o << "    u32 d = 0u, b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;\n";
+  o << "    long long until = burn_in + thin, smp = 0;\n";
+  if (n_free == 0 && !full) {
+    o << "    goto finished;\n";
+  }
+  o << "    for (;;) {\n";
+  int emitted = 0;
+  // optional re-convergence barrier every N nodes (BN_GIBBS_SYNC); measured no gain on B200, off by default
+  const int sync_every = getenv("BN_GIBBS_SYNC") ? atoi(getenv("BN_GIBBS_SYNC")) : (1 << 30);
+  for (int i = 0; i < n; ++i) {
+    if (ev_mask[i]) continue;
+    const int K = net.card[i];
+    o << "      {  // node " << i << ": card " << K << ", " << (net.child_ptr[i + 1] - net.child_ptr[i]) << " children\n";
+    o << "        u32 r; NEXT_R(r);\n";
+    o << "        const double uu = ((double)r + 0.5) * (1.0 / 4294967296.0);\n";
+    o << "        double";
+    for (int v = 0; v < K; ++v) o << (v ? ", p" : " p") << v;
+    o << ";\n";
+    bool first = true;
+    auto emit_cpd = [&](int c, bool own) {
+      // element index of the row P(. | pa_c) with x_i left out; `step` = stride of x_i in elements
+      const int Kc = net.card[c];
+      std::ostringstream idx;
+      idx << (uint32_t)net.cpt_off[c] << "u";
+      uint32_t step = own ? 1u : 0u;
+      int64_t stride = 1;
+      for (int k = net.par_ptr[c]; k < net.par_ptr[c + 1]; ++k) {
+        const int pa = net.par_idx[k];
+        if (!own && pa == i) step = (uint32_t)(stride * Kc);
+        else idx << " + (u32)st[" << pa << " * NT] * " << (uint32_t)(stride * Kc) << "u";
+        stride *= net.card[pa];
+      }
+      if (!own) idx << " + (u32)st[" << c << " * NT]";
+      o << "        { const double* pr = cpt + (" << idx.str() << ");";
+      for (int v = 0; v < K; ++v)
+        o << " p" << v << (first ? " = " : " *= ") << "__ldg(pr + " << (uint32_t)v * step << "u);";
+      o << " }  // " << (own ? "own CPD" : "child ") << c << "\n";
+      first = false;
+    };
+    for (int k = net.child_ptr[i]; k < net.child_ptr[i + 1]; ++k) emit_cpd(net.child_idx[k], false);
+    emit_cpd(i, true);
+    o << "        double sum = p0;";
+    for (int v = 1; v < K; ++v) o << " sum += p" << v << ";";
+    o << "\n        const double t = uu * sum;\n";
+    o << "        u32 pick = 0u; double cw = p0; bool go = true;\n";
+    for (int v = 1; v < K; ++v)
+      o << "        go = go && (cw < t); if (go) { cw += p" << v << "; pick = " << v << "u; }\n";
+    o << "        st[" << i << " * NT] = (unsigned char)pick;\n";
+    if (!full) o << "        TICK\n";
+    o << "      }\n";
+    if (++emitted % sync_every == 0) o << "      __syncthreads();  // keep the CTA's warps on the same code window\n";
+  }
+  if (full) o << "      TICK\n";
+  o << "    }\n";
+  o << "  finished:\n";
+  o << "    if (state_io && live) for (u32 i = 0; i < NN; ++i) state_io[ci * NN + i] = st[i * NT];\n";
+  o << "  }\n";
+  if (reg_bins) {
+    for (uint32_t c = 0; c < ncell; ++c) {
+      o << "  { u32 v = live ? n" << c << " : 0u;\n";
+      o << "#pragma unroll\n    for (int of = 16; of > 0; of >>= 1) v += __shfl_xor_sync(0xffffffffu, v, of);\n";
+      o << "    if ((tid & 31u) == 0u && v) atomicAdd(&bins[" << c << "], (unsigned long long)v); }\n";
+    }
+  }
+  o << "  __syncthreads();\n";
+  o << "  for (u32 c = tid; c < NCELL; c += NT) if (bins[c]) atomicAdd(&out[c], (double)bins[c]);\n";
+  o << "}\n";
+  if (n_free_out) *n_free_out = n_free;
+  return o.str();
+}
+
+thread_local int tl_gibbs_mode = 0;  // 0 auto, 1 generic only, 2 specialised required
+
+int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
+                                 const std::vector<int64_t>& qstride, uint32_t ncell, bool full, uint64_t first_chain,
+                                 uint64_t n_chains, int64_t burn_in, int64_t thin, int64_t total, uint64_t seed,
+                                 double* out_dev, double* chain_counts_dev, uint8_t* state_dev, int32_t init_from_state,
+                                 bool* used) {
+  *used = false;
+  if (tl_gibbs_mode == 1) return BN_OK;
+  const bool must = tl_gibbs_mode == 2;
+  Driver& drv = driver();
+  if (!nvrtc().ok || !drv.ok) {
+    BN_REQUIRE(!must, BN_UNSUPPORTED, "specialised Gibbs kernel unavailable: NVRTC / driver entry points missing");
+    return BN_OK;
+  }
+  bool ok = net->n <= 1024 && net->cpt_off[net->n] < (int64_t)0x7fffffff && total < (int64_t)(1ll << 26);  // 32 lanes x
+  // total kept samples must fit the u32 warp sums
+  for (int i = 0; i < net->n && ok; ++i) ok = net->card[i] <= GIBBS_SPEC_MAX_CARD;
+  const DevProps& dp = dev_props(net->device);
+  // small CTAs: the grid balances dynamically and 64-thread CTAs measured fastest (profiles/r1d_gibbs_spec_sweep.txt)
+  int T = n_chains >= (uint64_t)dp.sm_count * 2048 ? 128 : 64;
+  while (T > 64 && (size_t)ncell * 8 + (size_t)net->n * T + 1024 > (size_t)dp.max_smem_optin) T -= 32;
+  if (const char* e = getenv("BN_GIBBS_THREADS")) T = atoi(e);
+  const size_t smem = (size_t)ncell * 8 + (size_t)net->n * T;
+  if (!ok || smem + 1024 > (size_t)dp.max_smem_optin) {
+    BN_REQUIRE(!must, BN_UNSUPPORTED, "network not supported by the specialised Gibbs kernel (card > %d or too large)",
+               GIBBS_SPEC_MAX_CARD);
+    return BN_OK;
+  }
+  std::vector<char> ev_mask((size_t)net->n, 0);
+  for (int i = 0; i < net->n; ++i) ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0;
+  std::string key((size_t)net->n, '0');
+  for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
+  key += std::string("|g") + (full ? "F" : "N") + std::to_string(T);
+  for (uint32_t j = 0; j < n_query; ++j) key += "," + std::to_string(query[j]);
+  SpecKernel* k = nullptr;
+  auto it = net->spec_cache.find(key);
+  if (it != net->spec_cache.end()) {
+    k = it->second;
+  } else {
+    uint32_t n_free = 0;
+    int minb = 8;  // <= 128 registers per thread at T = 64
+    if (const char* e = getenv("BN_GIBBS_MINB")) minb = atoi(e);
+    const std::string src = gen_gibbs_source(*net, ev_mask, query, n_query, qstride, ncell, full, T, minb, &n_free);
+    const std::string gkey = std::to_string(net->device) + "|" + src;
+    std::lock_guard<std::mutex> lk(g_spec_mu);
+    auto git = g_spec.find(gkey);
+    if (git != g_spec.end()) {
+      k = git->second.get();
+    } else {
+      std::vector<char> cubin;
+      std::string log;
+      g_spec_compiles.fetch_add(1);
+      int32_t rc = nvrtc_compile(src, &cubin, &log);
+      if (rc != BN_OK) {
+        if (must) return rc;
+        g_spec[gkey] = nullptr;
+      } else {
+        std::unique_ptr<SpecKernel> nk(new SpecKernel());
+        CUresult r = drv.ModuleLoadData(&nk->mod, cubin.data());
+        if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
+        r = drv.ModuleGetFunction(&nk->fn, nk->mod, "gibbs_spec");
+        if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
+        nk->threads = T;
+        nk->smem = smem;
+        nk->n_live = n_free;
+        r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+        if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
+        drv.FuncGetAttribute(&nk->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, nk->fn);
+        k = nk.get();
+        g_spec[gkey] = std::move(nk);
+      }
+    }
+    net->spec_cache[key] = k;
+  }
+  if (!k) {
+    BN_REQUIRE(!must, BN_CUDA_ERR, "specialised Gibbs kernel failed to compile earlier for this (net, evidence, query)");
+    return BN_OK;
+  }
+  // evidence values -> device scratch
+  cudaStream_t s = tl_stream;
+  const size_t total_b = (size_t)net->n + 16;
+  if (net->scratch.n < total_b) BN_CUDA_TRY(net->scratch.alloc(total_b * 2));
+  std::vector<unsigned char> host(total_b, 0);
+  for (int i = 0; i < net->n; ++i) host[i] = (unsigned char)(evidence ? evidence[i] : -1);
+  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, host.data(), total_b, cudaMemcpyHostToDevice, s));
+  const double* cpt = net->d_cpt.p;
+  const signed char* ev_dev = reinterpret_cast<const signed char*>(net->scratch.p);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  long long bi = burn_in, th = thin, tot = total;
+  void* args[] = {(void*)&cpt, (void*)&ev_dev, (void*)&first_chain, (void*)&n_chains, (void*)&k0, (void*)&k1, (void*)&bi,
+                  (void*)&th, (void*)&tot, (void*)&out_dev, (void*)&chain_counts_dev, (void*)&state_dev,
+                  (void*)&init_from_state};
+  const unsigned grid = (unsigned)((n_chains + k->threads - 1) / k->threads);
+  CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)s, args, nullptr);
+  if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(gibbs_spec)", r);
+  count_launch();
+  *used = true;
+  return BN_OK;
+}
+
 }  // namespace bn
 
 using namespace bn;
@@ -538,10 +797,52 @@ extern "C" {
 
 uint64_t bn_lw_spec_compile_count(void) { return bn::g_spec_compiles.load(); }
 
+int32_t bn_set_gibbs_mode(int32_t mode) {
+  BN_REQUIRE(mode >= 0 && mode <= 2, BN_BAD_ARG, "bn_set_gibbs_mode: mode %d outside 0..2", mode);
+  bn::tl_gibbs_mode = mode;
+  return BN_OK;
+}
+
 int32_t bn_set_lw_mode(int32_t mode, int32_t prune) {
   BN_REQUIRE(mode >= 0 && mode <= 2, BN_BAD_ARG, "bn_set_lw_mode: mode %d outside 0..2", mode);
   bn::tl_lw_mode = mode;
   bn::tl_lw_prune = prune ? 1 : 0;
+  return BN_OK;
+}
+
+// Host-only: the specialised Gibbs inference source for a flat network (and its NVRTC cubin size when asked).
+int32_t bn_gibbs_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                             const int64_t* cpt_off, const double* cpt, const int8_t* evidence, const int32_t* query,
+                             int32_t n_query, int32_t full, int32_t threads, char* out_src, int64_t cap, int64_t* out_len,
+                             int64_t* cubin_size) {
+  BN_REQUIRE(card && par_ptr && cpt_off && cpt && out_len, BN_BAD_ARG, "bn_gibbs_spec_source: NULL argument");
+  Net net;
+  net.n = n_nodes;
+  net.card.assign(card, card + n_nodes);
+  net.par_ptr.assign(par_ptr, par_ptr + n_nodes + 1);
+  net.par_idx.assign(par_idx, par_idx + par_ptr[n_nodes]);
+  net.cpt_off.assign(cpt_off, cpt_off + n_nodes + 1);
+  net.cpt.assign(cpt, cpt + cpt_off[n_nodes]);
+  build_children(&net);
+  std::vector<int64_t> qstride;
+  int64_t cells = 1;
+  for (int j = 0; j < n_query; ++j) { qstride.push_back(cells); cells *= card[query[j]]; }
+  std::vector<char> ev_mask((size_t)n_nodes, 0);
+  for (int i = 0; i < n_nodes; ++i) ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0;
+  const std::string src = gen_gibbs_source(net, ev_mask, query, (uint32_t)n_query, qstride, (uint32_t)cells, full != 0,
+                                           threads > 0 ? threads : 64, 1, nullptr);
+  *out_len = (int64_t)src.size();
+  if (out_src && cap > 0) {
+    const size_t m = src.size() < (size_t)(cap - 1) ? src.size() : (size_t)(cap - 1);
+    memcpy(out_src, src.data(), m);
+    out_src[m] = 0;
+  }
+  if (cubin_size) {
+    std::vector<char> cubin;
+    std::string log;
+    BN_TRY(nvrtc_compile(src, &cubin, &log));
+    *cubin_size = (int64_t)cubin.size();
+  }
   return BN_OK;
 }
 

@@ -89,6 +89,8 @@ int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* que
  * prune: != 0 lets the specialised kernel skip "barren" nodes (not an ancestor of a query or evidence node);
  *        draw indices are static, so the counts are bit-identical either way.  Default: mode 0, prune 1. */
 int32_t bn_set_lw_mode(int32_t mode, int32_t prune);
+/* Same selection for bn_gibbs_infer: 0 = auto, 1 = generic interpreter kernel, 2 = specialised required. */
+int32_t bn_set_gibbs_mode(int32_t mode);
 /* Number of NVRTC compiles since load (kernels are cached process-wide by generated source). */
 uint64_t bn_lw_spec_compile_count(void);
 /* Host-only (no GPU): emit the CUDA source the specialised LW kernel would be built from for this flat network
@@ -97,6 +99,11 @@ int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* p
                           const int64_t* cpt_off, const double* cpt, const int8_t* evidence, const int32_t* query,
                           int32_t n_query, int32_t prune, char* out_src, int64_t cap, int64_t* out_len,
                           int64_t* cubin_size, int32_t* n_live);
+
+int32_t bn_gibbs_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                             const int64_t* cpt_off, const double* cpt, const int8_t* evidence, const int32_t* query,
+                             int32_t n_query, int32_t full, int32_t threads, char* out_src, int64_t cap, int64_t* out_len,
+                             int64_t* cubin_size);
 
 /* ---- table samplers: rand(bn, n) / rand(bn, n, evidence) / get_weighted_dataframe
  *      src/sampling.jl:24-41,52-57 (ancestral), :72-93 (rejection, <= max_attempts tries),

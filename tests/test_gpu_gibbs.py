@@ -16,9 +16,19 @@ from test_gpu_sampling import random_case
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture
+def gibbs_mode(bn):
+    yield bn.set_gibbs_mode
+    bn.set_gibbs_mode("auto")
+
+
+@pytest.mark.parametrize("mode", ["generic", "specialized"])
 @pytest.mark.parametrize("full", [False, True])
 @pytest.mark.parametrize("seed,n_nodes,n_ev", [(0, 30, 3), (1, 200, 20), (2, 9, 0)])
-def test_gibbs_infer_counts_equal_oracle(bn, full, seed, n_nodes, n_ev):
+def test_gibbs_infer_counts_equal_oracle(bn, gibbs_mode, mode, full, seed, n_nodes, n_ev):
+    """Both Gibbs kernels -- the interpreter (csrc/gibbs.cu) and the NVRTC network-specialised one
+    (csrc/specialize.cu) -- reproduce the oracle's chains exactly: counts, final states, per-chain counts."""
+    gibbs_mode(mode)
     net, lay, on, query, evidence = random_case(bn, n_nodes, seed, n_ev)
     cls = bn.GibbsSamplingFull if full else bn.GibbsSamplingNodewise
     nsamples, burn, thin = (60, 20, 3) if full else (1500, 500, 5)
@@ -32,8 +42,10 @@ def test_gibbs_infer_counts_equal_oracle(bn, full, seed, n_nodes, n_ev):
     assert counts.sum() == 300 * -(-(nsamples - burn) // thin)
 
 
-def test_gibbs_state_resume_equals_oracle(bn):
+@pytest.mark.parametrize("mode", ["generic", "specialized"])
+def test_gibbs_state_resume_equals_oracle(bn, gibbs_mode, mode):
     """im.state semantics (src/Inference/gibbs.jl:64,83-88): a second call continues the chains."""
+    gibbs_mode(mode)
     net, lay, on, query, evidence = random_case(bn, 25, 4, 2)
     im = bn.GibbsSamplingNodewise(nsamples=400, burn_in=100, thin=2, n_chains=64, seed=9)
     inf = bn.InferenceState(net, query, evidence)
