@@ -54,6 +54,8 @@ struct ContractParams {
   int32_t lead, pf_bytes, pf_ns;  // TMA L2 prefetch of the leading operand's next-tile rows (pf_bytes = 0: off)
   int32_t vec128[MAXF];  // operand is contiguous + 16-byte aligned along the vector dim: one 128-bit load
   int32_t vstep[MAXF];   // otherwise two 64-bit loads `vstep` elements apart (0 = broadcast)
+  int32_t rowvec[MAXF];  // the tile's 4 rows are 4 CONSECUTIVE elements of this operand (its two fastest dims were
+                         // chosen as the row dims): one thread fetches them as 2 x 128-bit instead of 4 x 64-bit
 };
 
 enum { VEC_NONE = 0, VEC_LO = 1, VEC_S = 2 };
@@ -193,9 +195,30 @@ __global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contr
         if constexpr (!SUM) {
           double2 v[JU][NF];
 #pragma unroll
-          for (int u = 0; u < JU; ++u)
+          for (int k = 0; k < NF; ++k) {
+            bool done = false;
+            if constexpr (JU == 4) {
+              if (p.rowvec[k]) {
+                // gathered operand whose dim order differs from the output's: a warp load touches 32 distinct
+                // 128-byte lines whatever we do (the lanes differ in dims that are far apart in this operand), so
+                // make every touched sector count: 32 useful bytes per 32-byte sector instead of 8
+                const double2* bx = reinterpret_cast<const double2*>(p.f[k] + off[0][k]);
+                const double2 x01 = __ldg(bx), x23 = __ldg(bx + 1);
+                double2 y01 = x01, y23 = x23;
+                if (vstep[k] != 0) {
+                  const double2* by = reinterpret_cast<const double2*>(p.f[k] + off[0][k] + vstep[k]);
+                  y01 = __ldg(by); y23 = __ldg(by + 1);
+                }
+                v[0][k] = make_double2(x01.x, y01.x); v[1][k] = make_double2(x01.y, y01.y);
+                v[2][k] = make_double2(x23.x, y23.x); v[3][k] = make_double2(x23.y, y23.y);
+                done = true;
+              }
+            }
+            if (!done) {
 #pragma unroll
-            for (int k = 0; k < NF; ++k) v[u][k] = ld2(p.f[k], off[u][k], vec128[k], vstep[k]);
+              for (int u = 0; u < JU; ++u) v[u][k] = ld2(p.f[k], off[u][k], vec128[k], vstep[k]);
+            }
+          }
 #pragma unroll
           for (int u = 0; u < JU; ++u) {
             acc[u] = v[u][0];
@@ -499,7 +522,59 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
   long long H = 1;
   int nj = 0;
   const long long h_target = 4ll * G;
-  for (int pass = 0; pass < 2; ++pass)
+  // Row-vector gather (plain products of <= 3 operands, one row group): if a large non-leading operand has its two
+  // fastest dims outside lo, make exactly those dims the tile's 4 rows so that a thread's 4 row values are 4
+  // consecutive doubles of that operand (see rowvec in the kernel).  Skipped when the leading operand lacks some
+  // output dim (then those dims go into the rows instead, which saves an HBM re-read of the leading operand).
+  int rowvec_op = -1;
+  if (vec == VEC_LO && ns == 0 && nf <= 3 && G == 1 && !getenv("BN_NO_ROWVEC")) {
+    bool lead_has_all = true;
+    for (int i = nlo; i < no; ++i) lead_has_all = lead_has_all && st[lead][i] != 0;
+    long long best_len = 1 << 15;  // smaller operands live in L1/L2 anyway
+    for (int k = 0; k < nf && lead_has_all; ++k) {
+      if (k == lead || ops[k].dims.empty()) continue;
+      long long len = 1;
+      for (int c : ops[k].card) len *= c;
+      if (len < best_len || (reinterpret_cast<uintptr_t>(p.f[k]) % 32) != 0) continue;
+      // its fastest dims as positions in the output
+      const int p0 = find_dim(out_dims, ops[k].dims[0]);
+      const int p1 = ops[k].dims.size() > 1 ? find_dim(out_dims, ops[k].dims[1]) : -1;
+      if (p0 >= nlo && out_card[p0] == 4) { rowvec_op = k; best_len = len; taken.assign(no, 0); taken[p0] = 1; }
+      else if (p0 >= nlo && p1 >= nlo && out_card[p0] * out_card[p1] == 4) {
+        rowvec_op = k; best_len = len; taken.assign(no, 0); taken[p0] = 1; taken[p1] = 1;
+      }
+    }
+    if (rowvec_op >= 0) {
+      const int p0 = find_dim(out_dims, ops[rowvec_op].dims[0]);
+      order.push_back(p0); H *= out_card[p0]; ++nj;
+      if (H < 4) { const int p1 = find_dim(out_dims, ops[rowvec_op].dims[1]); order.push_back(p1); H *= out_card[p1]; ++nj; }
+    }
+  }
+  // Sector rule for gathered operands: the 4 doubles of a 32-byte sector of the largest non-leading operand differ in
+  // its fastest dims.  Any of those dims that is not a lo dim (lanes / warps of the same CTA) becomes a row dim, so a
+  // sector is consumed by one thread back to back (L1 hit) instead of by 2-4 tiles far apart in time (2-4x the
+  // L2 -> L1 traffic for that operand).
+  if (rowvec_op < 0 && nf >= 2) {
+    int big = -1;
+    long long big_len = 1 << 15;
+    for (int k = 0; k < nf; ++k) {
+      if (k == lead) continue;
+      long long len = 1;
+      for (int c : ops[k].card) len *= c;
+      if (len >= big_len) { big_len = len; big = k; }
+    }
+    if (big >= 0) {
+      long long run = 1;
+      for (size_t i = 0; i < ops[big].dims.size() && run < 4; ++i) {
+        const int pos = find_dim(out_dims, ops[big].dims[i]);
+        run *= ops[big].card[i];
+        if (pos >= nlo && !taken[pos] && H * out_card[pos] <= 16) {
+          taken[pos] = 1; order.push_back(pos); H *= out_card[pos]; ++nj;
+        }
+      }
+    }
+  }
+  for (int pass = 0; pass < 2 && rowvec_op < 0; ++pass)
     for (int i = nlo; i < no; ++i) {
       if (taken[i] || (pass == 0 && st[lead][i] != 0)) continue;
       if (H >= h_target || H * out_card[i] > 1024) continue;
@@ -540,6 +615,7 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
     const bool aligned = (reinterpret_cast<uintptr_t>(p.f[k]) % 16) == 0;
     p.vec128[k] = (vec != VEC_NONE && sv == 1 && aligned) ? 1 : 0;
     p.vstep[k] = (int32_t)sv;
+    p.rowvec[k] = (k == rowvec_op) ? 1 : 0;
   }
   // L2 prefetch plan: the leading operand's bytes for one (row, summed state) must be one contiguous, 16-byte
   // aligned span: its strides over the lo dims are the running product of their cards (after the vector summed

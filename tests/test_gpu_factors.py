@@ -277,3 +277,39 @@ def test_full_size_properties_2_24(bn):
     n1 = fa.normalize().potential.reshape(-1, order="F")
     assert abs(n1.sum() - 1.0) < 1e-12
     np.testing.assert_allclose(n1, A / A.sum(), rtol=RTOL)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_product_with_reordered_large_operand_row_vector_path(bn, seed):
+    """Products whose second operand is large and ordered differently from the output take the row-vector gather
+    path (the operand's two fastest dims become the tile rows); mixed radix incl. a 4-state leading dim, a third
+    small operand, and operands that lack the output's first dim.  Bit-exact vs the oracle's fold."""
+    rng = np.random.default_rng(50 + seed)
+    nd = 17
+    cards = [2] * nd
+    if seed % 2:
+        cards[int(rng.integers(9, nd))] = 4
+        cards[int(rng.integers(0, 6))] = 3
+    names = [f"rv{seed}_{i}" for i in range(nd)]
+    A = rng.random(cards)
+    perm = [int(x) for x in rng.permutation(nd)]
+    if seed % 2:  # put the 4-state dim first in the second operand
+        four = cards.index(4)
+        perm.remove(four)
+        perm.insert(0, four)
+    if seed >= 4:  # second operand lacks the output's first dim
+        perm.remove(0)
+    B = rng.random([cards[i] for i in perm])
+    fa, fb = F(bn, names, A), F(bn, [names[i] for i in perm], B)
+    ref = NpFactor(list(range(nd)), A) * NpFactor(perm, B)
+    got = fa * fb
+    assert got.dimensions == [names[i] for i in ref.dimensions]
+    assert np.array_equal(got.potential, ref.potential)
+    # a third, small operand through the fused n-ary product
+    small = sorted(int(x) for x in rng.choice(nd, size=3, replace=False))
+    Cc = rng.random([cards[i] for i in small])
+    fc = F(bn, [names[i] for i in small], Cc)
+    ref3 = ref * NpFactor(small, Cc)
+    got3 = bn.eliminate([fa, fb, fc], [])
+    assert got3.dimensions == [names[i] for i in ref3.dimensions]
+    assert np.array_equal(got3.potential, ref3.potential)
