@@ -116,6 +116,7 @@ void spec_cache_clear(Net* net);
 struct Net {
   ~Net() { spec_cache_clear(this); }
   std::unordered_map<std::string, SpecKernel*> spec_cache;
+  std::unordered_map<std::string, double> spec_demand;  // work requested per key before its kernel was compiled
   int device = 0;
   int n = 0;
   // host copies (planning is host-side)

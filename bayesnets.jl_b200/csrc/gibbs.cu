@@ -344,11 +344,16 @@ static int32_t stage_gibbs(Net* net, const int8_t* evidence, uint32_t T, const i
   return BN_OK;
 }
 
-static int gibbs_threads(const DevProps& dp, int n_nodes, size_t extra) {
-  // keep >= 2 CTAs per SM where the state fits; one chain per thread
+static int gibbs_threads(const DevProps& dp, int n_nodes, size_t extra, uint64_t n_chains) {
+  // one chain per thread; the largest CTA whose state fits and that still gives every SM >= 4 CTAs to balance
+  // (65536 chains in 256-thread CTAs are 1.7 CTAs per SM: a third of the SMs would run twice as long)
+  int fit = 0;
   for (int t : {256, 128, 64, 32})
-    if ((size_t)n_nodes * t + extra + 64 <= (size_t)dp.max_smem_optin) return t;
-  return 0;
+    if ((size_t)n_nodes * t + extra + 64 <= (size_t)dp.max_smem_optin) {
+      if (!fit) fit = t;
+      if (n_chains >= (uint64_t)t * dp.sm_count * 4) return t;
+    }
+  return fit ? (fit > 64 ? 64 : fit) : 0;
 }
 
 }  // namespace bn
@@ -397,7 +402,7 @@ static int32_t gibbs_infer_impl(bn_net_t h, const int8_t* evidence, const int32_
     }
   }
   const DevProps& dp = dev_props(net->device);
-  const int T = gibbs_threads(dp, net->n, (size_t)ncell * 8);
+  const int T = gibbs_threads(dp, net->n, (size_t)ncell * 8, n_chains);
   BN_REQUIRE(T > 0, BN_UNSUPPORTED, "network too large for the Gibbs kernel (%d nodes)", net->n);
   GibbsDevice dev;
   GibbsArgs a{};
@@ -483,7 +488,7 @@ int32_t bn_gibbs_sample(bn_net_t h, const int8_t* evidence, uint64_t first_chain
   BN_CUDA_TRY(cudaSetDevice(net->device));
   if (n_chains == 0) return BN_OK;
   const DevProps& dp = dev_props(net->device);
-  const int T = gibbs_threads(dp, net->n, 0);
+  const int T = gibbs_threads(dp, net->n, 0, n_chains);
   BN_REQUIRE(T > 0, BN_UNSUPPORTED, "network too large for the Gibbs kernel (%d nodes)", net->n);
   cudaStream_t s = tl_stream;
   GibbsDevice dev;

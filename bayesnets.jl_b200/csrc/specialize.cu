@@ -382,6 +382,17 @@ static int32_t cu_fail(const char* what, CUresult r) {
 thread_local int tl_lw_mode = 0;   // 0 auto, 1 generic only, 2 specialised required
 thread_local int tl_lw_prune = 1;  // barren-node elimination in the specialised kernel
 
+// Tiered JIT for the "auto" modes.  NVRTC costs ~10 ms per node for the particle kernels and ~35 ms per node for Gibbs
+// (1 s / 7 s for the 100- / 200-node benchmark nets), which only pays off once enough work has been requested for
+// the same (structure, evidence mask, query): the interpreter serves calls until the cumulative demand for a key
+// crosses `threshold` (particles / rows, or node updates), then the specialised kernel is compiled and cached.
+// Explicit modes (bn_set_lw_mode / bn_set_gibbs_mode = 2) compile immediately.
+static bool jit_worthwhile(Net* net, const std::string& key, double work, double threshold) {
+  double& d = net->spec_demand[key];
+  d += work;
+  return d >= threshold;
+}
+
 struct SpecLaunch {
   SpecMode mode = SPEC_INFER;
   const int8_t* evidence = nullptr;  // host, n entries or NULL
@@ -426,6 +437,8 @@ static int32_t launch_specialized(Net* net, const SpecLaunch& a, bool* used) {
   auto it = net->spec_cache.find(key);
   if (it != net->spec_cache.end()) {
     k = it->second;
+  } else if (!must && !jit_worthwhile(net, key, (double)a.n, 2e9)) {
+    return BN_OK;  // auto mode: the interpreter kernel serves this call (see jit_worthwhile)
   } else {
     SpecShape shp;
     if (const char* e = getenv("BN_SPEC_THREADS")) shp.threads = atoi(e);
@@ -727,6 +740,8 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
   auto it = net->spec_cache.find(key);
   if (it != net->spec_cache.end()) {
     k = it->second;
+  } else if (!must && !jit_worthwhile(net, key, (double)n_chains * (double)(burn_in + total * thin) * (full ? net->n : 1), 2e11)) {
+    return BN_OK;
   } else {
     uint32_t n_free = 0;
     int minb = 8;  // <= 128 registers per thread at T = 64

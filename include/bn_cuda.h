@@ -84,8 +84,10 @@ int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* que
                         uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_dev);
 
 /* LW kernel selection for subsequent calls from this host thread.
- * mode : 0 = auto (network-specialised NVRTC kernel when it can be built, else the generic interpreter),
- *        1 = generic interpreter only, 2 = specialised required (error if unavailable).
+ * mode : 0 = auto: the generic interpreter kernel serves calls until the cumulative work requested for the same
+ *            (structure, evidence mask, query) reaches 2e9 particles/rows (2e11 node updates for Gibbs), then the
+ *            network-specialised kernel is NVRTC-compiled (~10 ms per node) and cached process-wide;
+ *        1 = generic interpreter only, 2 = specialised required (compiled on first use; error if unavailable).
  * prune: != 0 lets the specialised kernel skip "barren" nodes (not an ancestor of a query or evidence node);
  *        draw indices are static, so the counts are bit-identical either way.  Default: mode 0, prune 1. */
 int32_t bn_set_lw_mode(int32_t mode, int32_t prune);

@@ -35,6 +35,7 @@ def run(bn, torch, n_chains=65536, nsamples=2000, burn_in=1000, thin=5, reps=5, 
     from bayesnets_jl_b200 import _lib
     from bayesnets_jl_b200.device_layout import device_net
     net, lay, query, evidence = build_case(bn)
+    bn.set_gibbs_mode(os.environ.get("BN_GIBBS_KERNEL", "specialized"))  # auto would JIT only after 2e11 updates
     dn = device_net(net, 0)
     ev, q = lay.evidence_vector(evidence), lay.query_indices(query)
     ncell = int(np.prod([lay.card[i] for i in q]))

@@ -84,6 +84,9 @@ def main():
         return FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
 
     net, lay, query, evidence = bench.build_case(bn)
+    # the network-specialised kernels, compiled up front (the "auto" modes JIT only after enough cumulative work)
+    bn.set_lw_mode("specialized", True)
+    bn.set_gibbs_mode("specialized")
     on = onet(lay)
     dn = device_net(net, 0)
     ev, q = lay.evidence_vector(evidence), lay.query_indices(query)
