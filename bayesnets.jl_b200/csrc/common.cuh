@@ -125,8 +125,7 @@ struct Net {
   std::vector<double> cpt;
   std::vector<int32_t> child_ptr, child_idx;  // children in ascending topological index
   // device copies
-  DevBuf<int32_t> d_card, d_par_ptr, d_par_idx, d_child_ptr, d_child_idx;
-  DevBuf<int32_t> d_cpt_off;  // 32-bit offsets when the table fits (always for sampling paths)
+  DevBuf<int32_t> d_card;
   DevBuf<double> d_cpt;
   // scratch reused across calls (grown on demand)
   DevBuf<uint8_t> scratch;

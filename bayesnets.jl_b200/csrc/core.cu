@@ -169,17 +169,11 @@ int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_p
   net->cpt.assign(cpt, cpt + cpt_off[n_nodes]);
   build_children(net);
   cudaStream_t s = bn::tl_stream;
-  std::vector<int32_t> off32(n_nodes + 1);
-  bool fits32 = cpt_off[n_nodes] < (int64_t)0x7fffffff;
-  for (int i = 0; i <= n_nodes; ++i) off32[i] = fits32 ? (int32_t)cpt_off[i] : 0;
+  // only what kernels read lives in HBM: the fp64 CPTs (Gibbs, Factor(bn, node)) and the cardinalities; graph
+  // structure is consumed by the host-side planners (sampling programs, code generators, elimination order)
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   chk(net->d_card.upload(net->card.data(), net->card.size(), s));
-  chk(net->d_par_ptr.upload(net->par_ptr.data(), net->par_ptr.size(), s));
-  chk(net->d_par_idx.upload(net->par_idx.data(), net->par_idx.size(), s));
-  chk(net->d_child_ptr.upload(net->child_ptr.data(), net->child_ptr.size(), s));
-  chk(net->d_child_idx.upload(net->child_idx.data(), net->child_idx.size(), s));
-  chk(net->d_cpt_off.upload(off32.data(), off32.size(), s));
   chk(net->d_cpt.upload(net->cpt.data(), net->cpt.size(), s));
   chk(cudaStreamSynchronize(s));
   if (e != cudaSuccess) {

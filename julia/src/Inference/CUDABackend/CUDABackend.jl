@@ -35,6 +35,21 @@ function _bn_check(rc::Int32)
     error("libbn_cuda status $rc: $msg")
 end
 
+"""
+    set_lw_mode(mode::Symbol=:auto; prune::Bool=true)
+    set_gibbs_mode(mode::Symbol=:auto)
+
+Kernel selection for this thread (include/bn_cuda.h): `:auto` lets the generic interpreter kernels serve calls until
+enough work has been requested for one (structure, evidence mask, query) to amortise the NVRTC compile of the
+network-specialised kernel; `:generic` / `:specialized` force one or the other. `prune` lets the specialised LW
+kernel skip barren nodes (never changes a count bit).
+"""
+const _KERNEL_MODES = Dict(:auto => Int32(0), :generic => Int32(1), :specialized => Int32(2))
+set_lw_mode(mode::Symbol=:auto; prune::Bool=true) =
+    _bn_check(ccall((:bn_set_lw_mode, libbn_cuda), Int32, (Int32, Int32), _KERNEL_MODES[mode], prune))
+set_gibbs_mode(mode::Symbol=:auto) =
+    _bn_check(ccall((:bn_set_gibbs_mode, libbn_cuda), Int32, (Int32,), _KERNEL_MODES[mode]))
+
 # one resident copy of the network per BayesNet object (WeakKeyDict so it dies with the net)
 const _device_nets = WeakKeyDict{Any,DeviceNet}()
 device_net(bn::DiscreteBayesNet; device::Integer=0) = get!(() -> DeviceNet(bn; device=device), _device_nets, bn)
