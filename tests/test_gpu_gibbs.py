@@ -159,3 +159,39 @@ def test_gibbs_sample_reference_suite(bn, golden):
     # impossible evidence: no initial sample with non-zero probability (src/gibbs.jl:332-334)
     with pytest.raises(RuntimeError):
         bn.gibbs_sample(d_bn, 5, 10, consistent_with={"a": 2})
+
+
+def test_gibbs_specialized_falls_back_for_large_cardinalities(bn, gibbs_mode):
+    """Nodes with more than 8 states are outside the specialised generator: "auto" silently uses the interpreter
+    kernel, "specialized" refuses loudly (NotImplementedError <- BN_UNSUPPORTED)."""
+    rng = np.random.default_rng(0)
+    net = bn.BayesNet()
+    net.push(bn.CategoricalCPD("r", [], [], [rng.dirichlet(np.ones(11))]))
+    net.push(bn.CategoricalCPD("m", ["r"], [11], [rng.dirichlet(np.ones(3)) for _ in range(11)]))
+    gibbs_mode("specialized")
+    with pytest.raises(NotImplementedError):
+        bn.GibbsSamplingNodewise(nsamples=50, burn_in=10, thin=1, n_chains=32).raw_counts(bn.InferenceState(net, ["m"], {}))
+    gibbs_mode("auto")
+    c = bn.GibbsSamplingNodewise(nsamples=50, burn_in=10, thin=1, n_chains=32, seed=1).raw_counts(bn.InferenceState(net, ["m"], {}))
+    assert c.sum() == 32 * 40
+
+
+@pytest.mark.parametrize("mode", ["generic", "specialized"])
+def test_gibbs_wide_query_and_cards_up_to_8(bn, gibbs_mode, mode):
+    """> 16 query cells (MATCH.ANY-grouped atomics in the specialised kernel) and 5..8-state nodes."""
+    rng = np.random.default_rng(3)
+    net = bn.BayesNet()
+    net.push(bn.CategoricalCPD("a", [], [], [rng.dirichlet(np.ones(5))]))
+    net.push(bn.CategoricalCPD("b", ["a"], [5], [rng.dirichlet(np.ones(8)) for _ in range(5)]))
+    net.push(bn.CategoricalCPD("c", ["a", "b"], [5, 8], [rng.dirichlet(np.ones(6)) for _ in range(40)]))
+    net.push(bn.CategoricalCPD("d", ["c"], [6], [rng.dirichlet(np.ones(2)) for _ in range(6)]))
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    gibbs_mode(mode)
+    for full in (False, True):
+        cls = bn.GibbsSamplingFull if full else bn.GibbsSamplingNodewise
+        im = cls(nsamples=300, burn_in=60, thin=2, n_chains=200, seed=7)
+        c = im.raw_counts(bn.InferenceState(net, ["a", "b"], {"d": 1}))
+        oc, _ = capi.gibbs_infer(on, lay.evidence_vector({"d": 1}), lay.query_indices(["a", "b"]), 200, 300, 60, 2,
+                                 full=full, seed=7)
+        assert np.array_equal(c, oc.ravel(order="F"))

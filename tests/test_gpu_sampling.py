@@ -236,3 +236,36 @@ def test_lw_specialized_kernel_is_cached_per_evidence_mask(bn, lw_mode):
                                mode=capi.DEVICE_SPEC)
     np.testing.assert_allclose(counts, oc.ravel(order="F"), rtol=1e-12, atol=1e-300)
     assert sw == pytest.approx(osw, rel=1e-12)
+
+
+@pytest.mark.parametrize("mode", ["generic", "specialized"])
+def test_edge_cardinalities_and_deterministic_tables(bn, lw_mode, mode):
+    """Single-state nodes, a 7-state node (two threshold words per row), deterministic CPT rows (thresholds 0 and
+    2^31, i.e. 'always' / 'never') and impossible evidence (every weight 0 -> NaN posterior like the reference's 0/0)."""
+    rng = np.random.default_rng(11)
+    net = bn.BayesNet()
+    net.push(bn.CategoricalCPD("one", [], [], [[1.0]]))
+    net.push(bn.CategoricalCPD("det", ["one"], [1], [[0.0, 1.0, 0.0]]))
+    net.push(bn.CategoricalCPD("wide", ["det"], [3], [rng.dirichlet(np.ones(7)) for _ in range(3)]))
+    net.push(bn.CategoricalCPD("leaf", ["wide", "det"], [7, 3], [rng.dirichlet(np.ones(2)) for _ in range(21)]))
+    net.push(bn.CategoricalCPD("never", ["leaf"], [2], [[1.0, 0.0], [1.0, 0.0]]))
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    lw_mode(mode, True)
+    n = 40_000
+    for query, evidence in [(["wide"], {"leaf": 2}), (["wide", "leaf"], {}), (["det", "one"], {"wide": 4})]:
+        counts, (sw, sw2) = lw_raw(bn, net, query, evidence, n, seed=4)
+        oc, osw, osw2 = capi.lw_infer(on, lay.evidence_vector(evidence), lay.query_indices(query), n, seed=4)
+        np.testing.assert_allclose(counts, oc.ravel(order="F"), rtol=1e-12)
+        assert sw == pytest.approx(osw, rel=1e-12)
+    # det is always state 2: P(det) = [0, 1, 0] exactly
+    c, _ = lw_raw(bn, net, ["det"], {}, n, seed=5)
+    assert c.tolist() == [0.0, float(n), 0.0]
+    # impossible evidence: all weights are 0 -> normalize! gives NaN, as likelihood.jl:56 would
+    phi = bn.infer(bn.LikelihoodWeightingInference(nsamples=1000, seed=1), net, "wide", evidence={"never": 2})
+    assert np.isnan(phi.potential).all()
+    # tables from both kernels are identical to the oracle's
+    from bayesnets_jl_b200.sampling import _sample
+    _, st, w, ok = _sample(net, 5000, {"leaf": 1}, 2, 1, 9, None)
+    ost, ow, _ = capi.sample(on, 5000, evidence=lay.evidence_vector({"leaf": 1}), kind=2, seed=9)
+    assert np.array_equal(st, ost) and np.array_equal(w, ow)
