@@ -45,6 +45,8 @@ struct ContractParams {
   int32_t nt[TLEV], L[TLEV];       // dims / values per tile-digit group (L = 1 when unused)
   int32_t card[MAXD];
   uint32_t magic[MAXD];            // ceil(2^20 / card): digit extraction without division (numerators < 1024)
+  uint32_t pmagic[MAXD];           // ceil(2^20 / product of the earlier cards of the dim's group): all digits of a
+                                   // group value e < 1024 come out independently (no serial divide chain)
   int32_t fstride[MAXF + 1][MAXD]; // element stride of each operand along each loop dim (0 = absent);
                                    // row nf = the OUTPUT's strides (its rows need not be consecutive)
   const double* f[MAXF];
@@ -54,6 +56,7 @@ struct ContractParams {
   int32_t lead, pf_bytes, pf_ns;  // TMA L2 prefetch of the leading operand's next-tile rows (pf_bytes = 0: off)
   int32_t vec128[MAXF];  // operand is contiguous + 16-byte aligned along the vector dim: one 128-bit load
   int32_t vstep[MAXF];   // otherwise two 64-bit loads `vstep` elements apart (0 = broadcast)
+  int32_t waves;  // grid = waves x resident CTAs
   int32_t rowvec[MAXF];  // the tile's 4 rows are 4 CONSECUTIVE elements of this operand (its two fastest dims were
                          // chosen as the row dims): one thread fetches them as 2 x 128-bit instead of 4 x 64-bit
 };
@@ -93,6 +96,19 @@ __device__ __forceinline__ void fill_table(int32_t* tab, int count, int d0, int 
   }
 }
 
+// offsets of ONE joint value e < 1024 of loop dims [d0, d0 + nd), every digit extracted independently
+// (floor(e / P_d) by multiply-shift with pmagic, exact for e < 1024 and P_d <= 1024): no serial divide chain, so a
+// one-shot CTA reaches its first load after ~100 cycles
+template <int NSLOT>
+__device__ __forceinline__ void add_offsets(int32_t (&off)[NSLOT], uint32_t e, int d0, int nd, const ContractParams& p) {
+  for (int d = d0; d < d0 + nd; ++d) {
+    const uint32_t q = (e * p.pmagic[d]) >> 20;
+    const int32_t dg = (int32_t)(q - ((q * p.magic[d]) >> 20) * (uint32_t)p.card[d]);
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) off[k] += dg * p.fstride[k][d];
+  }
+}
+
 // rows in flight per thread: keep NF * (loads per row) * JU independent loads within the register budget
 // (<= 12 double2 or <= 16 double in flight)
 template <int NF, int VEC, int NS>
@@ -109,9 +125,10 @@ __global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contr
   constexpr int NS1 = NF + 1;  // table slots: the operands, then the output
   int32_t* jOff = reinterpret_cast<int32_t*>(smem_raw);  // [NF+1][H]
   int32_t* sOff = jOff + NS1 * p.H;                       // [NF][Ns]
+  const int L0 = p.L[0], L1 = p.L[1], L2 = p.L[2];
   int32_t* tOff0 = sOff + NF * p.Ns;                      // [NF+1][L0]
-  int32_t* tOff1 = tOff0 + NS1 * p.L[0];
-  int32_t* tOff2 = tOff1 + NS1 * p.L[1];
+  int32_t* tOff1 = tOff0 + NS1 * L0;
+  int32_t* tOff2 = tOff1 + NS1 * L1;
   const int tid = threadIdx.x;
   constexpr int W = (VEC == VEC_LO) ? 2 : 1;  // outputs per thread per row
   constexpr int JU = RowsInFlight<NF, VEC, NS>::value;
@@ -121,35 +138,14 @@ __global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contr
   const int jb = p.nlo, t0b = jb + p.nj, t1b = t0b + p.nt[0], t2b = t1b + p.nt[1], sb = t2b + p.nt[2];
   fill_table<NS1>(jOff, p.H, jb, p.nj, p);
   if (SUM) fill_table<NF>(sOff, p.Ns, sb, p.ns, p);
-  fill_table<NS1>(tOff0, p.L[0], t0b, p.nt[0], p);
-  fill_table<NS1>(tOff1, p.L[1], t1b, p.nt[1], p);
-  fill_table<NS1>(tOff2, p.L[2], t2b, p.nt[2], p);
-  // ---- this thread's column
-  const int V = p.V, G = p.G;
-  const int col = tid % V, g = tid / V;
-  int32_t loOff[NS1];
-  {
-    uint32_t r = (uint32_t)col * W;
-#pragma unroll
-    for (int k = 0; k < NS1; ++k) loOff[k] = 0;
-    for (int d = 0; d < p.nlo; ++d) {
-      const uint32_t q = (r * p.magic[d]) >> 20;
-      const int32_t dg = (int32_t)(r - q * (uint32_t)p.card[d]);
-      r = q;
-#pragma unroll
-      for (int k = 0; k < NS1; ++k) loOff[k] += dg * p.fstride[k][d];
-    }
-  }
-  __syncthreads();
-  if (g >= G) return;  // threads beyond G * V columns have no work (non power-of-two column counts)
-  const int ns_rt = (NS == 1) ? p.Ns : NS;
-  int vec128[NF], vstep[NF];
-#pragma unroll
-  for (int k = 0; k < NF; ++k) { vec128[k] = p.vec128[k]; vstep[k] = p.vstep[k]; }
-
-  // tiles are dealt round-robin (all CTAs sweep one moving window of memory: measured 77% vs 54% of HBM peak
-  // for contiguous per-CTA chunks, which open ~1200 DRAM streams at once); the three tile digits advance by the
-  // grid size as a mixed-radix add, so there are no divisions in the loop
+  // Tiles are dealt round-robin over p.waves waves of resident CTAs (all CTAs sweep one moving window of memory:
+  // contiguous per-CTA chunks open ~1200 DRAM streams at once and reach 54% of HBM peak instead of 77%); the three
+  // tile digits advance by the grid size as a mixed-radix add, so there are no divisions in the loop.
+  // Schedules tried on B200 (tools/probe/stream_probe2.cu for the bare traffic mix, this kernel at 2^24 entries):
+  //   bare loop: 1 wave static 0.85 of the copy peak, 4 waves 0.93, atomic tile counter 0.92, one CTA per tile 0.95;
+  //   here     : a CTA per tile / 4-8 waves lose to the per-CTA prologue (offset tables), a per-CTA atomic counter
+  //              needs a barrier per tile (+1..3% on plain streams, -4..7% with a gathered or third operand), per-warp
+  //              counters serialise on the atomics.  2 waves for plain 1-2 operand streams, 1 wave otherwise.
   uint32_t i0, i1, i2, s0, s1, s2;
   {
     uint32_t t = blockIdx.x;
@@ -159,11 +155,28 @@ __global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contr
     s0 = t % (uint32_t)p.L[0]; t /= (uint32_t)p.L[0];
     s1 = t % (uint32_t)p.L[1]; s2 = t / (uint32_t)p.L[1];
   }
+  fill_table<NS1>(tOff0, p.L[0], t0b, p.nt[0], p);
+  fill_table<NS1>(tOff1, p.L[1], t1b, p.nt[1], p);
+  fill_table<NS1>(tOff2, p.L[2], t2b, p.nt[2], p);
+  // ---- this thread's column
+  const int V = p.V, G = p.G;
+  const int col = tid % V, g = tid / V;
+  int32_t loOff[NS1];
+#pragma unroll
+  for (int k = 0; k < NS1; ++k) loOff[k] = 0;
+  add_offsets<NS1>(loOff, (uint32_t)col * W, 0, p.nlo, p);
+  __syncthreads();
+  const bool active = g < G;  // threads beyond G * V columns have no rows (non power-of-two column counts)
+  const int ns_rt = (NS == 1) ? p.Ns : NS;
+  int vec128[NF], vstep[NF];
+#pragma unroll
+  for (int k = 0; k < NF; ++k) { vec128[k] = p.vec128[k]; vstep[k] = p.vstep[k]; }
+
   for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     int32_t base[NS1];
 #pragma unroll
     for (int k = 0; k < NS1; ++k)
-      base[k] = loOff[k] + tOff0[k * p.L[0] + i0] + tOff1[k * p.L[1] + i1] + tOff2[k * p.L[2] + i2];
+      base[k] = loOff[k] + tOff0[k * L0 + i0] + tOff1[k * L1 + i1] + tOff2[k * L2 + i2];
     i0 += s0;
     i1 += s1;
     if (i0 >= (uint32_t)p.L[0]) { i0 -= (uint32_t)p.L[0]; ++i1; }
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contr
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.f[lk] + o), "r"(p.pf_bytes) : "memory");
     }
 
-    for (int j0 = g; j0 < p.H; j0 += G * JU) {
+    for (int j0 = g; active && j0 < p.H; j0 += G * JU) {
       int32_t off[JU][NF], ooff[JU];
 #pragma unroll
       for (int u = 0; u < JU; ++u) {
@@ -336,30 +349,29 @@ __global__ void __launch_bounds__(NTHR, (NF <= 2 ? 4 : (NF == 3 ? 3 : 2))) contr
   }
 }
 
-// ---- normalize!: two launches -- (1) per-CTA partial sums, last CTA folds them in a fixed order,
-//      (2) x ./= total.  Deterministic (no fp atomics).
-__global__ void __launch_bounds__(512) norm_reduce_kernel(const double* __restrict__ x, long long n, int p,
-                                                          double* partial, unsigned int* ticket, double* total) {
-  __shared__ double wsum[16];
+// ---- normalize!: two launches -- (1) per-CTA partial sums, the last CTA to finish folds them in a fixed order,
+//      (2) x ./= total.  Deterministic (no fp atomics).  One-shot CTAs of 256 threads x 4 x 128 bit = 16 KB (the shape
+//      that reaches 0.93 of the copy peak in tools/probe/stream_probe.cu); the scale pass walks the chunks in
+//      DESCENDING order so that it starts on the bytes the reduce pass left in the 126 MB L2.
+constexpr int NORM_THR = 256, NORM_VEC = 4;  // double2 per thread
+constexpr long long NORM_CHUNK = (long long)NORM_THR * NORM_VEC;
+
+__global__ void __launch_bounds__(NORM_THR) norm_reduce_kernel(const double* __restrict__ x, long long n, int p,
+                                                               double* partial, unsigned int* ticket, double* total) {
+  __shared__ double wsum[NORM_THR / 32];
   __shared__ bool last;
   const long long n2 = n / 2;
-  double acc = 0.0;
   const double2* x2 = reinterpret_cast<const double2*>(x);
-  const long long step = (long long)gridDim.x * blockDim.x;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // four independent 128-bit loads in flight per thread (HBM latency x bandwidth needs ~40 KB per SM in flight)
-  for (; i + 3 * step < n2; i += 4 * step) {
-    const double2 a = __ldg(x2 + i), b = __ldg(x2 + i + step), c = __ldg(x2 + i + 2 * step), d = __ldg(x2 + i + 3 * step);
-    if (p == 1) acc += (fabs(a.x) + fabs(a.y)) + (fabs(b.x) + fabs(b.y)) + (fabs(c.x) + fabs(c.y)) + (fabs(d.x) + fabs(d.y));
-    else acc += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
-  }
-  for (; i < n2; i += step) {
-    const double2 v = __ldg(x2 + i);
-    acc += (p == 1) ? (fabs(v.x) + fabs(v.y)) : (v.x * v.x + v.y * v.y);
-  }
+  const long long i = (long long)blockIdx.x * NORM_CHUNK + threadIdx.x;
+  double2 v[NORM_VEC];
+#pragma unroll
+  for (int u = 0; u < NORM_VEC; ++u) v[u] = (i + u * NORM_THR < n2) ? __ldg(x2 + i + u * NORM_THR) : make_double2(0.0, 0.0);
+  double acc = 0.0;
+#pragma unroll
+  for (int u = 0; u < NORM_VEC; ++u) acc += (p == 1) ? (fabs(v[u].x) + fabs(v[u].y)) : (v[u].x * v[u].x + v[u].y * v[u].y);
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const double v = x[n - 1];
-    acc += (p == 1) ? fabs(v) : v * v;
+    const double t = x[n - 1];
+    acc += (p == 1) ? fabs(t) : t * t;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(512) norm_reduce_kernel(const double* __restri
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wsum[w];
+    for (int w = 0; w < NORM_THR / 32; ++w) s += wsum[w];
     partial[blockIdx.x] = s;
     __threadfence();
     const unsigned int t = atomicAdd(ticket, 1u);
@@ -375,33 +387,37 @@ __global__ void __launch_bounds__(512) norm_reduce_kernel(const double* __restri
   }
   __syncthreads();
   if (last) {
-    // fixed-order fold of the partials by one warp
+    // fixed-order fold of the partials by this CTA: strided per-thread sums, then a fixed tree
     double s = 0.0;
-    if (threadIdx.x < 32) {
-      for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) s += __ldcg(partial + i);
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += NORM_THR) s += __ldcg(partial + k);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (threadIdx.x == 0) { *total = s; *ticket = 0u; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tsum = 0.0;
+      for (int w = 0; w < NORM_THR / 32; ++w) tsum += wsum[w];
+      *total = tsum;
+      *ticket = 0u;
     }
   }
 }
 
-__global__ void __launch_bounds__(512) norm_scale_kernel(double* __restrict__ x, long long n, const double* total) {
+__global__ void __launch_bounds__(NORM_THR) norm_scale_kernel(double* __restrict__ x, long long n, const double* total) {
   const double t = *total;
   const long long n2 = n / 2;
   double2* x2 = reinterpret_cast<double2*>(x);
-  const long long step = (long long)gridDim.x * blockDim.x;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * step < n2; i += 4 * step) {
-    double2 a = x2[i], b = x2[i + step], c = x2[i + 2 * step], d = x2[i + 3 * step];
-    a.x /= t; a.y /= t; b.x /= t; b.y /= t; c.x /= t; c.y /= t; d.x /= t; d.y /= t;  // true division, as `./=`
-    x2[i] = a; x2[i + step] = b; x2[i + 2 * step] = c; x2[i + 3 * step] = d;
-  }
-  for (; i < n2; i += step) {
-    double2 v = x2[i];
-    v.x /= t; v.y /= t;
-    x2[i] = v;
-  }
+  const long long i = (long long)(gridDim.x - 1 - blockIdx.x) * NORM_CHUNK + threadIdx.x;
+  double2 v[NORM_VEC];
+#pragma unroll
+  for (int u = 0; u < NORM_VEC; ++u) if (i + u * NORM_THR < n2) v[u] = x2[i + u * NORM_THR];
+#pragma unroll
+  for (int u = 0; u < NORM_VEC; ++u)
+    if (i + u * NORM_THR < n2) {
+      v[u].x /= t; v[u].y /= t;  // true division, as `./=`
+      x2[i + u * NORM_THR] = v[u];
+    }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] /= t;
 }
 
@@ -425,8 +441,8 @@ static int32_t launch_contract_v(const ContractParams& p, int sm_count, size_t s
     if (occ < 1) occ = 1;
   }
   BN_REQUIRE(smem <= 64 * 1024, BN_UNSUPPORTED, "contraction offset tables need %zu bytes of shared memory", smem);
-  // persistent grid: every resident CTA slot gets tiles round-robin
-  const int grid = (int)std::min<long long>(p.n_tiles, (long long)sm_count * occ);
+  // tiles round-robin over p.waves waves of resident CTAs (see the kernel comment)
+  const int grid = (int)std::min<long long>(p.n_tiles, (long long)sm_count * occ * p.waves);
   contract_kernel<NF, VEC, NS><<<grid, NTHR, smem, s>>>(p);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
@@ -521,7 +537,8 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
   std::vector<char> taken(no, 0);
   long long H = 1;
   int nj = 0;
-  const long long h_target = 4ll * G;
+  static const int h_rows = getenv("BN_FACTOR_H") ? atoi(getenv("BN_FACTOR_H")) : 4;
+  const long long h_target = (long long)h_rows * G;
   // Row-vector gather (plain products of <= 3 operands, one row group): if a large non-leading operand has its two
   // fastest dims outside lo, make exactly those dims the tile's 4 rows so that a thread's 4 row values are 4
   // consecutive doubles of that operand (see rowvec in the kernel).  Skipped when the leading operand lacks some
@@ -609,6 +626,17 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
     p.fstride[nf][no + i] = 0;
   }
   for (int i = 0; i < no + ns; ++i) p.magic[i] = (uint32_t)(((1u << 20) + (uint32_t)p.card[i] - 1u) / (uint32_t)p.card[i]);
+  {  // prefix-product magics per dim group [lo | j | t0 | t1 | t2 | s]; lo and t groups hold < 1024 values each
+    const int ends[6] = {nlo, nlo + nj, nlo + nj + p.nt[0], nlo + nj + p.nt[0] + p.nt[1], no, no + ns};
+    int d = 0;
+    for (int gI = 0; gI < 6; ++gI) {
+      unsigned long long P = 1;
+      for (; d < ends[gI]; ++d) {
+        p.pmagic[d] = P <= 1024 ? (uint32_t)(((1ull << 20) + P - 1) / P) : 0u;
+        P *= (unsigned long long)p.card[d];
+      }
+    }
+  }
   const int vdim = vec == VEC_S ? no : 0;
   for (int k = 0; k < nf; ++k) {
     const long long sv = vec != VEC_NONE ? p.fstride[k][vdim] : 0;
@@ -640,7 +668,10 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
       p.pf_ns = (int32_t)ns_sep;
     }
   }
-  const size_t smem = ((size_t)(nf + 1) * ((size_t)H + (size_t)p.L[0] + p.L[1] + p.L[2]) + (size_t)nf * (size_t)Ns) * sizeof(int32_t);
+  const size_t tl = (size_t)p.L[0] + p.L[1] + p.L[2];
+  static const int waves_env = getenv("BN_FACTOR_WAVES") ? std::max(1, atoi(getenv("BN_FACTOR_WAVES"))) : 0;
+  p.waves = waves_env ? waves_env : ((vec == VEC_LO && nf <= 2 && rowvec_op < 0) ? 2 : 1);
+  const size_t smem = ((size_t)(nf + 1) * ((size_t)H + tl) + (size_t)nf * (size_t)Ns) * sizeof(int32_t);
   cudaStream_t s = tl_stream;
   const int ns_mode = ns == 0 ? 0 : ((Ns >= 2 && Ns <= 4) ? (int)Ns : 1);
   switch (nf) {
@@ -916,20 +947,24 @@ int32_t bn_factor_normalize(bn_factor_t h, int32_t pnorm) {
   BN_REQUIRE(pnorm == 1 || pnorm == 2, BN_BAD_ARG, "p = %d is not supported", pnorm);  // factors_dims.jl:51
   BN_CUDA_TRY(cudaSetDevice(f->device));
   const DevProps& dp = dev_props(f->device);
-  const int grid = (int)std::min<long long>((f->len / 2 + 511) / 512 + 1, (long long)dp.sm_count * 4);
-  static thread_local DevBuf<double> scratch;      // [grid partials | total]
+  const long long grid_ll = std::max<long long>(1, (f->len / 2 + NORM_CHUNK - 1) / NORM_CHUNK);
+  BN_REQUIRE(grid_ll < (1ll << 31), BN_UNSUPPORTED, "factor too large to normalise");
+  const int grid = (int)grid_ll;
+  (void)dp;
+  static thread_local DevBuf<double> scratch;      // [total | grid partials]
   static thread_local DevBuf<unsigned int> ticket;
   static thread_local int scratch_dev = -1;
-  if (scratch_dev != f->device || scratch.n < (size_t)dp.sm_count * 4 + 1) {
-    BN_CUDA_TRY(scratch.alloc((size_t)dp.sm_count * 4 + 1));
+  if (scratch_dev != f->device || scratch.n < (size_t)grid + 1) {
+    BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));  // an earlier normalise may still be reading the old scratch
+    BN_CUDA_TRY(scratch.alloc(std::max<size_t>((size_t)grid + 1, 16384)));
     BN_CUDA_TRY(ticket.alloc(1));
     BN_CUDA_TRY(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), tl_stream));
     scratch_dev = f->device;
   }
-  double* total = scratch.p + (size_t)dp.sm_count * 4;
-  norm_reduce_kernel<<<grid, 512, 0, tl_stream>>>(f->data.p, f->len, pnorm, scratch.p, ticket.p, total);
+  double* total = scratch.p;
+  norm_reduce_kernel<<<grid, NORM_THR, 0, tl_stream>>>(f->data.p, f->len, pnorm, scratch.p + 1, ticket.p, total);
   count_launch();
-  norm_scale_kernel<<<grid, 512, 0, tl_stream>>>(f->data.p, f->len, total);
+  norm_scale_kernel<<<grid, NORM_THR, 0, tl_stream>>>(f->data.p, f->len, total);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   return BN_OK;

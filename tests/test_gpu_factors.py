@@ -313,3 +313,51 @@ def test_product_with_reordered_large_operand_row_vector_path(bn, seed):
     got3 = bn.eliminate([fa, fb, fc], [])
     assert got3.dimensions == [names[i] for i in ref3.dimensions]
     assert np.array_equal(got3.potential, ref3.potential)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_large_streaming_shapes_bit_exact(bn, seed):
+    """2^22..2^24-entry leading operands (thousands of tiles): 512-entry leading block, mixed radix, summed states
+    inside and outside the contiguous span, row dims the leading operand lacks, 1-3 operands.  Bit-exact vs the oracle."""
+    rng = np.random.default_rng(900 + seed)
+    lead_cards = [[2] * 9, [4, 2, 2, 2, 2, 2, 2, 2], [2, 4, 4, 2, 2, 2, 2], [4, 4, 4, 2, 2, 2]][seed % 4]
+    tail = [2] * (22 - int(np.log2(np.prod(lead_cards))))
+    if seed % 2:
+        tail[int(rng.integers(0, len(tail)))] = 3
+        tail[int(rng.integers(0, len(tail)))] = 4
+    cards = lead_cards + tail
+    nd = len(cards)
+    names = [f"tm{seed}_{i}" for i in range(nd)]
+    ids = list(range(nd))
+    A = rng.random(cards)
+    fa = F(bn, names, A)
+    na = NpFactor(ids, A)
+
+    def both(fn):
+        return fn()
+
+    # sums: inside the span (dim 0), outside (middle / last), both, and a 3-dim sum
+    for sd in ([0], [nd - 1], [len(lead_cards) + 2], [0, nd - 2], [1, len(lead_cards), nd - 1]):
+        got = both(lambda: fa.sum([names[i] for i in sd]))
+        ref = na.sum(sd)
+        assert got.dimensions == [names[i] for i in ref.dimensions]
+        assert np.array_equal(got.potential, ref.potential), sd
+    # products: small interleaved operand; operand with a dim the leading operand lacks
+    sub = [int(x) for x in sorted(rng.choice(nd, size=6, replace=False))]
+    B = rng.random([cards[i] for i in sub])
+    got = both(lambda: fa * F(bn, [names[i] for i in sub], B))
+    assert np.array_equal(got.potential, (na * NpFactor(sub, B)).potential)
+    extra = f"tm{seed}_x"
+    Bx = rng.random([cards[i] for i in sub] + [2])
+    got = both(lambda: fa * F(bn, [names[i] for i in sub] + [extra], Bx))
+    assert np.array_equal(got.potential, (na * NpFactor(sub + [nd], Bx)).potential)
+    # fused eliminate: 3 operands sharing dim 0 (inside the span) / a tail dim (outside)
+    for h in (0, nd - 3):
+        d1 = [h] + [int(x) for x in rng.choice([i for i in ids if i != h], size=5, replace=False)]
+        d2 = [int(x) for x in rng.choice([i for i in ids if i != h], size=4, replace=False)] + [h]
+        B1, B2 = rng.random([cards[i] for i in d1]), rng.random([cards[i] for i in d2])
+        fs = [fa, F(bn, [names[i] for i in d1], B1), F(bn, [names[i] for i in d2], B2)]
+        got = both(lambda: bn.eliminate(fs, [names[h]]))
+        ref = (na * NpFactor(d1, B1) * NpFactor(d2, B2)).sum(h)
+        assert got.dimensions == [names[i] for i in ref.dimensions]
+        assert np.array_equal(got.potential, ref.potential), h
