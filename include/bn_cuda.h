@@ -184,6 +184,19 @@ int32_t bn_factor_eliminate(const bn_factor_t* factors, int32_t n_factors, const
 int32_t bn_exact_infer(bn_net_t net, const int8_t* evidence, const int32_t* query, int32_t n_query,
                        int32_t fused, int32_t* out_dims, int32_t* out_card, double* out);
 
+/* ---- statistics(parent_list, ncategories, data): src/DiscreteBayesNet/discrete_bayes_net.jl:151-172,221-231 ----
+ * Sufficient statistics of a data table under the structure of `net` (its CPT values are not read), all nodes in
+ * one pass.  states: uint8, node-major (states[i * pitch + row]), 0-based, i.e. exactly what bn_sample[_dev] writes;
+ * rows whose first byte is 0xFF (rejection sampler gave up) are skipped.  out_counts: cpt_off[n] int64 in the flat
+ * CPT layout, counts[cpt_off[i] + k + card_i * j] = N_i[k, j] = the reference's r x q matrix, column-major
+ * (first parent fastest, :131-136).  bn_statistics validates states < card (BN_BOUNDS); the _dev variant trusts
+ * the table (out-of-range states are dropped or miscounted, never written out of bounds), zeroes out_counts_dev
+ * and enqueues on the current stream.  pitch >= n_rows; TMA staging needs pitch % 16 == 0 and a 16-byte aligned
+ * table (otherwise plain loads). */
+int32_t bn_statistics(bn_net_t net, const uint8_t* states, uint64_t n_rows, int64_t* out_counts);
+int32_t bn_statistics_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_rows, uint64_t pitch,
+                          int64_t* out_counts_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -675,6 +675,35 @@ int orc_factor_normalize(int64_t n, double* x, int32_t p) {
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * statistics(parent_list, ncategories, data): src/DiscreteBayesNet/discrete_bayes_net.jl:151-172 (one node:
+ * js = (data[parents,:] .- 1)' * stridevec .+ 1, stridevec[k] = prod of the earlier parents' ncategories;
+ * N = sparse(data[target,:], js, 1, r, q) -- duplicates add) and :221-231 (all nodes).
+ * data: uint8, node-major data[i * pitch + row], 0-based; rows whose first byte is 0xFF are skipped (the device
+ * sampler's "rejection gave up" marker).  out: cpt_off[n] int64 in the flat CPT layout = each N_i column-major.
+ * OpenMP over nodes (each node's table is private to one thread: no atomics, deterministic).
+ * ---------------------------------------------------------------------------------------- */
+int orc_statistics(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                   const int64_t* cpt_off, const uint8_t* data, uint64_t n_rows, uint64_t pitch, int64_t* out) {
+  for (int64_t b = 0; b < cpt_off[n_nodes]; ++b) out[b] = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < n_nodes; ++i) {
+    int64_t* N = out + cpt_off[i];
+    const uint8_t* xi = data + (uint64_t)i * pitch;
+    for (uint64_t r = 0; r < n_rows; ++r) {
+      if (data[r] == 0xFF) continue;
+      int64_t j = 0, stride = 1;
+      for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) {
+        const int p = par_idx[k];
+        j += stride * data[(uint64_t)p * pitch + r];
+        stride *= card[p];
+      }
+      N[xi[r] + (int64_t)card[i] * j] += 1;
+    }
+  }
+  return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

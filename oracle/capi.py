@@ -231,3 +231,20 @@ def factor_normalize(a, p=1):
     if rc != 0:
         raise ValueError(f"p = {p} is not supported")
     return buf.reshape(a.shape, order="F")
+
+
+def statistics(net, data, n_rows=None, pitch=None):
+    """src/DiscreteBayesNet/discrete_bayes_net.jl:151-172,221-231 -> int64 counts in the flat CPT layout
+    (counts[cpt_off[i] + k + card_i * j]).  data: uint8 [n_nodes, pitch] node-major, 0-based states."""
+    args, keep = _net_args(net)
+    d = np.ascontiguousarray(data, np.uint8)
+    n_nodes = int(np.asarray(net.card).size)
+    if d.ndim == 2:
+        assert d.shape[0] == n_nodes
+        pitch = d.shape[1] if pitch is None else pitch
+        n_rows = d.shape[1] if n_rows is None else n_rows
+    out = np.zeros(int(np.asarray(net.cpt_off)[-1]), np.int64)
+    rc = lib().orc_statistics(args[0], args[1], args[2], args[3], args[4], _p(d, C.c_uint8), C.c_uint64(n_rows),
+                              C.c_uint64(pitch), _p(out, C.c_int64))
+    assert rc == 0
+    return out

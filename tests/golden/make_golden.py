@@ -115,6 +115,24 @@ def main():
                       ["D", ["T", "L", "B"], [[0.9, 0.1], [0.2, 0.8], [0.3, 0.7], [0.1, 0.9],
                                               [0.3, 0.7], [0.1, 0.9], [0.3, 0.7], [0.1, 0.9]]]],
         },
+        "statistics_ab": {
+            "cite": "test/test_discrete_bayes_nets.jl:13-67 (bn a -> b; data; bayesian_score_component values)",
+            "names": ["a", "b"], "edges": [["a", "b"]],
+            "data": {"a": [1, 1, 1, 1, 2, 2, 2, 2], "b": [1, 2, 1, 2, 1, 1, 1, 2]},
+            "count_a": [4, 4],
+            "count_b_given_a_1based": {"1,1": 2, "2,1": 3, "1,2": 2, "2,2": 1},  # (a, b) -> count
+            "score_1_uniform": -6.445719819385579, "score_1_uniform2": -6.13556489108174,
+            "score_1_bdeu": -6.841859646909766, "score_1_bdeu2": -6.445719819385579,
+            "score_2_uniform": -6.396929655216146,
+        },
+        "statistics_abc": {
+            "cite": "test/test_learning.jl:40-49 (data, dag A->B, A->C, B->C), :87-96 (statistics matrices)",
+            "names": ["A", "B", "C"], "edges": [["A", "B"], ["A", "C"], ["B", "C"]],
+            "data": {"A": [1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3], "B": [1, 1, 1, 2, 2, 2, 2, 1, 1, 2, 1, 1],
+                     "C": [1, 1, 1, 2, 1, 1, 2, 1, 1, 2, 1, 1]},
+            "stats_A": [[4], [4], [4]],
+            "stats_C": [[3, 1, 3, 0, 2, 0], [0, 0, 0, 1, 1, 1]],
+        },
         "philox4x32_10_kat": {
             "cite": "Random123 kat_vectors (Salmon et al. SC'11), philox4x32 10 rounds",
             "vectors": [

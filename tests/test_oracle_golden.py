@@ -289,3 +289,50 @@ def test_sweep_permutation_is_permutation():
         p = capi.sweep_permutation(3, 5, m)
         assert sorted(p.tolist()) == list(range(m))
     assert not np.array_equal(capi.sweep_permutation(3, 5, 50), capi.sweep_permutation(3, 6, 50))
+
+
+# --------------------------------------------------------------------------------------------- statistics / scores
+def _flat_structure(names, edges, cards):
+    """structure-only flat net for the oracle: parents ascending by node index (inneighbors), nodes in `names` order."""
+    from oracle.factors_np import FlatNet
+    idx = {n: i for i, n in enumerate(names)}
+    plist = [sorted(idx[p] for p, c in edges if c == n) for n in names]
+    par_ptr, par_idx, cpt_off = [0], [], [0]
+    for i, ps in enumerate(plist):
+        par_idx += ps
+        par_ptr.append(len(par_idx))
+        cpt_off.append(cpt_off[-1] + cards[i] * int(np.prod([cards[p] for p in ps])) if ps else cpt_off[-1] + cards[i])
+    return FlatNet(list(names), np.array(cards, np.int32), np.array(par_ptr, np.int32), np.array(par_idx, np.int32),
+                   np.array(cpt_off, np.int64), np.zeros(cpt_off[-1]), idx)
+
+
+def test_statistics_and_bayesian_scores_match_reference_tests(golden):
+    """test/test_discrete_bayes_nets.jl:40-44 (five score values), test/test_learning.jl:87-96 (count matrices)."""
+    from oracle import capi
+    from oracle.scoring_py import bayesian_score_component, bdeu_alpha, split_counts, uniform_alpha
+    g = golden["statistics_ab"]
+    net = _flat_structure(g["names"], g["edges"], [2, 2])
+    data = np.array([g["data"][n] for n in g["names"]], np.uint8) - 1
+    Ns = split_counts(net.card, net.par_ptr, net.par_idx, net.cpt_off, capi.statistics(net, data))
+    assert Ns[0].ravel().tolist() == g["count_a"]
+    for key, cnt in g["count_b_given_a_1based"].items():
+        a, b = (int(x) for x in key.split(","))
+        assert Ns[1][b - 1, a - 1] == cnt
+    assert np.isclose(bayesian_score_component(Ns[0], uniform_alpha(2, 1)), g["score_1_uniform"], rtol=1e-13)
+    assert np.isclose(bayesian_score_component(Ns[0], uniform_alpha(2, 1, 2.0)), g["score_1_uniform2"], rtol=1e-13)
+    assert np.isclose(bayesian_score_component(Ns[0], bdeu_alpha(2, 1)), g["score_1_bdeu"], rtol=1e-13)
+    assert np.isclose(bayesian_score_component(Ns[0], bdeu_alpha(2, 1, 2.0)), g["score_1_bdeu2"], rtol=1e-13)
+    assert np.isclose(bayesian_score_component(Ns[1], uniform_alpha(2, 2)), g["score_2_uniform"], rtol=1e-13)
+    g = golden["statistics_abc"]
+    net = _flat_structure(g["names"], g["edges"], [3, 2, 2])
+    data = np.array([g["data"][n] for n in g["names"]], np.uint8) - 1
+    Ns = split_counts(net.card, net.par_ptr, net.par_idx, net.cpt_off, capi.statistics(net, data))
+    assert Ns[0].tolist() == g["stats_A"]
+    assert Ns[2].tolist() == g["stats_C"]
+    # skipped rows (0xFF marker) and a padded pitch
+    padded = np.full((3, 16), 0, np.uint8)
+    padded[:, :12] = data
+    padded[:, 5] = 0xFF
+    c = capi.statistics(net, padded, n_rows=12, pitch=16)
+    keep = np.delete(data, 5, axis=1)
+    assert np.array_equal(c, capi.statistics(net, keep))
