@@ -10,113 +10,154 @@
 // Output layout = the network's flat CPT layout (include/bn_cuda.h): counts[cpt_off[i] + k + card_i * j], which is
 // the reference's r x q matrix in column-major order.
 //
-// Design (B200): persistent CTAs, one table row per thread.  A tile of TR rows x all nodes is staged into shared
-// memory by TMA bulk copies (one per node column: TR contiguous bytes), double-buffered on two mbarriers so the
-// next tile streams in while the current one is counted.  Each thread walks a small per-node program (offset,
-// parents, strides -- warp-uniform shared-memory broadcasts), reads its row's states as u8 from the tile and bumps
-// a CTA-private u32 histogram with shared-memory atomics; the histogram is flushed once per CTA with 64-bit global
-// atomics.  Algorithmic traffic: n_nodes bytes per row, read once (HBM-read-bound in principle; in practice the
-// per-(row, node) instruction count and same-address atomic conflicts bound it).
+// Design (B200): persistent CTAs.  A tile of TR rows x all nodes is staged into shared memory with 16-byte
+// asynchronous copies (cp.async), double-buffered so the next tile streams in while the current one is counted.  Counting is OWNER-COMPUTES, WITHOUT ATOMICS: inside a warp the 32 lanes are 32 different
+// nodes, and a (row slice, node group) pair belongs to exactly one warp of the CTA, so a lane is the only thread of
+// its CTA that ever touches its node's count table in its slice's histogram copy -- a plain load / add / store.
+// Each lane works on two rows at a time into two different copies, so the two read-modify-writes are independent.
+// Measured on the C2 net (100 nodes, 2^24 rows, B200): with shared-memory atomics 3.98e9 rows/s (32 rows of one node
+// per warp: a binary root has two bins for 32 lanes) and 3.79e9 (nodes across lanes, no same-address conflicts) --
+// the atomic unit, not the conflicts, was the limit; owner-computes with a branchy inner loop 2.7e9 (72 instructions
+// per lane-row, ncu), branch-free 4.25e9 (38 per lane-row; issue-bound at 25% occupancy, profiles/r1e_stats_*).
+// A lane keeps its node's program (table offset, first parents and strides) in registers for the whole tile.
+// Column i of a tile starts at byte i * (TR + 16), i.e. in bank group 4 * (i % 8); lane i reads row r + 4 * (i / 8),
+// which moves the four lanes of a bank group onto four different banks: the state loads are conflict free.  The
+// histogram copies are summed and flushed once per CTA with 64-bit global atomics.  Algorithmic traffic: n_nodes
+// bytes per row, read once.  Count tables too large for shared memory fall back to global atomics.
 #include "common.cuh"
 
 namespace bn {
 
+constexpr int STATS_REG_PARENTS = 3;  // parents held in registers; further ones are read from the program
+
 struct StatsArgs {
   const uint8_t* data;   // [n_nodes][pitch]
   uint64_t n_rows, pitch;
-  const uint32_t* prog;  // device copy: per node  [cpt_off, card | n_par << 8, (parent, stride * card) ...]
+  const uint32_t* prog;  // device copy: per node 4 + 2 * max(0, n_par - 3) words, see statistics_launch
+  const uint32_t* prog_off;  // [n_nodes] word offset of each node's record
   uint32_t prog_words, n_nodes, n_bins, TR;
-  uint32_t hist_in_smem, use_tma;
+  uint32_t hist_in_smem, use_async;  // use_async: table and pitch 16-byte aligned
+  uint32_t bins_pad;                        // words per histogram copy; 2 * row_step copies
+  uint32_t n_groups, group_step, row_step;  // warp w: node groups w % group_step + k * group_step, row slice w / group_step
   unsigned long long* out;  // [n_bins]
 };
 
 __device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// MORE: some node has more than STATS_REG_PARENTS parents (generic tail loop); SMEM: the histogram copies fit
+template <bool MORE, bool SMEM>
 __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2];
-  // layout: [prog | hist u32 (n_bins, when it fits) | tile 0 | tile 1], tiles are [n_nodes][TR] u8
+  // layout: [prog | prog_off | hist u32 (n_bins, when it fits) | tile 0 | tile 1], tiles are [n_nodes][TR + 16] u8
   uint32_t* prog = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* hist = prog + a.prog_words;
-  const uint32_t hist_words = a.hist_in_smem ? a.n_bins : 0u;
-  const uint32_t tile_bytes = a.n_nodes * a.TR;
-  unsigned char* tiles = smem_raw + (((a.prog_words + hist_words) * 4u + 127u) & ~127u);
-  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  uint32_t* prog_off = prog + a.prog_words;
+  uint32_t* hist = prog_off + a.n_nodes;
+  const uint32_t hist_words = SMEM ? a.bins_pad * 2u * a.row_step : 0u;
+  const uint32_t TRP = a.TR + 16u;
+  const uint32_t tile_bytes = a.n_nodes * TRP;
+  unsigned char* tiles = smem_raw + (((a.prog_words + a.n_nodes + hist_words) * 4u + 127u) & ~127u);
+  const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5;
   for (uint32_t w = tid; w < a.prog_words; w += T) prog[w] = a.prog[w];
+  for (uint32_t w = tid; w < a.n_nodes; w += T) prog_off[w] = a.prog_off[w];
   for (uint32_t b = tid; b < hist_words; b += T) hist[b] = 0u;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_addr(&full_bar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_addr(&full_bar[1])));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
 
   const uint64_t n_tiles = (a.n_rows + a.TR - 1) / a.TR;
-  // stage tile `t` into buffer `buf`: full tiles by TMA (one bulk copy per node column, issued by warp 0);
-  // the ragged last tile and unaligned tables by plain loads of all threads (then a barrier instead of the mbarrier)
-  auto tile_is_tma = [&](uint64_t t) { return a.use_tma && (t + 1) * a.TR <= a.n_rows; };
+  // stage tile `t` into buffer `buf`: 16-byte asynchronous copies (cp.async / LDGSTS) spread over all threads.  A tile
+  // is n_nodes column segments of only TR = 128..512 bytes; one TMA bulk copy per segment was measured to cap at
+  // about one copy per 150 cycles per SM (1.6-1.9e9 copies/s chip-wide), which bounded the whole kernel, so the
+  // segments are moved as independent 16-byte requests instead.  The ragged last tile and unaligned tables use
+  // plain byte loads.
   auto stage = [&](uint64_t t, uint32_t buf) {
     unsigned char* dst = tiles + buf * tile_bytes;
     const uint64_t r0 = t * a.TR;
-    if (tile_is_tma(t)) {
-      if (tid < 32) {
-        const uint32_t bar = s_addr(&full_bar[buf]);
-        if (tid == 0)
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
-        __syncwarp();
-        for (uint32_t i = tid; i < a.n_nodes; i += 32)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           s_addr(dst + i * a.TR)),
-                       "l"(a.data + (uint64_t)i * a.pitch + r0), "r"(a.TR), "r"(bar)
-                       : "memory");
+    if (a.use_async && (t + 1) * a.TR <= a.n_rows) {
+      const uint32_t per_col = a.TR / 16u, total = a.n_nodes * per_col;
+      for (uint32_t c = tid; c < total; c += T) {
+        const uint32_t i = c / per_col, k = c - i * per_col;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_addr(dst + i * TRP + 16u * k)),
+                     "l"(a.data + (uint64_t)i * a.pitch + r0 + 16u * k)
+                     : "memory");
       }
     } else {
       const uint64_t rows = a.n_rows - r0 < a.TR ? a.n_rows - r0 : a.TR;
       for (uint32_t i = 0; i < a.n_nodes; ++i)
-        for (uint32_t r = tid; r < rows; r += T) dst[i * a.TR + r] = a.data[(uint64_t)i * a.pitch + r0 + r];
+        for (uint32_t r = tid; r < rows; r += T) dst[i * TRP + r] = a.data[(uint64_t)i * a.pitch + r0 + r];
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  uint32_t phase = 0u;  // bit b = parity the next wait on buffer b expects
   uint64_t t = blockIdx.x;
   if (t < n_tiles) stage(t, 0);
   uint32_t buf = 0;
+  const uint32_t skew = 4u * (lane >> 3);
   for (; t < n_tiles; t += gridDim.x, buf ^= 1u) {
+    // one barrier per tile: it publishes tile t (every thread has waited for its own copies) and proves that every
+    // thread is done with the other buffer, which is refilled right after it
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     const uint64_t tn = t + gridDim.x;
-    if (tn < n_tiles) stage(tn, buf ^ 1u);  // the other buffer was released by the barrier that ended the last tile
-    if (tile_is_tma(t)) {
-      const uint32_t bar = s_addr(&full_bar[buf]);
-      uint32_t ok = 0;
-      while (!ok)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"((phase >> buf) & 1u) : "memory");
-      phase ^= 1u << buf;
-    } else {
-      __syncthreads();
-    }
+    if (tn < n_tiles) stage(tn, buf ^ 1u);
     const unsigned char* tile = tiles + buf * tile_bytes;
     const uint64_t r0 = t * a.TR;
-    const uint64_t rows = a.n_rows - r0 < a.TR ? a.n_rows - r0 : a.TR;
-    for (uint32_t r = tid; r < rows; r += T) {
-      const unsigned char* st = tile + r;
-      const uint32_t* pc = prog;
-      if (st[0] == 0xFFu) continue;  // row the rejection sampler gave up on (bn_sample: out_states = 0xFF)
-      for (uint32_t i = 0; i < a.n_nodes; ++i) {
-        uint32_t idx = pc[0] + st[i * a.TR];
-        const uint32_t npar = pc[1] >> 8;
-        for (uint32_t k = 0; k < npar; ++k) idx += pc[3 + 2 * k] * (uint32_t)st[pc[2 + 2 * k] * a.TR];
-        pc += 2 + 2 * npar;
-        if (idx < a.n_bins) {  // memory safety only: a state >= card[i] is the caller's error (see bn_cuda.h)
-          if (a.hist_in_smem) atomicAdd(&hist[idx], 1u);
-          else atomicAdd(&a.out[idx], 1ull);
+    const uint32_t rows = (uint32_t)(a.n_rows - r0 < a.TR ? a.n_rows - r0 : a.TR);
+    for (uint32_t g = warp % a.group_step; g < a.n_groups; g += a.group_step) {
+      const uint32_t node = g * 32u + lane;
+      const bool live = node < a.n_nodes;
+      // this lane's node program -> registers
+      uint32_t base = 0, npar = 0, po[STATS_REG_PARENTS], ps[STATS_REG_PARENTS];
+      const uint32_t* rec = prog;
+      if (live) {
+        rec = prog + prog_off[node];
+        base = rec[0];
+        npar = rec[1];
+      }
+#pragma unroll
+      for (int k = 0; k < STATS_REG_PARENTS; ++k) {
+        po[k] = (live && (uint32_t)k < npar) ? rec[2 + 2 * k] * TRP : 0u;
+        ps[k] = (live && (uint32_t)k < npar) ? rec[3 + 2 * k] : 0u;  // stride 0: absent parents add nothing
+      }
+      // Branch-free inner loop: every lane always reads (in-bounds) states and always updates a bin; rows / lanes that
+      // do not count (past the table end, 0xFF-marked, lanes beyond the last node, states out of range) are steered
+      // to the spare bin n_bins of their copy (bins_pad > n_bins), which is never flushed.
+      const uint32_t coff = live ? node * TRP : 0u;
+      const uint32_t slice = warp / a.group_step;
+      uint32_t* hA = hist + (2u * slice) * a.bins_pad;
+      uint32_t* hB = hA + a.bins_pad;
+      const uint32_t spare = a.n_bins;
+      auto index_of = [&](uint32_t step) -> uint32_t {
+        uint32_t r = step + skew;
+        r = r >= a.TR ? r - a.TR : r;
+        uint32_t idx = base + tile[coff + r];
+#pragma unroll
+        for (int k = 0; k < STATS_REG_PARENTS; ++k) idx += ps[k] * (uint32_t)tile[po[k] + r];
+        if (MORE)
+          for (uint32_t k = STATS_REG_PARENTS; k < npar; ++k) idx += rec[3 + 2 * k] * (uint32_t)tile[rec[2 + 2 * k] * TRP + r];
+        const bool ok = live && step < a.TR && r < rows && tile[r] != 0xFFu && idx < spare;
+        return ok ? idx : spare;
+      };
+      if (SMEM) {
+        for (uint32_t step = slice; step < a.TR; step += 2u * a.row_step) {
+          const uint32_t i0 = index_of(step), i1 = index_of(step + a.row_step);
+          // this lane is the only thread of the CTA that touches node `node`'s bins in copies 2 * slice (+ 1); the
+          // spare bins are shared by the warp's lanes, but nobody reads them
+          const uint32_t v0 = hA[i0], v1 = hB[i1];
+          hA[i0] = v0 + 1u;
+          hB[i1] = v1 + 1u;
+        }
+      } else {
+        for (uint32_t step = slice; step < a.TR; step += a.row_step) {
+          const uint32_t i0 = index_of(step);
+          if (i0 != spare) atomicAdd(&a.out[i0], 1ull);
         }
       }
     }
-    __syncthreads();  // everyone is done with this buffer (and, for plain staging, sees the next one complete)
   }
-  if (a.hist_in_smem)
+  __syncthreads();
+  if (SMEM)
     for (uint32_t b = tid; b < a.n_bins; b += T) {
-      const uint32_t c = hist[b];
-      if (c) atomicAdd(&a.out[b], (unsigned long long)c);
+      unsigned long long c = 0;
+      for (uint32_t k = 0; k < 2u * a.row_step; ++k) c += hist[k * a.bins_pad + b];
+      if (c) atomicAdd(&a.out[b], c);
     }
 }
 
@@ -131,58 +172,72 @@ static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_r
              (unsigned long long)n_rows);
   BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)n_bins * sizeof(unsigned long long), s));
   if (n_rows == 0 || n == 0) return BN_OK;
-  // per-node program
-  std::vector<uint32_t> prog;
-  prog.reserve((size_t)n * 6);
+  // per-node program: [table offset, n_par, (parent, stride) x n_par], stride includes the node's own cardinality
+  std::vector<uint32_t> prog, prog_off((size_t)n);
+  prog.reserve((size_t)n * 8);
   for (int i = 0; i < n; ++i) {
     const uint32_t npar = (uint32_t)(net->par_ptr[i + 1] - net->par_ptr[i]);
+    prog_off[(size_t)i] = (uint32_t)prog.size();
     prog.push_back((uint32_t)net->cpt_off[i]);
-    prog.push_back((uint32_t)net->card[i] | (npar << 8));
+    prog.push_back(npar);
     int64_t stride = net->card[i];
     for (int k = net->par_ptr[i]; k < net->par_ptr[i + 1]; ++k) {
       prog.push_back((uint32_t)net->par_idx[k]);
       prog.push_back((uint32_t)stride);
       stride *= net->card[net->par_idx[k]];
     }
+    while (prog.size() - prog_off[(size_t)i] < 2 + 2 * STATS_REG_PARENTS) prog.push_back(0);  // register slots readable
   }
   while (prog.size() % 4) prog.push_back(0);
-  // shape: rows per tile = threads per CTA; two tiles + program + (histogram when it fits) within 227 KB
+  // shape: one warp per (row slice, node group of 32 nodes); 2 histogram copies per row slice; two tiles of TR rows;
+  // everything within 227 KB, aiming for >= 2 CTAs per SM
   StatsArgs a{};
-  const size_t prog_b = prog.size() * 4;
+  const size_t prog_b = (prog.size() + (size_t)n) * 4;
   const size_t budget = (size_t)dp.max_smem_optin - 2048;
-  a.hist_in_smem = ((size_t)n_bins * 4 + prog_b + 2 * (size_t)n * 64 <= budget) ? 1u : 0u;
-  const size_t fixed = ((prog_b + (a.hist_in_smem ? (size_t)n_bins * 4 : 0) + 127) / 128) * 128;
-  BN_REQUIRE(fixed + 2 * (size_t)n * 32 <= budget, BN_UNSUPPORTED, "network too large for the statistics kernel (%d nodes)", n);
-  uint32_t TR = 1024;
-  while (TR > 32 && fixed + 2 * (size_t)n * TR > budget / 2) TR /= 2;  // aim for two CTAs per SM
-  while (TR > 32 && fixed + 2 * (size_t)n * TR > budget) TR /= 2;
+  a.n_groups = (uint32_t)((n + 31) / 32);
+  a.group_step = std::min<uint32_t>(a.n_groups, 32u);
+  a.bins_pad = (uint32_t)((n_bins + 32) / 32 * 32 + 1);  // odd pitch: the copies of a bin sit in different banks
+  const size_t min_tiles = 2 * (size_t)n * (32 + 16);
+  uint32_t slices = std::max<uint32_t>(1u, std::min<uint32_t>(4u, 8u / a.group_step));  // ~8 warps per CTA
+  while (slices > 1 && prog_b + (size_t)a.bins_pad * 4 * 2 * slices + 2 * (size_t)n * (128 + 16) > budget / 2) slices /= 2;
+  a.hist_in_smem = (prog_b + (size_t)a.bins_pad * 4 * 2 * slices + min_tiles <= budget) ? 1u : 0u;
+  a.row_step = slices;
+  const size_t fixed = ((prog_b + (a.hist_in_smem ? (size_t)a.bins_pad * 4 * 2 * slices : 0) + 127) / 128) * 128;
+  BN_REQUIRE(fixed + min_tiles <= budget, BN_UNSUPPORTED, "network too large for the statistics kernel (%d nodes)", n);
+  uint32_t TR = 512;
+  while (TR > 32 && fixed + 2 * (size_t)n * (TR + 16) > budget / 2) TR /= 2;
+  while (TR > 32 && fixed + 2 * (size_t)n * (TR + 16) > budget) TR /= 2;
   a.TR = TR;
-  a.use_tma = (pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(data_dev) % 16) == 0 && TR % 16 == 0) ? 1u : 0u;
-  const size_t smem = fixed + 2 * (size_t)n * TR;
+  const uint32_t warps = a.group_step * slices;
+  const int threads = (int)warps * 32;
+  a.use_async = (pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(data_dev) % 16) == 0 && TR % 16 == 0) ? 1u : 0u;
+  const size_t smem = fixed + 2 * (size_t)n * (TR + 16);
   // program -> device scratch (reused across calls)
   if (net->scratch.n < prog_b + 16) BN_CUDA_TRY(net->scratch.alloc((prog_b + 16) * 2));
-  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, prog.data(), prog_b, cudaMemcpyHostToDevice, s));
-  BN_CUDA_TRY(cudaStreamSynchronize(s));  // `prog` is pageable host memory about to go out of scope
+  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice, s));
+  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p + prog.size() * 4, prog_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  BN_CUDA_TRY(cudaStreamSynchronize(s));  // pageable host vectors about to go out of scope
   a.data = data_dev;
   a.n_rows = n_rows;
   a.pitch = pitch;
   a.prog = reinterpret_cast<const uint32_t*>(net->scratch.p);
+  a.prog_off = a.prog + prog.size();
   a.prog_words = (uint32_t)prog.size();
   a.n_nodes = (uint32_t)n;
   a.n_bins = (uint32_t)n_bins;
   a.out = out_dev;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    BN_CUDA_TRY(cudaFuncSetAttribute(statistics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin - 1024));
-    attr_set = true;
-  }
+  bool more = false;
+  for (int i = 0; i < n; ++i) more = more || (net->par_ptr[i + 1] - net->par_ptr[i] > STATS_REG_PARENTS);
+  void (*kern)(const StatsArgs) = a.hist_in_smem ? (more ? statistics_kernel<true, true> : statistics_kernel<false, true>)
+                                                 : (more ? statistics_kernel<true, false> : statistics_kernel<false, false>);
+  BN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin - 1024));
   int per_sm = (int)((size_t)dp.smem_per_sm / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm * (int)TR > 2048) per_sm = 2048 / (int)TR;
+  if (per_sm * threads > 2048) per_sm = 2048 / threads;
   const uint64_t n_tiles = (n_rows + TR - 1) / TR;
   const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)dp.sm_count * per_sm);
   BN_REQUIRE(n_rows / (uint64_t)grid < (1ull << 31), BN_UNSUPPORTED, "too many rows per CTA for the 32-bit CTA histogram");
-  statistics_kernel<<<grid, TR, smem, s>>>(a);
+  kern<<<grid, threads, smem, s>>>(a);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   return BN_OK;

@@ -123,7 +123,31 @@ def main():
                     "hbm_write_GBs": n_rows * (lay.n + (8 if kind == 2 else 0)) / (ms * 1e-3) / 1e9,
                     "cpu": {"value": n_cpu / dt, "cores": cores, "kind": "port", "sample": f"{n_cpu} rows"},
                     "check": f"first {n_cpu} rows identical to the oracle: {same}"})
-    del st, w, ok
+    # ---- f4 statistics: count the ancestral table where it lies (sample -> count never leaves HBM)
+    _lib.check(L.bn_sample_dev(_lib.h64(dn.handle), _lib.ptr(no_ev, _lib.i8p), C.c_int32(0), C.c_int32(1), C.c_uint64(0),
+                               C.c_uint64(n_rows), C.c_uint64(3), C.c_void_p(st.data_ptr()), None, None))
+    cnt = torch.empty(int(lay.cpt_off[-1]), dtype=torch.int64, device="cuda:0")
+
+    def fn_stats():
+        _lib.check(L.bn_statistics_dev(_lib.h64(dn.handle), C.c_void_p(st.data_ptr()), C.c_uint64(n_rows), C.c_uint64(n_rows),
+                                       C.c_void_p(cnt.data_ptr())))
+    ms = ev_time(torch, fn_stats)
+    n_cpu = min(n_rows, 1 << 21)
+    host_tab = np.ascontiguousarray(st[:, :n_cpu].cpu().numpy())
+    capi.statistics(on, host_tab)
+    t0 = time.perf_counter()
+    cref = capi.statistics(on, host_tab)
+    dt = time.perf_counter() - t0
+    _lib.check(L.bn_statistics_dev(_lib.h64(dn.handle), C.c_void_p(st.data_ptr()), C.c_uint64(n_cpu), C.c_uint64(n_rows),
+                                   C.c_void_p(cnt.data_ptr())))
+    same = bool(np.array_equal(cnt.cpu().numpy(), cref))
+    out.append({"row": "f4", "api": "statistics(bn, data): all nodes' count tables in one pass",
+                "cite": "src/DiscreteBayesNet/discrete_bayes_net.jl:151-172,221-231",
+                "config": f"C2 net, device-resident {n_rows} rows x {lay.n} nodes (uint8) from rand(bn, n)", "unit": "rows/s",
+                "gpu": n_rows / (ms * 1e-3), "gpu_ms": ms, "hbm_read_GBs": n_rows * lay.n / (ms * 1e-3) / 1e9,
+                "cpu": {"value": n_cpu / dt, "cores": cores, "kind": "port", "sample": f"{n_cpu} rows (OpenMP over nodes)"},
+                "check": f"counts of the first {n_cpu} rows identical to the oracle: {same}"})
+    del st, w, ok, cnt
 
     # ---- a8 gibbs_sample: 4096 chains x 16 kept samples, burn-in 50 sweeps, thinning 1 (C2 net)
     nch, ns, bi, th = (4096, 16, 50, 1) if not a.quick else (256, 4, 10, 1)
