@@ -315,3 +315,28 @@ function eliminate(factors::Vector{DeviceFactor}, h::NodeName)
                     hs, length(hs), ids, 1, out))
     return _wrap(out[])
 end
+
+# ---------------------------------------------------------------------------------------------------------------
+# statistics(bn, data) on the device          replaces src/DiscreteBayesNet/discrete_bayes_net.jl:151-172,221-231
+# One pass over the table counts every node.  `data`: n_nodes x m Matrix{Int} with 1-based states (the reference's
+# `Matrix{Int}(data)'`); the structure (parents in cpd.parents order, cardinalities) is the network's.  Returns the
+# reference's Vector{Matrix{Int}} (r_i x q_i, first parent fastest).  For the reference's DataFrame front ends, which
+# take parents = inneighbors(dag, i) and ncategories from the data, build the structure-only DeviceNet accordingly
+# (bayesnets.jl_b200/learning.py does exactly that).
+function cuda_statistics(bn::DiscreteBayesNet, data::AbstractMatrix{<:Integer})
+    net = device_net(bn)
+    lay = net.layout
+    n, m = size(data)
+    n == length(lay.names) || throw(DimensionMismatch("statistics' dag and data must be of the same dimension, $(length(lay.names)) ≠ $n"))
+    states = Matrix{UInt8}(undef, m, n)                    # node-major on the device = one column per node
+    for i in 1:n, r in 1:m
+        1 <= data[i, r] <= lay.card[i] || throw(BoundsError(1:lay.card[i], data[i, r]))
+        states[r, i] = UInt8(data[i, r] - 1)
+    end
+    counts = Vector{Int64}(undef, lay.cpt_off[end])
+    GC.@preserve states counts begin
+        _bn_check(ccall((:bn_statistics, libbn_cuda), Int32, (UInt64, Ptr{UInt8}, UInt64, Ptr{Int64}),
+                        net.handle, states, m, counts))
+    end
+    return [reshape(counts[lay.cpt_off[i]+1:lay.cpt_off[i+1]], Int(lay.card[i]), :) for i in 1:n]
+end
