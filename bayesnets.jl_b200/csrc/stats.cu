@@ -14,11 +14,13 @@
 // asynchronous copies (cp.async), double-buffered so the next tile streams in while the current one is counted.  Counting is OWNER-COMPUTES, WITHOUT ATOMICS: inside a warp the 32 lanes are 32 different
 // nodes, and a (row slice, node group) pair belongs to exactly one warp of the CTA, so a lane is the only thread of
 // its CTA that ever touches its node's count table in its slice's histogram copy -- a plain load / add / store.
-// Each lane works on two rows at a time into two different copies, so the two read-modify-writes are independent.
+// Each lane takes four consecutive rows per step (one 32-bit load per column carries their four states) and alternates
+// between two histogram copies, so consecutive read-modify-writes are independent.
 // Measured on the C2 net (100 nodes, 2^24 rows, B200): with shared-memory atomics 3.98e9 rows/s (32 rows of one node
 // per warp: a binary root has two bins for 32 lanes) and 3.79e9 (nodes across lanes, no same-address conflicts) --
 // the atomic unit, not the conflicts, was the limit; owner-computes with a branchy inner loop 2.7e9 (72 instructions
-// per lane-row, ncu), branch-free 4.25e9 (38 per lane-row; issue-bound at 25% occupancy, profiles/r1e_stats_*).
+// per lane-row, ncu), branch-free 4.25e9 (38 per lane-row; issue-bound at 25% occupancy, profiles/r1f_stats_*), four
+// rows per step with 32-bit state loads 6.57e9.
 // A lane keeps its node's program (table offset, first parents and strides) in registers for the whole tile.
 // Column i of a tile starts at byte i * (TR + 16), i.e. in bank group 4 * (i % 8); lane i reads row r + 4 * (i / 8),
 // which moves the four lanes of a bank group onto four different banks: the state loads are conflict free.  The
@@ -124,30 +126,48 @@ __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) 
       uint32_t* hA = hist + (2u * slice) * a.bins_pad;
       uint32_t* hB = hA + a.bins_pad;
       const uint32_t spare = a.n_bins;
-      auto index_of = [&](uint32_t step) -> uint32_t {
-        uint32_t r = step + skew;
+      // four consecutive rows per step: one 32-bit load per (node | parent) column carries their four states
+      auto quad = [&](uint32_t Q, uint32_t (&idx)[4]) {
+        uint32_t r = 4u * Q + skew;
         r = r >= a.TR ? r - a.TR : r;
-        uint32_t idx = base + tile[coff + r];
+        const uint32_t ws = *reinterpret_cast<const uint32_t*>(tile + coff + r);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile + r);  // node 0's states carry the 0xFF marks
+        uint32_t wp[STATS_REG_PARENTS];
 #pragma unroll
-        for (int k = 0; k < STATS_REG_PARENTS; ++k) idx += ps[k] * (uint32_t)tile[po[k] + r];
-        if (MORE)
-          for (uint32_t k = STATS_REG_PARENTS; k < npar; ++k) idx += rec[3 + 2 * k] * (uint32_t)tile[rec[2 + 2 * k] * TRP + r];
-        const bool ok = live && step < a.TR && r < rows && tile[r] != 0xFFu && idx < spare;
-        return ok ? idx : spare;
+        for (int k = 0; k < STATS_REG_PARENTS; ++k) wp[k] = *reinterpret_cast<const uint32_t*>(tile + po[k] + r);
+        const bool quad_ok = live && 4u * Q < a.TR;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          uint32_t v = base + ((ws >> (8 * b)) & 0xffu);
+#pragma unroll
+          for (int k = 0; k < STATS_REG_PARENTS; ++k) v += ps[k] * ((wp[k] >> (8 * b)) & 0xffu);
+          if (MORE)
+            for (uint32_t k = STATS_REG_PARENTS; k < npar; ++k) v += rec[3 + 2 * k] * (uint32_t)tile[rec[2 + 2 * k] * TRP + r + b];
+          const bool ok = quad_ok && r + b < rows && ((w0 >> (8 * b)) & 0xffu) != 0xFFu && v < spare;
+          idx[b] = ok ? v : spare;
+        }
       };
+      const uint32_t n_quads = a.TR / 4u;
       if (SMEM) {
-        for (uint32_t step = slice; step < a.TR; step += 2u * a.row_step) {
-          const uint32_t i0 = index_of(step), i1 = index_of(step + a.row_step);
+        for (uint32_t Q = slice; Q < n_quads; Q += a.row_step) {
+          uint32_t i[4];
+          quad(Q, i);
           // this lane is the only thread of the CTA that touches node `node`'s bins in copies 2 * slice (+ 1); the
-          // spare bins are shared by the warp's lanes, but nobody reads them
-          const uint32_t v0 = hA[i0], v1 = hB[i1];
-          hA[i0] = v0 + 1u;
-          hB[i1] = v1 + 1u;
+          // spare bins are shared by the warp's lanes, but nobody reads them.  Rows 0, 2 -> copy A, rows 1, 3 -> copy B.
+          const uint32_t v0 = hA[i[0]], v1 = hB[i[1]];
+          hA[i[0]] = v0 + 1u;
+          hB[i[1]] = v1 + 1u;
+          const uint32_t v2 = hA[i[2]], v3 = hB[i[3]];
+          hA[i[2]] = v2 + 1u;
+          hB[i[3]] = v3 + 1u;
         }
       } else {
-        for (uint32_t step = slice; step < a.TR; step += a.row_step) {
-          const uint32_t i0 = index_of(step);
-          if (i0 != spare) atomicAdd(&a.out[i0], 1ull);
+        for (uint32_t Q = slice; Q < n_quads; Q += a.row_step) {
+          uint32_t i[4];
+          quad(Q, i);
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (i[b] != spare) atomicAdd(&a.out[i[b]], 1ull);
         }
       }
     }
