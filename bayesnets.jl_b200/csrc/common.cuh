@@ -106,7 +106,17 @@ struct PoolBuf {
     n = count;
     return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), tl_stream);
   }
+  cudaError_t upload(const T* host, size_t count, cudaStream_t s) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess) return e;
+    if (count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
 };
+// Per-call temporaries of the host-buffer entry points (bn_sample, bn_gibbs_*, bn_statistics): pool allocations, so a
+// call costs no cudaMalloc / cudaFree (each ~0.1-1 ms and a device synchronisation) after the first one.
+template <typename T>
+using TmpBuf = PoolBuf<T>;
 
 // ---------------------------------------------------------------------------- objects behind handles
 struct SpecKernel;  // specialize.cu: one NVRTC-compiled LW kernel per (evidence mask, query)
@@ -180,6 +190,11 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
                                  uint64_t n_chains, int64_t burn_in, int64_t thin, int64_t total, uint64_t seed,
                                  double* out_dev, double* chain_counts_dev, uint8_t* state_dev, int32_t init_from_state,
                                  bool* used);
+
+int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const int32_t* orders_dev, uint32_t order_stride,
+                                        const uint8_t* init_dev, uint64_t first_chain, uint64_t n_chains, int64_t burn_in,
+                                        int64_t nsamples, int64_t thinning, uint64_t seed, uint8_t* out_states_dev,
+                                        uint64_t n_rows, bool* used);
 
 // ---------------------------------------------------------------------------- Philox4x32-10
 // Salmon et al. SC'11.  key bumps are warp-uniform so only 2 IMAD.WIDE + 2 LOP3 per round are

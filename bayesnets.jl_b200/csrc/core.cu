@@ -158,6 +158,7 @@ int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_p
   BN_CUDA_TRY(cudaGetDeviceCount(&ndev));
   BN_REQUIRE(device >= 0 && device < ndev, BN_BAD_ARG, "device %d out of range (%d visible)", device, ndev);
   BN_CUDA_TRY(cudaSetDevice(device));
+  ensure_pool(device);  // per-call temporaries of the host-buffer entry points come from the stream-ordered pool
 
   Net* net = new Net();
   net->device = device;

@@ -314,9 +314,9 @@ static void sweep_permutation(uint64_t seed, uint64_t sweep, int32_t m, int32_t*
 }
 
 struct GibbsDevice {
-  DevBuf<uint32_t> prog, upd_off, query;
-  DevBuf<int8_t> evidence;
-  DevBuf<int32_t> orders;
+  TmpBuf<uint32_t> prog, upd_off, query;
+  TmpBuf<int8_t> evidence;
+  TmpBuf<int32_t> orders;
 };
 
 static int32_t stage_gibbs(Net* net, const int8_t* evidence, uint32_t T, const int32_t* query, int32_t n_query,
@@ -451,8 +451,8 @@ int32_t bn_gibbs_infer(bn_net_t h, const int8_t* evidence, const int32_t* query,
   for (int j = 0; j < n_query; ++j)
     if (query && query[j] >= 0 && query[j] < net->n) ncell *= net->card[query[j]];
   BN_REQUIRE(ncell <= 4096, BN_UNSUPPORTED, "query table has more than 4096 cells");
-  DevBuf<double> d_out, d_cc;
-  DevBuf<uint8_t> d_state;
+  TmpBuf<double> d_out, d_cc;
+  TmpBuf<uint8_t> d_state;
   BN_CUDA_TRY(d_out.alloc((size_t)ncell));
   const size_t nst = (size_t)n_chains * net->n;
   if (state_inout) {
@@ -520,9 +520,9 @@ int32_t bn_gibbs_sample(bn_net_t h, const int8_t* evidence, uint64_t first_chain
   a.orders = dev.orders.p;
 
   // initial states
-  DevBuf<uint8_t> d_init, d_cand, d_out;
-  DevBuf<double> d_w;
-  DevBuf<int> d_flag;
+  TmpBuf<uint8_t> d_init, d_cand, d_out;
+  TmpBuf<double> d_w;
+  TmpBuf<int> d_flag;
   const size_t nst = (size_t)n_chains * net->n;
   BN_CUDA_TRY(d_init.alloc(nst));
   if (init_state) {
@@ -555,11 +555,16 @@ int32_t bn_gibbs_sample(bn_net_t h, const int8_t* evidence, uint64_t first_chain
   a.n_rows = n_chains * (uint64_t)nsamples;
   BN_CUDA_TRY(d_out.alloc((size_t)net->n * a.n_rows));
   a.out_states = d_out.p;
-  const size_t smem = (size_t)net->n * T;
-  BN_CUDA_TRY(cudaFuncSetAttribute(gibbs_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gibbs_sample_kernel<<<(unsigned)((n_chains + T - 1) / T), T, smem, s>>>(a, d_init.p);
-  count_launch();
-  BN_CUDA_TRY(cudaGetLastError());
+  bool used = false;  // network-specialised kernel first (specialize.cu); same tables either way
+  BN_TRY(launch_gibbs_sample_specialized(net, evidence, dev.orders.p, a.order_stride, d_init.p, first_chain, n_chains, burn_in,
+                                         nsamples, thinning, seed, d_out.p, a.n_rows, &used));
+  if (!used) {
+    const size_t smem = (size_t)net->n * T;
+    BN_CUDA_TRY(cudaFuncSetAttribute(gibbs_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gibbs_sample_kernel<<<(unsigned)((n_chains + T - 1) / T), T, smem, s>>>(a, d_init.p);
+    count_launch();
+    BN_CUDA_TRY(cudaGetLastError());
+  }
   BN_CUDA_TRY(cudaMemcpyAsync(out_states, d_out.p, (size_t)net->n * a.n_rows, cudaMemcpyDeviceToHost, s));
   BN_CUDA_TRY(cudaStreamSynchronize(s));
   return BN_OK;

@@ -482,8 +482,8 @@ int32_t bn_sample(bn_net_t h, const int8_t* evidence, int32_t kind, int32_t max_
   BN_REQUIRE(out_states, BN_BAD_ARG, "bn_sample: out_states is NULL");
   BN_CUDA_TRY(cudaSetDevice(net->device));
   const size_t nst = (size_t)net->n * n_rows;
-  DevBuf<uint8_t> d_states, d_ok;
-  DevBuf<double> d_w;
+  TmpBuf<uint8_t> d_states, d_ok;
+  TmpBuf<double> d_w;
   BN_CUDA_TRY(d_states.alloc(nst));
   BN_CUDA_TRY(d_w.alloc(n_rows));
   BN_CUDA_TRY(d_ok.alloc(n_rows));

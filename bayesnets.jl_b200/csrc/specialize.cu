@@ -701,6 +701,89 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   return o.str();
 }
 
+// gibbs_sample(bn, nsamples, burn_in; thinning, variable_order) specialised the same way (replaces the interpreter
+// gibbs_sample_kernel of gibbs.cu for src/gibbs.jl:183-245): the per-node blocks are the ones gibbs_spec uses, but
+// the sweep order changes every sweep (a fresh permutation, shared by all chains, :222-234), so the blocks sit behind
+// one `switch` on the sweep's order entry -- a warp-uniform indexed branch per update.  At small chain counts the
+// interpreter is bound by its ~2000-cycle dependent latency per update (4096 chains: one warp per scheduler); the
+// straight-line block cuts that by an order of magnitude.
+static std::string gen_gibbs_sample_source(const Net& net, const std::vector<char>& ev_mask, int threads, int min_blocks,
+                                           uint32_t* n_free_out) {
+  const int n = net.n;
+  std::ostringstream o;
+  uint32_t n_free = 0;
+  for (int i = 0; i < n; ++i) n_free += ev_mask[i] ? 0 : 1;
+  o << "// generated by libbn_cuda (specialize.cu): gibbs_sample, " << n << " nodes, " << n_free << " free\n";
+  o << kPrelude << kGibbsPrelude;
+  o << "#define NT " << threads << "\n#define NN " << n << "u\n#define NFREE " << n_free << "u\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(NT, " << min_blocks << ") gibbs_sample_spec(const double* __restrict__ cpt, "
+       "const int* __restrict__ orders, u32 order_stride, const unsigned char* __restrict__ init, u64 first_chain, "
+       "u64 n_chains, u32 k0, u32 k1, long long burn_in, long long nsamples, long long thinning, "
+       "unsigned char* __restrict__ out_states, u64 n_rows) {\n";
+  o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
+  o << "  const u32 tid = threadIdx.x;\n";
+  o << "  unsigned char* st = smem_raw + tid;\n";
+  o << "  const u64 ci = (u64)blockIdx.x * NT + tid;\n";
+  o << "  if (ci >= n_chains) return;\n";
+  o << "  const u64 chain = first_chain + ci;\n";
+  o << "  const u32 c0 = (u32)chain, c1 = (u32)(chain >> 32);\n";
+  o << "  for (u32 i = 0; i < NN; ++i) st[i * NT] = init[ci * NN + i];\n";
+  o << "  u32 d = 0u, b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;\n";
+  o << "  const long long total_sweeps = burn_in + nsamples * (thinning + 1);\n";
+  o << "  long long until = burn_in + thinning + 1, row = 0;  // sweeps until the next kept sample (src/gibbs.jl:226-240)\n";
+  o << "  for (long long sweep = 0; sweep < total_sweeps; ++sweep) {\n";
+  o << "    const int* ord = orders + (u64)sweep * order_stride;\n";
+  o << "    for (u32 f = 0; f < NFREE; ++f) {\n";
+  o << "      u32 r; NEXT_R(r);\n";
+  o << "      const double uu = ((double)r + 0.5) * (1.0 / 4294967296.0);\n";
+  o << "      switch (__ldg(ord + f)) {\n";
+  uint32_t rank = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ev_mask[i]) continue;
+    const int K = net.card[i];
+    o << "      case " << rank++ << ": {  // node " << i << ": card " << K << ", " << (net.child_ptr[i + 1] - net.child_ptr[i]) << " children\n";
+    o << "        double";
+    for (int v = 0; v < K; ++v) o << (v ? ", p" : " p") << v;
+    o << ";\n";
+    bool first = true;
+    auto emit_cpd = [&](int c, bool own) {
+      const int Kc = net.card[c];
+      std::ostringstream idx;
+      idx << (uint32_t)net.cpt_off[c] << "u";
+      uint32_t step = own ? 1u : 0u;
+      int64_t stride = 1;
+      for (int k = net.par_ptr[c]; k < net.par_ptr[c + 1]; ++k) {
+        const int pa = net.par_idx[k];
+        if (!own && pa == i) step = (uint32_t)(stride * Kc);
+        else idx << " + (u32)st[" << pa << " * NT] * " << (uint32_t)(stride * Kc) << "u";
+        stride *= net.card[pa];
+      }
+      if (!own) idx << " + (u32)st[" << c << " * NT]";
+      o << "        { const double* pr = cpt + (" << idx.str() << ");";
+      for (int v = 0; v < K; ++v)
+        o << " p" << v << (first ? " = " : " *= ") << "__ldg(pr + " << (uint32_t)v * step << "u);";
+      o << " }  // " << (own ? "own CPD" : "child ") << c << "\n";
+      first = false;
+    };
+    for (int k = net.child_ptr[i]; k < net.child_ptr[i + 1]; ++k) emit_cpd(net.child_idx[k], false);
+    emit_cpd(i, true);
+    o << "        double sum = p0;";
+    for (int v = 1; v < K; ++v) o << " sum += p" << v << ";";
+    o << "\n        const double t = uu * sum;\n";
+    o << "        u32 pick = 0u; double cw = p0; bool go = true;\n";
+    for (int v = 1; v < K; ++v)
+      o << "        go = go && (cw < t); if (go) { cw += p" << v << "; pick = " << v << "u; }\n";
+    o << "        st[" << i << " * NT] = (unsigned char)pick;\n";
+    o << "      } break;\n";
+  }
+  o << "      default: break;\n      }\n    }\n";
+  o << "    if (--until == 0) {\n      until = thinning + 1;\n";
+  o << "      for (u32 i = 0; i < NN; ++i) out_states[(u64)i * n_rows + ci * (u64)nsamples + (u64)row] = st[i * NT];\n";
+  o << "      ++row;\n    }\n  }\n}\n";
+  if (n_free_out) *n_free_out = n_free;
+  return o.str();
+}
+
 thread_local int tl_gibbs_mode = 0;  // 0 auto, 1 generic only, 2 specialised required
 
 int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t* query, uint32_t n_query,
@@ -799,6 +882,80 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
   const unsigned grid = (unsigned)((n_chains + k->threads - 1) / k->threads);
   CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)s, args, nullptr);
   if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(gibbs_spec)", r);
+  count_launch();
+  *used = true;
+  return BN_OK;
+}
+
+// Specialised gibbs_sample: orders / init / out are device pointers prepared by bn_gibbs_sample (gibbs.cu).
+int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const int32_t* orders_dev, uint32_t order_stride,
+                                        const uint8_t* init_dev, uint64_t first_chain, uint64_t n_chains, int64_t burn_in,
+                                        int64_t nsamples, int64_t thinning, uint64_t seed, uint8_t* out_states_dev,
+                                        uint64_t n_rows, bool* used) {
+  *used = false;
+  if (tl_gibbs_mode == 1) return BN_OK;
+  const bool must = tl_gibbs_mode == 2;
+  Driver& drv = driver();
+  if (!nvrtc().ok || !drv.ok) return BN_OK;  // the interpreter kernel serves the call
+  bool ok = net->n <= 1024 && net->cpt_off[net->n] < (int64_t)0x7fffffff;
+  for (int i = 0; i < net->n && ok; ++i) ok = net->card[i] <= GIBBS_SPEC_MAX_CARD;
+  const DevProps& dp = dev_props(net->device);
+  const int T = 64;
+  const size_t smem = (size_t)net->n * T;
+  if (!ok || smem + 1024 > (size_t)dp.max_smem_optin) return BN_OK;
+  std::vector<char> ev_mask((size_t)net->n, 0);
+  uint32_t n_free = 0;
+  for (int i = 0; i < net->n; ++i) { ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0; n_free += ev_mask[i] ? 0 : 1; }
+  if (n_free == 0) return BN_OK;
+  std::string key((size_t)net->n, '0');
+  for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
+  key += "|gsample";
+  SpecKernel* k = nullptr;
+  auto it = net->spec_cache.find(key);
+  if (it != net->spec_cache.end()) {
+    k = it->second;
+  } else if (!must && !jit_worthwhile(net, key, (double)n_chains * (double)(burn_in + nsamples * (thinning + 1)) * n_free, 2e11)) {
+    return BN_OK;
+  } else {
+    const std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 8, nullptr);
+    const std::string gkey = std::to_string(net->device) + "|" + src;
+    std::lock_guard<std::mutex> lk(g_spec_mu);
+    auto git = g_spec.find(gkey);
+    if (git != g_spec.end()) {
+      k = git->second.get();
+    } else {
+      std::vector<char> cubin;
+      std::string log;
+      g_spec_compiles.fetch_add(1);
+      int32_t rc = nvrtc_compile(src, &cubin, &log);
+      if (rc != BN_OK) {
+        g_spec[gkey] = nullptr;  // the interpreter serves this structure from now on
+      } else {
+        std::unique_ptr<SpecKernel> nk(new SpecKernel());
+        CUresult r = drv.ModuleLoadData(&nk->mod, cubin.data());
+        if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
+        r = drv.ModuleGetFunction(&nk->fn, nk->mod, "gibbs_sample_spec");
+        if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
+        nk->threads = T;
+        nk->smem = smem;
+        nk->n_live = n_free;
+        r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+        if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
+        k = nk.get();
+        g_spec[gkey] = std::move(nk);
+      }
+    }
+    net->spec_cache[key] = k;
+  }
+  if (!k) return BN_OK;
+  const double* cpt = net->d_cpt.p;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  long long bi = burn_in, ns = nsamples, th = thinning;
+  void* args[] = {(void*)&cpt, (void*)&orders_dev, (void*)&order_stride, (void*)&init_dev, (void*)&first_chain, (void*)&n_chains,
+                  (void*)&k0, (void*)&k1, (void*)&bi, (void*)&ns, (void*)&th, (void*)&out_states_dev, (void*)&n_rows};
+  const unsigned grid = (unsigned)((n_chains + k->threads - 1) / k->threads);
+  CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)tl_stream, args, nullptr);
+  if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(gibbs_sample_spec)", r);
   count_launch();
   *used = true;
   return BN_OK;

@@ -290,8 +290,8 @@ int32_t bn_statistics(bn_net_t h, const uint8_t* states, uint64_t n_rows, int64_
                  (int)c - 1);
   }
   const uint64_t pitch = (n_rows + 15) / 16 * 16;
-  DevBuf<uint8_t> d_states;
-  DevBuf<unsigned long long> d_out;
+  TmpBuf<uint8_t> d_states;
+  TmpBuf<unsigned long long> d_out;
   BN_CUDA_TRY(d_states.alloc((size_t)net->n * pitch + 16));
   BN_CUDA_TRY(d_out.alloc(n_bins + 1));
   if (n_rows)

@@ -91,7 +91,9 @@ int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* que
  * prune: != 0 lets the specialised kernel skip "barren" nodes (not an ancestor of a query or evidence node);
  *        draw indices are static, so the counts are bit-identical either way.  Default: mode 0, prune 1. */
 int32_t bn_set_lw_mode(int32_t mode, int32_t prune);
-/* Same selection for bn_gibbs_infer: 0 = auto, 1 = generic interpreter kernel, 2 = specialised required. */
+/* Same selection for bn_gibbs_infer and bn_gibbs_sample: 0 = auto, 1 = generic interpreter kernel, 2 = specialised
+ * (bn_gibbs_infer: required; bn_gibbs_sample: used whenever the network qualifies -- <= 8 states per node -- else the
+ * interpreter serves the call).  Chains, counts and tables are identical either way. */
 int32_t bn_set_gibbs_mode(int32_t mode);
 /* Number of NVRTC compiles since load (kernels are cached process-wide by generated source). */
 uint64_t bn_lw_spec_compile_count(void);

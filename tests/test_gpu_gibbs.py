@@ -112,8 +112,12 @@ def test_gibbs_reference_suite(bn, golden):
             bn.infer(cls(nsamples=10, burn_in=10), stu, "D")
 
 
+@pytest.mark.parametrize("mode", ["generic", "specialized"])
 @pytest.mark.parametrize("order", [None, "fixed"])
-def test_gibbs_sample_tables_equal_oracle(bn, order):
+def test_gibbs_sample_tables_equal_oracle(bn, gibbs_mode, order, mode):
+    """gibbs_sample tables from the interpreter kernel and from the NVRTC network-specialised one (per-node blocks behind
+    a switch on the sweep order) are identical to the oracle's: random and fixed sweep orders, thinning, burn-in."""
+    gibbs_mode(mode)
     net, lay, on, query, evidence = random_case(bn, 30, 5, 3)
     evv = lay.evidence_vector(evidence)
     free = [n for n in lay.names if evv[lay.index[n]] < 0]
