@@ -637,8 +637,10 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   }
   o << "    for (;;) {\n";
   int emitted = 0;
-  // optional re-convergence barrier every N nodes (BN_GIBBS_SYNC); measured no gain on B200, off by default
-  const int sync_every = getenv("BN_GIBBS_SYNC") ? atoi(getenv("BN_GIBBS_SYNC")) : (1 << 30);
+  // Re-convergence barrier every N nodes: the generated code (~1.2 KB per node) is larger than the instruction caches,
+  // and 20% of the warp-state samples were `no_inst`; 256-thread CTAs that meet every 32 nodes fetch each code
+  // window once for 8 warps (C4: 0.84 -> 0.76 ms; profiles/r1f_gibbs_sync_sweep.txt).  64-thread CTAs do not sync.
+  const int sync_every = getenv("BN_GIBBS_SYNC") ? std::max(1, atoi(getenv("BN_GIBBS_SYNC"))) : (threads >= 128 ? 32 : (1 << 30));
   for (int i = 0; i < n; ++i) {
     if (ev_mask[i]) continue;
     const int K = net.card[i];
@@ -804,7 +806,7 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
   for (int i = 0; i < net->n && ok; ++i) ok = net->card[i] <= GIBBS_SPEC_MAX_CARD;
   const DevProps& dp = dev_props(net->device);
   // small CTAs: the grid balances dynamically and 64-thread CTAs measured fastest (profiles/r1d_gibbs_spec_sweep.txt)
-  int T = n_chains >= (uint64_t)dp.sm_count * 2048 ? 128 : 64;
+  int T = n_chains >= (uint64_t)dp.sm_count * 256 ? 256 : 64;  // one 256-thread CTA per SM or more: see sync_every
   while (T > 64 && (size_t)ncell * 8 + (size_t)net->n * T + 1024 > (size_t)dp.max_smem_optin) T -= 32;
   if (const char* e = getenv("BN_GIBBS_THREADS")) T = atoi(e);
   const size_t smem = (size_t)ncell * 8 + (size_t)net->n * T;
@@ -827,7 +829,7 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
     return BN_OK;
   } else {
     uint32_t n_free = 0;
-    int minb = 8;  // <= 128 registers per thread at T = 64
+    int minb = 512 / T;  // <= 128 registers per thread
     if (const char* e = getenv("BN_GIBBS_MINB")) minb = atoi(e);
     const std::string src = gen_gibbs_source(*net, ev_mask, query, n_query, qstride, ncell, full, T, minb, &n_free);
     const std::string gkey = std::to_string(net->device) + "|" + src;
