@@ -710,7 +710,7 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
 // interpreter is bound by its ~2000-cycle dependent latency per update (4096 chains: one warp per scheduler); the
 // straight-line block cuts that by an order of magnitude.
 static std::string gen_gibbs_sample_source(const Net& net, const std::vector<char>& ev_mask, int threads, int min_blocks,
-                                           uint32_t* n_free_out) {
+                                           int sync_every, uint32_t* n_free_out) {
   const int n = net.n;
   std::ostringstream o;
   uint32_t n_free = 0;
@@ -726,10 +726,10 @@ static std::string gen_gibbs_sample_source(const Net& net, const std::vector<cha
   o << "  const u32 tid = threadIdx.x;\n";
   o << "  unsigned char* st = smem_raw + tid;\n";
   o << "  const u64 ci = (u64)blockIdx.x * NT + tid;\n";
-  o << "  if (ci >= n_chains) return;\n";
+  o << "  const bool live = ci < n_chains;  // surplus threads of the last CTA run a dummy chain (barriers need them)\n";
   o << "  const u64 chain = first_chain + ci;\n";
   o << "  const u32 c0 = (u32)chain, c1 = (u32)(chain >> 32);\n";
-  o << "  for (u32 i = 0; i < NN; ++i) st[i * NT] = init[ci * NN + i];\n";
+  o << "  for (u32 i = 0; i < NN; ++i) st[i * NT] = live ? init[ci * NN + i] : (unsigned char)0;\n";
   o << "  u32 d = 0u, b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;\n";
   o << "  const long long total_sweeps = burn_in + nsamples * (thinning + 1);\n";
   o << "  long long until = burn_in + thinning + 1, row = 0;  // sweeps until the next kept sample (src/gibbs.jl:226-240)\n";
@@ -778,9 +778,11 @@ static std::string gen_gibbs_sample_source(const Net& net, const std::vector<cha
     o << "        st[" << i << " * NT] = (unsigned char)pick;\n";
     o << "      } break;\n";
   }
-  o << "      default: break;\n      }\n    }\n";
+  o << "      default: break;\n      }\n";
+  if (sync_every > 0) o << "      if ((f % " << sync_every << "u) == " << (sync_every - 1) << "u) __syncthreads();  // one instruction fetch per block for the whole CTA\n";
+  o << "    }\n";
   o << "    if (--until == 0) {\n      until = thinning + 1;\n";
-  o << "      for (u32 i = 0; i < NN; ++i) out_states[(u64)i * n_rows + ci * (u64)nsamples + (u64)row] = st[i * NT];\n";
+  o << "      if (live) for (u32 i = 0; i < NN; ++i) out_states[(u64)i * n_rows + ci * (u64)nsamples + (u64)row] = st[i * NT];\n";
   o << "      ++row;\n    }\n  }\n}\n";
   if (n_free_out) *n_free_out = n_free;
   return o.str();
@@ -902,7 +904,9 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
   bool ok = net->n <= 1024 && net->cpt_off[net->n] < (int64_t)0x7fffffff;
   for (int i = 0; i < net->n && ok; ++i) ok = net->card[i] <= GIBBS_SPEC_MAX_CARD;
   const DevProps& dp = dev_props(net->device);
-  const int T = 64;
+  int T = 64, sync_every = 0;
+  if (const char* e = getenv("BN_GSAMPLE_THREADS")) T = atoi(e);
+  if (const char* e = getenv("BN_GSAMPLE_SYNC")) sync_every = atoi(e);
   const size_t smem = (size_t)net->n * T;
   if (!ok || smem + 1024 > (size_t)dp.max_smem_optin) return BN_OK;
   std::vector<char> ev_mask((size_t)net->n, 0);
@@ -911,7 +915,7 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
   if (n_free == 0) return BN_OK;
   std::string key((size_t)net->n, '0');
   for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
-  key += "|gsample";
+  key += "|gsample" + std::to_string(T) + "s" + std::to_string(sync_every);
   SpecKernel* k = nullptr;
   auto it = net->spec_cache.find(key);
   if (it != net->spec_cache.end()) {
@@ -919,7 +923,7 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
   } else if (!must && !jit_worthwhile(net, key, (double)n_chains * (double)(burn_in + nsamples * (thinning + 1)) * n_free, 2e11)) {
     return BN_OK;
   } else {
-    const std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 8, nullptr);
+    const std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 512 / T, sync_every, nullptr);
     const std::string gkey = std::to_string(net->device) + "|" + src;
     std::lock_guard<std::mutex> lk(g_spec_mu);
     auto git = g_spec.find(gkey);
