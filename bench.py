@@ -217,10 +217,22 @@ def run_gpu(args):
     from bayesnets_jl_b200.distributed import ShardedLikelihoodWeighting, env_rank_world
 
     rank, world, local = env_rank_world()
+    torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # stdout carries exactly one JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) to fd 1
+        # while the communicator is created, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if args.gpus != world and rank == 0:
         print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     torch.cuda.set_device(local)
