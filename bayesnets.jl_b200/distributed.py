@@ -85,3 +85,47 @@ class ShardedLikelihoodWeighting:
         c = self.out[:self.ncell].cpu().numpy()
         with np.errstate(invalid="ignore", divide="ignore"):
             return (c / c.sum()).reshape(self.shape, order="F")
+
+
+class ShardedGibbs:
+    """Gibbs inference (Nodewise / Full) whose CHAINS are split over the ranks of the default process group
+    (BASELINE config C4: 65 536 chains over 8 GPUs).  Rank g runs chains [g*C//G, (g+1)*C//G) of one global chain
+    index space (the Philox counter is the global chain index), then the integer count tensors are all-reduced:
+    the result equals the single-GPU counts exactly."""
+
+    def __init__(self, bn, query, evidence, n_chains: int, nsamples: int, burn_in: int, thin: int, full: bool = False,
+                 seed: int = 0, device: int | None = None):
+        import torch
+        self.torch = torch
+        rank, world, local = env_rank_world()
+        self.rank, self.world = rank, world
+        self.device = local if device is None else device
+        self.net = device_net(bn, self.device)
+        lay = self.net.layout
+        self.ev = lay.evidence_vector(evidence)
+        self.q = lay.query_indices(query)
+        self.shape = [int(lay.card[i]) for i in self.q]
+        self.ncell = int(np.prod(self.shape)) if self.shape else 1
+        self.first, self.count = shard_range(int(n_chains), rank, world)
+        self.nsamples, self.burn_in, self.thin, self.full, self.seed = int(nsamples), int(burn_in), int(thin), bool(full), int(seed)
+        self.out = torch.zeros(self.ncell, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def launch(self):
+        """Enqueue the local shard only (no collective); counts in self.out."""
+        _lib.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+        qp = self.q if self.q.size else np.zeros(1, np.int32)
+        check(_lib.lib().bn_gibbs_infer_dev(_lib.h64(self.net.handle), ptr(self.ev, _lib.i8p), ptr(qp, _lib.i32p),
+                                            C.c_int32(self.q.size), C.c_uint64(self.first), C.c_uint64(self.count),
+                                            C.c_int64(self.nsamples), C.c_int64(self.burn_in), C.c_int64(self.thin),
+                                            C.c_int32(1 if self.full else 0), C.c_uint64(self.seed),
+                                            C.c_void_p(self.out.data_ptr())))
+        return self.out
+
+    def step(self):
+        self.launch()
+        return allreduce_sum_(self.out)
+
+    def posterior(self) -> np.ndarray:
+        c = self.out.cpu().numpy()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return (c / c.sum()).reshape(self.shape, order="F")
