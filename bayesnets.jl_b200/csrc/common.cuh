@@ -93,13 +93,18 @@ template <typename T>
 struct PoolBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owns = true;  // false: a read-only view of memory owned elsewhere (borrow)
   PoolBuf() = default;
   PoolBuf(const PoolBuf&) = delete;
   PoolBuf& operator=(const PoolBuf&) = delete;
   ~PoolBuf() { release(); }
   void release() {
-    if (p) cudaFreeAsync(p, tl_stream);
-    p = nullptr; n = 0;
+    if (p && owns) cudaFreeAsync(p, tl_stream);
+    p = nullptr; n = 0; owns = true;
+  }
+  void borrow(T* ptr, size_t count) {
+    release();
+    p = ptr; n = count; owns = false;
   }
   cudaError_t alloc(size_t count) {
     release();
@@ -156,6 +161,10 @@ bn_factor_t register_factor(Factor* f);
 Factor* take_factor(bn_factor_t h);  // removes the handle, caller deletes
 int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>& card, int device,
                    Factor** out);
+// convert(Factor, cpd) WITHOUT the copy: a read-only view of the node's CPT inside the net (dims = [node, parents...]).
+// Internal to variable elimination, whose kernels only read their operands; never handed to callers, never normalised
+// in place.  The view must not outlive the net.
+int32_t factor_view_of_cpd(Net* net, int32_t node, bn_factor_t* out);
 
 // ---------------------------------------------------------------------------- sampling program
 // Host-compiled form of (net, evidence) shared by the generic particle kernel (sampling.cu) and the

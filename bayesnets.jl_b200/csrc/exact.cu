@@ -86,11 +86,16 @@ extern "C" int32_t bn_exact_infer(bn_net_t hnet, const int8_t* evidence, const i
 
   HandleBag bag;
   // factors = map(n -> Factor(bn, n, evidence), nodes)   (:16)
+  // The CPTs are used where they lie: a factor is a read-only VIEW of its node's table inside the net (no copy; the
+  // C5 net's 2^24-entry CPT alone would be 128 MB read + written per call), and only factors that actually mention an
+  // evidence variable are sliced into a new table.
   for (int i = 0; i < net->n; ++i) {
     bn_factor_t f = 0, g = 0;
-    BN_TRY(bn_factor_from_cpd(hnet, i, &f));
+    BN_TRY(factor_view_of_cpd(net, i, &f));
     bag.hs.push_back(f);
-    if (!ev_dims.empty()) {
+    bool touched = false;
+    for (int32_t d : get_factor(f)->dims) touched = touched || (evidence && evidence[d] >= 0);
+    if (touched) {
       BN_TRY(bn_factor_slice(f, ev_dims.data(), ev_states.data(), (int32_t)ev_dims.size(), &g));
       bag.drop(f);
       bag.hs.push_back(g);
@@ -133,6 +138,11 @@ extern "C" int32_t bn_exact_infer(bn_net_t hnet, const int8_t* evidence, const i
     if (own) bn_factor_free(acc);
     BN_TRY(rc);
     acc = nxt; own = true;
+  }
+  if (!get_factor(acc)->data.owns) {  // a lone CPT view (single-factor network): normalise a copy, never the net
+    bn_factor_t cp = 0;
+    BN_TRY(bn_factor_slice(acc, nullptr, nullptr, 0, &cp));
+    acc = cp; own = true;
   }
   int32_t rc = bn_factor_normalize(acc, 1);
   Factor* f = get_factor(acc);

@@ -544,7 +544,8 @@ static int32_t contract(int device, const std::vector<Operand>& ops, const std::
   // consecutive doubles of that operand (see rowvec in the kernel).  Skipped when the leading operand lacks some
   // output dim (then those dims go into the rows instead, which saves an HBM re-read of the leading operand).
   int rowvec_op = -1;
-  if (vec == VEC_LO && ns == 0 && nf <= 3 && G == 1 && !getenv("BN_NO_ROWVEC")) {
+  static const bool no_rowvec = getenv("BN_NO_ROWVEC") != nullptr;
+  if (vec == VEC_LO && ns == 0 && nf <= 3 && G == 1 && !no_rowvec) {
     bool lead_has_all = true;
     for (int i = nlo; i < no; ++i) lead_has_all = lead_has_all && st[lead][i] != 0;
     long long best_len = 1 << 15;  // smaller operands live in L1/L2 anyway
@@ -786,6 +787,40 @@ int32_t bn_factor_from_cpd(bn_net_t h, int32_t node, bn_factor_t* out) {
   return BN_OK;
 }
 
+}  // extern "C"
+
+namespace bn {
+int32_t factor_view_of_cpd(Net* net, int32_t node, bn_factor_t* out) {
+  std::vector<int32_t> d{node}, c{net->card[node]};
+  for (int k = net->par_ptr[node]; k < net->par_ptr[node + 1]; ++k) {
+    d.push_back(net->par_idx[k]);
+    c.push_back(net->card[net->par_idx[k]]);
+  }
+  BN_REQUIRE((int)d.size() <= MAXD, BN_UNSUPPORTED, "node %d has too many parents", node);
+  const double* src = net->d_cpt.p + net->cpt_off[node];
+  if (reinterpret_cast<uintptr_t>(src) % 16 != 0) {
+    // tables are packed back to back, so one that follows an odd number of doubles is only 8-byte aligned; the
+    // kernels would fall back to 64-bit loads on it, so take the (pool-allocated, aligned) copy instead
+    Factor* c2 = nullptr;
+    BN_TRY(new_factor(d, c, net->device, &c2));
+    cudaError_t e = cudaMemcpyAsync(c2->data.p, src, (size_t)c2->len * 8, cudaMemcpyDeviceToDevice, tl_stream);
+    if (e != cudaSuccess) { delete c2; BN_CUDA_TRY(e); }
+    *out = register_factor(c2);
+    return BN_OK;
+  }
+  Factor* f = new Factor();
+  f->device = net->device;
+  f->dims = d;
+  f->card = c;
+  f->len = net->cpt_off[node + 1] - net->cpt_off[node];
+  f->data.borrow(const_cast<double*>(src), (size_t)f->len);
+  *out = register_factor(f);
+  return BN_OK;
+}
+}  // namespace bn
+
+extern "C" {
+
 int32_t bn_factor_relabel(bn_factor_t h, const int32_t* new_dims) {
   Factor* f = get_factor(h);
   BN_REQUIRE(f && (new_dims || f->dims.empty()), BN_BAD_ARG, "bn_factor_relabel: bad arguments");
@@ -945,6 +980,7 @@ int32_t bn_factor_normalize(bn_factor_t h, int32_t pnorm) {
   Factor* f = get_factor(h);
   BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_normalize: unknown handle");
   BN_REQUIRE(pnorm == 1 || pnorm == 2, BN_BAD_ARG, "p = %d is not supported", pnorm);  // factors_dims.jl:51
+  BN_REQUIRE(f->data.owns, BN_BAD_ARG, "bn_factor_normalize: the factor is a read-only view");
   BN_CUDA_TRY(cudaSetDevice(f->device));
   const DevProps& dp = dev_props(f->device);
   const long long grid_ll = std::max<long long>(1, (f->len / 2 + NORM_CHUNK - 1) / NORM_CHUNK);
