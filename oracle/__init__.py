@@ -9,6 +9,9 @@ Two halves:
                           C factor ops that are timed as the CPU baseline
   * ``oracle.factors_np`` numpy restatement of ``src/Factors`` + ``ExactInference`` + brute-force
                           joint enumeration (independent second opinion on the C code)
+  * ``oracle.scoring_py`` Dirichlet priors + ``bayesian_score_component`` on the count tables of
+                          ``capi.statistics`` (``structure_scoring.jl:17-42``), pinned to the five score
+                          values of ``test/test_discrete_bayes_nets.jl:40-44``
 
 Parity status: the reference cannot run in this image (no Julia; deps un-vendored, ``Project.toml:5-25``),
 so the oracle is pinned against the reference's golden vectors (``tests/test_oracle_golden.py``).

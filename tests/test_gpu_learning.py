@@ -142,3 +142,35 @@ def test_sample_then_count_on_device_recovers_the_cpts(bn):
     _, counts = bn.statistics_device(net, tab.data_ptr(), n_rows)
     assert counts[lay.cpt_off[0]:lay.cpt_off[1]].sum() == n_ok
     assert np.array_equal(counts, capi.statistics(oracle_net_from_layout(lay), tab.cpu().numpy()))
+
+
+@pytest.mark.parametrize("n_rows", [0, 1, 257, 100_003])
+def test_statistics_many_parents_and_empty_tables(bn, n_rows):
+    """Nodes with more parents than the kernel keeps in registers (generic tail loop), a parentless single-state node,
+    zero rows, and the same structure with a count table too large for shared memory (global-atomic path)."""
+    from bayesnets_jl_b200 import _lib
+    rng = np.random.default_rng(21)
+    for wide in (False, True):
+        cards = [3, 2, 4, 2, 3, 1, 2] + ([200, 150] if wide else [])
+        cpds = []
+        for i, k in enumerate(cards):
+            if i < 5 or i == 5:
+                parents = []
+            elif i == 6:
+                parents = [0, 1, 2, 3, 4]          # 5 parents: 3 in registers + 2 from the program
+            else:
+                parents = [0, 2, 4, 6][: (4 if i == 7 else 2)] + ([7] if i == 8 else [])  # 4 parents; 255-ish wide tables
+            pn = [cards[p] for p in parents]
+            q = int(np.prod(pn)) if parents else 1
+            cpds.append(bn.CategoricalCPD(f"m{i}", [f"m{p}" for p in parents], pn, [np.full(k, 1.0 / k)] * q))
+        net = bn.BayesNet(cpds)
+        lay = bn.flatten(net)
+        table = np.stack([rng.integers(0, int(c), n_rows, dtype=np.uint8) for c in lay.card]) if n_rows else \
+            np.zeros((lay.n, 0), np.uint8)
+        out = np.full(int(lay.cpt_off[-1]), -1, np.int64)
+        dn = bn.device_net(net)
+        _lib.check(_lib.lib().bn_statistics(_lib.h64(dn.handle), _lib.ptr(table, _lib.u8p) if n_rows else None,
+                                            C.c_uint64(n_rows), _lib.ptr(out, _lib.i64p)))
+        ref = capi.statistics(oracle_net_from_layout(lay), table, n_rows=n_rows, pitch=max(n_rows, 1)) if n_rows else \
+            np.zeros_like(out)
+        assert np.array_equal(out, ref), (wide, n_rows)
