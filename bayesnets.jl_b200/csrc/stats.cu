@@ -14,13 +14,14 @@
 // asynchronous copies (cp.async), double-buffered so the next tile streams in while the current one is counted.  Counting is OWNER-COMPUTES, WITHOUT ATOMICS: inside a warp the 32 lanes are 32 different
 // nodes, and a (row slice, node group) pair belongs to exactly one warp of the CTA, so a lane is the only thread of
 // its CTA that ever touches its node's count table in its slice's histogram copy -- a plain load / add / store.
-// Each lane takes four consecutive rows per step (one 32-bit load per column carries their four states) and alternates
-// between two histogram copies, so consecutive read-modify-writes are independent.
+// Each lane takes four consecutive rows per step (one 32-bit load per column carries their four states).
 // Measured on the C2 net (100 nodes, 2^24 rows, B200): with shared-memory atomics 3.98e9 rows/s (32 rows of one node
 // per warp: a binary root has two bins for 32 lanes) and 3.79e9 (nodes across lanes, no same-address conflicts) --
 // the atomic unit, not the conflicts, was the limit; owner-computes with a branchy inner loop 2.7e9 (72 instructions
 // per lane-row, ncu), branch-free 4.25e9 (38 per lane-row; issue-bound at 25% occupancy, profiles/r1f_stats_*), four
-// rows per step with 32-bit state loads 6.57e9.
+// rows per step with 32-bit state loads 6.5e9.  At that point the kernel issues ~0.7 shared-memory wavefronts per clock
+// per SM (state loads + histogram read-modify-writes, half of them bank-conflict replays): occupancy (25 -> 50%), a
+// second histogram copy per slice for independent read-modify-writes and more row slices all measured within 3%.
 // A lane keeps its node's program (table offset, first parents and strides) in registers for the whole tile.
 // Column i of a tile starts at byte i * (TR + 16), i.e. in bank group 4 * (i % 8); lane i reads row r + 4 * (i / 8),
 // which moves the four lanes of a bank group onto four different banks: the state loads are conflict free.  The
@@ -39,7 +40,7 @@ struct StatsArgs {
   const uint32_t* prog_off;  // [n_nodes] word offset of each node's record
   uint32_t prog_words, n_nodes, n_bins, TR;
   uint32_t hist_in_smem, use_async;  // use_async: table and pitch 16-byte aligned
-  uint32_t bins_pad;                        // words per histogram copy; 2 * row_step copies
+  uint32_t bins_pad, copies;                // words per histogram copy; copies (1 or 2) per row slice
   uint32_t n_groups, group_step, row_step;  // warp w: node groups w % group_step + k * group_step, row slice w / group_step
   unsigned long long* out;  // [n_bins]
 };
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) 
   uint32_t* prog = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* prog_off = prog + a.prog_words;
   uint32_t* hist = prog_off + a.n_nodes;
-  const uint32_t hist_words = SMEM ? a.bins_pad * 2u * a.row_step : 0u;
+  const uint32_t hist_words = SMEM ? a.bins_pad * a.copies * a.row_step : 0u;
   const uint32_t TRP = a.TR + 16u;
   const uint32_t tile_bytes = a.n_nodes * TRP;
   unsigned char* tiles = smem_raw + (((a.prog_words + a.n_nodes + hist_words) * 4u + 127u) & ~127u);
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) 
       // to the spare bin n_bins of their copy (bins_pad > n_bins), which is never flushed.
       const uint32_t coff = live ? node * TRP : 0u;
       const uint32_t slice = warp / a.group_step;
-      uint32_t* hA = hist + (2u * slice) * a.bins_pad;
-      uint32_t* hB = hA + a.bins_pad;
+      uint32_t* hA = hist + (a.copies * slice) * a.bins_pad;
+      uint32_t* hB = hA + (a.copies - 1u) * a.bins_pad;
       const uint32_t spare = a.n_bins;
       // four consecutive rows per step: one 32-bit load per (node | parent) column carries their four states
       auto quad = [&](uint32_t Q, uint32_t (&idx)[4]) {
@@ -154,12 +155,17 @@ __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) 
           quad(Q, i);
           // this lane is the only thread of the CTA that touches node `node`'s bins in copies 2 * slice (+ 1); the
           // spare bins are shared by the warp's lanes, but nobody reads them.  Rows 0, 2 -> copy A, rows 1, 3 -> copy B.
-          const uint32_t v0 = hA[i[0]], v1 = hB[i[1]];
-          hA[i[0]] = v0 + 1u;
-          hB[i[1]] = v1 + 1u;
-          const uint32_t v2 = hA[i[2]], v3 = hB[i[3]];
-          hA[i[2]] = v2 + 1u;
-          hB[i[3]] = v3 + 1u;
+          if (a.copies == 2u) {
+            const uint32_t v0 = hA[i[0]], v1 = hB[i[1]];
+            hA[i[0]] = v0 + 1u;
+            hB[i[1]] = v1 + 1u;
+            const uint32_t v2 = hA[i[2]], v3 = hB[i[3]];
+            hA[i[2]] = v2 + 1u;
+            hB[i[3]] = v3 + 1u;
+          } else {  // one copy: the four read-modify-writes may hit the same bin, so they stay in program order
+#pragma unroll
+            for (int b = 0; b < 4; ++b) hA[i[b]] += 1u;
+          }
         }
       } else {
         for (uint32_t Q = slice; Q < n_quads; Q += a.row_step) {
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) 
   if (SMEM)
     for (uint32_t b = tid; b < a.n_bins; b += T) {
       unsigned long long c = 0;
-      for (uint32_t k = 0; k < 2u * a.row_step; ++k) c += hist[k * a.bins_pad + b];
+      for (uint32_t k = 0; k < a.copies * a.row_step; ++k) c += hist[k * a.bins_pad + b];
       if (c) atomicAdd(&a.out[b], c);
     }
 }
@@ -218,11 +224,16 @@ static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_r
   a.group_step = std::min<uint32_t>(a.n_groups, 32u);
   a.bins_pad = (uint32_t)((n_bins + 32) / 32 * 32 + 1);  // odd pitch: the copies of a bin sit in different banks
   const size_t min_tiles = 2 * (size_t)n * (32 + 16);
+  static const uint32_t copies_env = getenv("BN_STATS_COPIES") ? (uint32_t)atoi(getenv("BN_STATS_COPIES")) : 0u;
+  static const uint32_t slices_env = getenv("BN_STATS_SLICES") ? (uint32_t)atoi(getenv("BN_STATS_SLICES")) : 0u;
+  const uint32_t copies = copies_env == 2u ? 2u : 1u;
+  a.copies = copies;
   uint32_t slices = std::max<uint32_t>(1u, std::min<uint32_t>(4u, 8u / a.group_step));  // ~8 warps per CTA
-  while (slices > 1 && prog_b + (size_t)a.bins_pad * 4 * 2 * slices + 2 * (size_t)n * (128 + 16) > budget / 2) slices /= 2;
-  a.hist_in_smem = (prog_b + (size_t)a.bins_pad * 4 * 2 * slices + min_tiles <= budget) ? 1u : 0u;
+  if (slices_env) slices = slices_env;
+  while (slices > 1 && prog_b + (size_t)a.bins_pad * 4 * copies * slices + 2 * (size_t)n * (128 + 16) > budget / 2) slices /= 2;
+  a.hist_in_smem = (prog_b + (size_t)a.bins_pad * 4 * copies * slices + min_tiles <= budget) ? 1u : 0u;
   a.row_step = slices;
-  const size_t fixed = ((prog_b + (a.hist_in_smem ? (size_t)a.bins_pad * 4 * 2 * slices : 0) + 127) / 128) * 128;
+  const size_t fixed = ((prog_b + (a.hist_in_smem ? (size_t)a.bins_pad * 4 * copies * slices : 0) + 127) / 128) * 128;
   BN_REQUIRE(fixed + min_tiles <= budget, BN_UNSUPPORTED, "network too large for the statistics kernel (%d nodes)", n);
   uint32_t TR = 512;
   while (TR > 32 && fixed + 2 * (size_t)n * (TR + 16) > budget / 2) TR /= 2;
