@@ -66,6 +66,8 @@ _SIGS = {
     "bn_factor_sum": (C.c_int32, [h64, i32p, C.c_int32, C.POINTER(h64)]),
     "bn_factor_slice": (C.c_int32, [h64, i32p, i32p, C.c_int32, C.POINTER(h64)]),
     "bn_factor_normalize": (C.c_int32, [h64, C.c_int32]),
+    "bn_factor_norm": (C.c_int32, [h64, C.c_int32, f64p]),
+    "bn_factor_div_scalar": (C.c_int32, [h64, C.c_double]),
     "bn_factor_eliminate": (C.c_int32, [C.POINTER(h64), C.c_int32, i32p, C.c_int32, C.POINTER(h64)]),
     "bn_exact_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_int32, i32p, i32p, f64p]),
     "bn_statistics": (C.c_int32, [h64, u8p, C.c_uint64, i64p]),

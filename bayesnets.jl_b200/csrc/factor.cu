@@ -976,17 +976,11 @@ int32_t bn_factor_slice(bn_factor_t h, const int32_t* dims, const int32_t* state
   return BN_OK;
 }
 
-int32_t bn_factor_normalize(bn_factor_t h, int32_t pnorm) {
-  Factor* f = get_factor(h);
-  BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_normalize: unknown handle");
-  BN_REQUIRE(pnorm == 1 || pnorm == 2, BN_BAD_ARG, "p = %d is not supported", pnorm);  // factors_dims.jl:51
-  BN_REQUIRE(f->data.owns, BN_BAD_ARG, "bn_factor_normalize: the factor is a read-only view");
-  BN_CUDA_TRY(cudaSetDevice(f->device));
-  const DevProps& dp = dev_props(f->device);
+// norm pass shared by normalize! and the split-factor entry points: total (device) = sum |x|^p, deterministic
+static int32_t norm_total(Factor* f, int32_t pnorm, double** total_dev, int* grid_out) {
   const long long grid_ll = std::max<long long>(1, (f->len / 2 + NORM_CHUNK - 1) / NORM_CHUNK);
   BN_REQUIRE(grid_ll < (1ll << 31), BN_UNSUPPORTED, "factor too large to normalise");
   const int grid = (int)grid_ll;
-  (void)dp;
   static thread_local DevBuf<double> scratch;      // [total | grid partials]
   static thread_local DevBuf<unsigned int> ticket;
   static thread_local int scratch_dev = -1;
@@ -997,10 +991,54 @@ int32_t bn_factor_normalize(bn_factor_t h, int32_t pnorm) {
     BN_CUDA_TRY(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), tl_stream));
     scratch_dev = f->device;
   }
-  double* total = scratch.p;
-  norm_reduce_kernel<<<grid, NORM_THR, 0, tl_stream>>>(f->data.p, f->len, pnorm, scratch.p + 1, ticket.p, total);
-  count_launch();
+  if (pnorm) {
+    norm_reduce_kernel<<<grid, NORM_THR, 0, tl_stream>>>(f->data.p, f->len, pnorm, scratch.p + 1, ticket.p, scratch.p);
+    count_launch();
+  }
+  *total_dev = scratch.p;
+  *grid_out = grid;
+  return BN_OK;
+}
+
+int32_t bn_factor_normalize(bn_factor_t h, int32_t pnorm) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_normalize: unknown handle");
+  BN_REQUIRE(pnorm == 1 || pnorm == 2, BN_BAD_ARG, "p = %d is not supported", pnorm);  // factors_dims.jl:51
+  BN_REQUIRE(f->data.owns, BN_BAD_ARG, "bn_factor_normalize: the factor is a read-only view");
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  double* total = nullptr;
+  int grid = 0;
+  BN_TRY(norm_total(f, pnorm, &total, &grid));
   norm_scale_kernel<<<grid, NORM_THR, 0, tl_stream>>>(f->data.p, f->len, total);
+  count_launch();
+  BN_CUDA_TRY(cudaGetLastError());
+  return BN_OK;
+}
+
+int32_t bn_factor_norm(bn_factor_t h, int32_t pnorm, double* out_total) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out_total, BN_BAD_ARG, "bn_factor_norm: bad arguments");
+  BN_REQUIRE(pnorm == 1 || pnorm == 2, BN_BAD_ARG, "p = %d is not supported", pnorm);
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  double* total = nullptr;
+  int grid = 0;
+  BN_TRY(norm_total(f, pnorm, &total, &grid));
+  BN_CUDA_TRY(cudaMemcpyAsync(out_total, total, sizeof(double), cudaMemcpyDeviceToHost, tl_stream));
+  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_factor_div_scalar(bn_factor_t h, double total) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f, BN_BAD_ARG, "bn_factor_div_scalar: unknown handle");
+  BN_REQUIRE(f->data.owns, BN_BAD_ARG, "bn_factor_div_scalar: the factor is a read-only view");
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  double* tdev = nullptr;
+  int grid = 0;
+  BN_TRY(norm_total(f, 0, &tdev, &grid));  // scratch only, no reduction
+  BN_CUDA_TRY(cudaMemcpyAsync(tdev, &total, sizeof(double), cudaMemcpyHostToDevice, tl_stream));
+  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));  // `total` lives on this stack frame
+  norm_scale_kernel<<<grid, NORM_THR, 0, tl_stream>>>(f->data.p, f->len, tdev);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   return BN_OK;

@@ -173,6 +173,11 @@ int32_t bn_factor_slice(bn_factor_t f, const int32_t* dims, const int32_t* state
                         bn_factor_t* out);
 /* normalize!(phi; p): src/Factors/factors_dims.jl:45-57 (p in {1,2}; p=2 divides by sum(abs2)). */
 int32_t bn_factor_normalize(bn_factor_t f, int32_t p);
+/* The two halves of normalize!, for a factor that is split over several GPUs (bayesnets.jl_b200/sharded_factors.py):
+ * bn_factor_norm returns sum(abs, phi) (p = 1) or sum(abs2, phi) (p = 2) of the local part, the caller adds the parts
+ * up (one scalar all-reduce) and bn_factor_div_scalar applies phi ./= total, the division normalize! performs. */
+int32_t bn_factor_norm(bn_factor_t f, int32_t p, double* out_total);
+int32_t bn_factor_div_scalar(bn_factor_t f, double total);
 /* sum(reduce(*, factors), var) in ONE pass (the elimination step of src/Inference/exact.jl:27):
  * multiplies left to right like the reference's fold, never materialising the product.
  * n_sum = 0 gives the plain n-ary product. */

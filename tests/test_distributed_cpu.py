@@ -87,3 +87,107 @@ def test_two_rank_gloo_allreduce_equals_single_stream():
     assert lw2[-2] == pytest.approx(sw, rel=1e-12) and lw2[-1] == pytest.approx(sw2, rel=1e-12)
     gc, _ = capi.gibbs_infer(on, ev, qi, 64, 300, 100, 3, seed=4)
     assert np.array_equal(g2, gc.astype(np.float64).ravel(order="F"))
+
+
+# ------------------------------------------------------------------------------------------ split factors (8e)
+def _np_backend():
+    """The numpy oracle's factors behind ShardedFactor's backend interface (CPU, gloo)."""
+    import torch
+    import torch.distributed as dist
+    from bayesnets_jl_b200.sharded_factors import FactorBackend
+
+    class NpBackend(FactorBackend):
+        def slice(self, f, assignment):
+            return f.slice(assignment)
+
+        def allreduce_sum(self, f):
+            t = torch.from_numpy(f.potential) if f.potential.ndim else torch.from_numpy(f.potential.reshape(1))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return f
+
+        def norm(self, f, p):
+            return float(np.abs(f.potential).sum() if p == 1 else (f.potential ** 2).sum())
+
+        def div_scalar(self, f, total):
+            f.potential /= total
+            return f
+    return NpBackend()
+
+
+def _split_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+        from bayesnets_jl_b200.sharded_factors import ShardedFactor
+        from oracle.factors_np import NpFactor
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        be = _np_backend()
+        rng = np.random.default_rng(3)  # same operands on every rank
+        cards = {"a": 3, "b": 2, "c": 4, "d": 2, "e": 3, "z": 2, "y": 2}
+        A = NpFactor(["a", "b", "c", "d", "y", "z"], rng.random([cards[k] for k in "abcdyz"]))
+        B = NpFactor(["c", "z", "e"], rng.random([4, 2, 3]))        # mentions the split variable z
+        Cc = NpFactor(["b", "a"], rng.random([2, 3]))                # does not
+        D = NpFactor(["d", "y", "z", "a"], rng.random([2, 2, 2, 3]))  # split alike below
+        split = ["y", "z"] if world == 4 else ["z"]
+        sa = ShardedFactor.from_replicated(A, split, rank, world, be)
+        sd = ShardedFactor.from_replicated(D, split, rank, world, be)
+        prod = (sa * B) * Cc * sd                                     # local everywhere
+        part = prod.sum(["c", "a"])                                   # local
+        fused = sa.eliminate([B, Cc, sd], ["c"])                      # local, one pass
+        total = part.sum(split)                                       # THE exchange step: all-reduce
+        norm = (sa * B).normalize_()
+        out = {"prod": prod.gather(), "prod_dims": prod.dimensions, "part": part.gather(), "part_dims": part.dimensions,
+               "fused": fused.gather(), "fused_dims": fused.dimensions, "total": total.potential.copy(),
+               "total_dims": list(total.dimensions), "norm": norm.gather(), "norm_dims": norm.dimensions}
+        if rank == 0:
+            q.put(out)
+        dist.destroy_process_group()
+    except Exception as e:
+        if rank == 0:
+            q.put(e)
+        raise
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_split_factor_algebra_equals_single_process(world):
+    """A factor split over 2 / 4 ranks along its outermost variables: local products (replicated operands sliced at
+    the rank's state, operands split alike), local sums, the fused eliminate, the all-reduce sum over the split
+    variables and the two-step normalise all equal the unsplit computation (products exactly, sums to 1e-12)."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from oracle.factors_np import NpFactor
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if isinstance(got, Exception):
+        raise got
+    rng = np.random.default_rng(3)
+    cards = {"a": 3, "b": 2, "c": 4, "d": 2, "e": 3, "z": 2, "y": 2}
+    A = NpFactor(["a", "b", "c", "d", "y", "z"], rng.random([cards[k] for k in "abcdyz"]))
+    B = NpFactor(["c", "z", "e"], rng.random([4, 2, 3]))
+    Cc = NpFactor(["b", "a"], rng.random([2, 3]))
+    D = NpFactor(["d", "y", "z", "a"], rng.random([2, 2, 2, 3]))
+    split = ["y", "z"] if world == 4 else ["z"]
+
+    def same(arr, dims, ref, exact):
+        perm = [ref.dimensions.index(d) for d in dims]
+        want = np.transpose(ref.potential, perm)
+        if exact:
+            assert np.array_equal(arr, want)
+        else:
+            np.testing.assert_allclose(arr, want, rtol=1e-12)
+    prod = ((A * B) * Cc) * D
+    same(got["prod"], got["prod_dims"], prod, True)
+    same(got["part"], got["part_dims"], prod.sum(["c", "a"]), False)
+    same(got["fused"], got["fused_dims"], prod.sum(["c"]), False)
+    same(got["total"], got["total_dims"], prod.sum(["c", "a"] + split), False)
+    nrm = A * B
+    same(got["norm"], got["norm_dims"], NpFactor(nrm.dimensions, nrm.potential / np.abs(nrm.potential).sum()), False)
