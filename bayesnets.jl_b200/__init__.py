@@ -17,7 +17,7 @@ from .bayes_net import (Assignment, BayesNet, CategoricalCPD, DiscreteBayesNet, 
 from .device_layout import DeviceLayout, DeviceNet, device_net, flatten, set_default_device  # noqa: F401
 from .factors import Factor, eliminate  # noqa: F401
 from .inference import (ExactInference, GibbsSamplingFull, GibbsSamplingNodewise, InferenceMethod,  # noqa: F401
-                        InferenceState, LikelihoodWeightingInference, infer)
+                        InferenceState, LikelihoodWeightingInference, LoopyBelief, infer)
 from .io import read_text, readxdsl, write_text  # noqa: F401
 from .learning import (BDeuPrior, DirichletPrior, UniformPrior, bayesian_score, bayesian_score_component,  # noqa: F401
                        bayesian_score_components, fit, fit_from_device_table, statistics, statistics_device)

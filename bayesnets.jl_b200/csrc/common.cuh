@@ -127,9 +127,12 @@ using TmpBuf = PoolBuf<T>;
 struct SpecKernel;  // specialize.cu: one NVRTC-compiled LW kernel per (evidence mask, query)
 struct Net;
 void spec_cache_clear(Net* net);
+struct LoopyPlan;  // loopy.cu: message layout + task list of the LoopyBelief kernel (depends on the structure only)
+void loopy_plan_free(LoopyPlan* p);
 
 struct Net {
-  ~Net() { spec_cache_clear(this); }
+  ~Net() { spec_cache_clear(this); loopy_plan_free(loopy); }
+  LoopyPlan* loopy = nullptr;
   std::unordered_map<std::string, SpecKernel*> spec_cache;
   std::unordered_map<std::string, double> spec_demand;  // work requested per key before its kernel was compiled
   int device = 0;

@@ -1,7 +1,7 @@
-"""infer(im, bn, query; evidence) for the three offloaded InferenceMethods.
+"""infer(im, bn, query; evidence) for the offloaded InferenceMethods.
 
 Mirrors src/ProbabilisticGraphicalModels/inference.jl:4-49 (InferenceState, generic infer entry) and the
-`infer` methods of src/Inference/{likelihood,gibbs,exact}.jl.  Each method flattens nothing itself: the
+`infer` methods of src/Inference/{likelihood,gibbs,exact,loopy_belief}.jl.  Each method flattens nothing itself: the
 network is uploaded once (device_layout.device_net) and the inner loop is one C-ABI call.
 
 Extra fields the reference does not have: `seed` (counter-based Philox key; the reference uses Julia's
@@ -175,6 +175,56 @@ class ExactInference(InferenceMethod):
         # the result's dim order is join-order dependent, as in the reference (compare by name)
         dims = [lay.names[int(i)] for i in od]
         return Factor(dims, out.reshape([int(c) for c in oc], order="F"), device=net.device)
+
+
+@dataclass
+class LoopyBelief(InferenceMethod):
+    """src/Inference/loopy_belief.jl:7-11: nsamples = iteration cap, early stop once the largest message change
+    stayed <= tol for iters_for_convergence iterations (tol < 0: never).  `last_iters` = iterations of the last call.
+
+    Same numbers as the reference, including the effect of its message aliasing (csrc/loopy.cu header): exact on the
+    reference's own test nets, not textbook LBP when an unobserved root has several children."""
+    nsamples: int = 500
+    tol: float = 1e-8
+    iters_for_convergence: int = 6
+    device: Optional[int] = None
+    last_iters: Optional[np.ndarray] = field(default=None, repr=False, compare=False)
+
+    def infer(self, inf: InferenceState) -> Factor:
+        if len(inf.query) != 1:  # loopy_belief.jl:26
+            raise ValueError("There can only be one query variable")
+        post = self.infer_batch(inf.pgm, [inf.query[0]], [inf.evidence])
+        net = device_net(inf.pgm, self.device)
+        return Factor(inf.query, post[0, :inf.pgm.ncategories(inf.query[0])], device=net.device)
+
+    def infer_batch(self, bn, queries, evidences) -> np.ndarray:
+        """Many (query, evidence) pairs of one network in ONE kernel launch (one warp per pair).  queries: node names;
+        evidences: Assignments (1-based states) or None.  Returns [n_pairs, max_card] posteriors, rows zero-padded."""
+        net = device_net(bn, self.device)
+        lay = net.layout
+        queries = list(queries)
+        evidences = list(evidences) if evidences is not None else [None] * len(queries)
+        if len(evidences) != len(queries):
+            raise ValueError("one evidence Assignment per query")
+        infs = [InferenceState(bn, q, e) for q, e in zip(queries, evidences)]
+        for i in infs:
+            if len(i.query) != 1:
+                raise ValueError("There can only be one query variable")
+        B = len(infs)
+        ev = np.empty((B, lay.n), np.int8)
+        for b, i in enumerate(infs):
+            ev[b] = lay.evidence_vector(i.evidence)
+        q = np.array([lay.index[i.query[0]] for i in infs], np.int32)
+        stride = int(lay.card.max())
+        out = np.zeros((B, stride), np.float64)
+        iters = np.zeros(B, np.int32)
+        if B:
+            check(_lib.lib().bn_loopy_infer(_lib.h64(net.handle), ptr(ev, _lib.i8p), ptr(q, _lib.i32p), C.c_uint64(B),
+                                            C.c_int32(self.nsamples), C.c_double(self.tol),
+                                            C.c_int32(self.iters_for_convergence), C.c_int32(stride),
+                                            ptr(out, _lib.f64p), ptr(iters, _lib.i32p)))
+        self.last_iters = iters
+        return out
 
 
 def infer(*args, evidence: Optional[dict] = None) -> Factor:

@@ -204,6 +204,22 @@ int32_t bn_statistics(bn_net_t net, const uint8_t* states, uint64_t n_rows, int6
 int32_t bn_statistics_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_rows, uint64_t pitch,
                           int64_t* out_counts_dev);
 
+/* ---- infer(::LoopyBelief, ::InferenceState): src/Inference/loopy_belief.jl:24-218 -------------------------
+ * Loopy belief propagation, batched: instance b has evidence row evidence[b * n_nodes .. ] (NULL = no evidence
+ * anywhere) and ONE query node query[b] (:26); all instances run concurrently, one warp each, messages in shared
+ * memory.  nsamples = iteration cap, tol / iters_for_convergence = the reference's early stop (:196; tol < 0 never
+ * stops).  out[b * out_stride + s] = P(query[b] = s | evidence_b), s < card(query[b]) (rest zero-filled);
+ * out_iters[b] (may be NULL) = iterations run.  Reproduces the reference's message aliasing (csrc/loopy.cu header),
+ * i.e. the same numbers as the reference, which on nets whose roots have several children are not textbook LBP.
+ * bn_loopy_infer validates like InferenceState (query in the net and not in the evidence -> BN_BAD_ARG; state out
+ * of range -> BN_BOUNDS); the _dev variant takes device pointers, trusts them (out-of-range evidence = free,
+ * bad query -> NaN row) and enqueues on the current stream. */
+int32_t bn_loopy_infer(bn_net_t net, const int8_t* evidence, const int32_t* query, uint64_t n_inst, int32_t nsamples,
+                       double tol, int32_t iters_for_convergence, int32_t out_stride, double* out, int32_t* out_iters);
+int32_t bn_loopy_infer_dev(bn_net_t net, const int8_t* evidence_dev, const int32_t* query_dev, uint64_t n_inst,
+                           int32_t nsamples, double tol, int32_t iters_for_convergence, int32_t out_stride,
+                           double* out_dev, int32_t* out_iters_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -336,3 +336,43 @@ def test_statistics_and_bayesian_scores_match_reference_tests(golden):
     c = capi.statistics(net, padded, n_rows=12, pitch=16)
     keep = np.delete(data, 5, axis=1)
     assert np.array_equal(c, capi.statistics(net, keep))
+
+
+# ------------------------------------------------------------------------------------- LoopyBelief
+def test_loopy_oracle_reference_posteriors(golden):
+    """test/test_inference.jl:45-63,94-110 with im = LoopyBelief(): the four posteriors the reference pins for it
+    (atol 0.02 / 0.05 there; the restatement lands on them to 1e-12 because both nets are polytrees whose
+    unobserved roots have at most uniform lambdas coming back)."""
+    from oracle.loopy_np import loopy_infer
+    g = golden["inference_acb"]
+    net = net_from(g["nodes"])
+    np.testing.assert_allclose(loopy_infer(net, net.index["a"]), g["P_a"], atol=1e-12)
+    np.testing.assert_allclose(loopy_infer(net, net.index["c"]), g["P_c"], atol=1e-12)
+    s = golden["inference_student"]
+    net = net_from(s["nodes"])
+    np.testing.assert_allclose(loopy_infer(net, net.index["D"]), s["P_D"], rtol=1e-12)
+    ev = np.array([0, 0, -1, -1, -1], np.int8)
+    np.testing.assert_allclose(loopy_infer(net, net.index["G"], ev), s["P_G_given_d1_i1"], rtol=1e-12)
+    # without evidence belief propagation is exact on a polytree: every marginal of the Student net
+    for name in net.names:
+        np.testing.assert_allclose(loopy_infer(net, net.index[name]), exact_infer(net, name).potential, rtol=1e-12)
+
+
+def test_loopy_oracle_stopping_rule_and_aliasing(golden):
+    """Early stop needs iters_for_convergence quiet iterations (loopy_belief.jl:94-96,192-198); tol < 0 never stops;
+    the in-place update of a root's prior (:125,:170-175) is visible once evidence sits below a root with two
+    children: the reference's answer is NOT the exact posterior there, and the oracle reproduces that."""
+    from oracle.loopy_np import loopy_infer
+    net = net_from(golden["inference_student"]["nodes"])
+    _, it = loopy_infer(net, 0, return_iters=True)
+    assert 6 <= it < 20
+    _, it = loopy_infer(net, 0, iters_for_convergence=1, return_iters=True)
+    assert it < 8
+    _, it = loopy_infer(net, 0, nsamples=37, tol=-1.0, return_iters=True)
+    assert it == 37
+    out0 = loopy_infer(net, 1, nsamples=0)                       # no iteration: prior x uniform lambdas
+    np.testing.assert_allclose(out0, [0.7, 0.3], rtol=1e-15)
+    ev = np.array([-1, -1, -1, 0, 1], np.int8)                   # L = 1, S = 2 (1-based)
+    lbp = loopy_infer(net, net.index["I"], ev)
+    exact = exact_infer(net, "I", {"L": 0, "S": 1}).potential
+    assert abs(lbp[0] - exact[0]) > 0.05 and lbp[0] < 1e-12      # the root's prior was multiplied in every iteration
