@@ -29,14 +29,19 @@
 namespace bn {
 
 struct LoopyPlan {
-  std::vector<uint32_t> words;  // [nodes | edges | child edges | tasks A | tasks B by lane | lane ptr | digit rows]
+  std::vector<uint32_t> words;  // [nodes | edges | child edges | tasks A | tasks P | task records B by lane | lane ptr | digit rows]
   uint32_t off_node = 0, off_edge = 0, off_child = 0, off_taskA = 0, off_taskB = 0, off_taskP = 0, off_lane = 0, off_dig = 0;
-  uint32_t nA = 0, nB = 0, nP = 0, n_edges = 0, S_c = 0, S_l = 0, max_card = 0;
+  uint32_t nA = 0, nB = 0, nP = 0, n_edges = 0, S_c = 0, S_l = 0, S_pp = 0, max_card = 0;
   DevBuf<uint32_t> dev;
 };
 void loopy_plan_free(LoopyPlan* p) { delete p; }
 
-enum : uint32_t { NODE_WORDS = 12, EDGE_WORDS = 8, TASK_LAMBDA = 0x80000000u };
+enum : uint32_t { NODE_WORDS = 12, EDGE_WORDS = 8, TASK_WORDS = 12, NO_PP = 0xffffffffu };
+// phase-B task record (TASK_WORDS words): everything the flat loop needs, so a lane switches task with three
+// 128-bit loads.  w0 cpt offset | w1 c + k<<8 + pc<<16 + flags<<24 | w2 stride | w3 n_hi (lambda) / node (pi) |
+// w4 digit-row offset | w5 destination offset | w6 offset of the node's lambda_i / pi | w7 digit mask |
+// w8..w11 pi-plane offsets of parents 0..3 (the ONE slot for absent / skipped parents); k > 4: w8 = first edge, w9 = j
+enum : uint32_t { TF_LAMBDA = 1u << 24, TF_SLOW = 2u << 24 };
 
 struct LoopyArgs {
   const uint32_t* plan;
@@ -48,7 +53,7 @@ struct LoopyArgs {
   unsigned long long n_inst;
   double tol, delta, eps_delta;
   uint32_t plan_words, cpt_len;
-  uint32_t n_nodes, n_edges, S_c, S_l;
+  uint32_t n_nodes, n_edges, S_c, S_l, S_pp;
   uint32_t off_node, off_edge, off_child, off_taskA, off_taskB, off_taskP, off_lane, off_dig, nA, nB, nP;
   uint32_t shared_bytes, per_warp_bytes, out_stride;
   int32_t nsamples, K;
@@ -94,6 +99,7 @@ struct LoopyCtx {
   double* Rp;
   const double* LAMr;
   double* LAMw;
+  const double* PP;
   double delta, eps_delta;
   int32_t t;
 };
@@ -111,14 +117,9 @@ __device__ __forceinline__ double pi_messages(const LoopyCtx g, uint32_t i, doub
     for (uint32_t x = 0; x < c; ++x) {
       double v = px[x];
       if (m > 1) {  // px .*= reduce(.*, lambdas of the other children)
-        double p = 0.0;
-        bool first = true;
-        for (uint32_t k2 = 0; k2 < m; ++k2) {
-          if (k2 == kk) continue;
-          const double l = g.LAMr[g.edges[ce[k2] * EDGE_WORDS + 1] + x];
-          p = first ? l : p * l;
-          first = false;
-        }
+        double p;
+        if (m == 2) p = g.LAMr[g.edges[ce[kk ^ 1u] * EDGE_WORDS + 1] + x];
+        else p = g.PP[g.edges[ce[kk] * EDGE_WORDS + 7] + x];  // folded in phase A
         v = v * p;
         px[x] = v;
       }
@@ -182,7 +183,7 @@ __device__ __forceinline__ double lambda_finish(const LoopyCtx g, uint32_t loff,
 }
 
 template <bool CPT_SMEM>
-__global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
+__global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* plan = reinterpret_cast<uint32_t*>(smem_raw);
   for (uint32_t i = threadIdx.x; i < a.plan_words; i += blockDim.x) plan[i] = a.plan[i];
@@ -194,21 +195,25 @@ __global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
   const uint32_t* nodes = plan + a.off_node;
   const uint32_t* edges = plan + a.off_edge;
   const uint32_t* taskA = plan + a.off_taskA;
-  const uint32_t* taskB = plan + a.off_taskB;
+  const uint4* taskB = reinterpret_cast<const uint4*>(plan + a.off_taskB);
   const uint32_t* taskP = plan + a.off_taskP;
   const uint32_t* dig = plan + a.off_dig;
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   unsigned char* mine = smem_raw + a.shared_bytes + (size_t)warp * a.per_warp_bytes;
-  double* PI0 = reinterpret_cast<double*>(mine);  // planes: PI[0], PI[1], R, LAMN, LAM[0], LAM[1]
-  double* LAMN = PI0 + 3 * a.S_c;                 // lambda_i[x] of the current iteration
-  double* LAM0 = PI0 + 4 * a.S_c;
+  // planes: PI[0], PI[1] (S_c + 1 each, the last entry is the constant 1.0), R, LAMN, PP, LAM[0], LAM[1]
+  const uint32_t P1 = a.S_c + 1u;
+  double* PI0 = reinterpret_cast<double*>(mine);
+  double* LAMN = PI0 + 2 * P1 + a.S_c;  // lambda_i[x] of the current iteration
+  double* PPw = LAMN + a.S_c;           // products of the sibling lambdas (nodes with more than two children)
+  double* LAM0 = PPw + a.S_pp;
   int8_t* ev = reinterpret_cast<int8_t*>(LAM0 + 2 * a.S_l);
   LoopyCtx g;
   g.nodes = nodes;
   g.edges = edges;
   g.childe = plan + a.off_child;
-  g.Rp = PI0 + 2 * a.S_c;
+  g.Rp = PI0 + 2 * P1;
+  g.PP = PPw;
   g.delta = a.delta;
   g.eps_delta = a.eps_delta;
   // this lane's share of the phase-B tasks (packed by the host so that every lane carries the same load)
@@ -228,10 +233,11 @@ __global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
       for (uint32_t x = 0; x < c; ++x) {
         const double v = e >= 0 ? ((int)x == e ? 1.0 : 0.0) : u;
         PI0[poff + x] = v;
-        PI0[a.S_c + poff + x] = v;
+        PI0[P1 + poff + x] = v;
         g.Rp[poff + x] = nd[2] == 0 ? (CPT_SMEM ? cpt[nd[1] + x] : __ldg(cpt + nd[1] + x)) : 0.0;
       }
     }
+    if (lane == 0) PI0[a.S_c] = PI0[P1 + a.S_c] = 1.0;
     for (uint32_t e = lane; e < a.n_edges; e += 32) {
       const uint32_t* ed = edges + e * EDGE_WORDS;
       const double u = 1.0 / (double)ed[3];
@@ -247,18 +253,17 @@ __global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
     for (int32_t t = 1; t <= a.nsamples; ++t) {
       iters = t;
       g.t = t;
-      g.PIr = PI0 + ((t - 1) & 1) * a.S_c;
-      g.PIw = PI0 + (t & 1) * a.S_c;
+      g.PIr = PI0 + ((t - 1) & 1) * P1;
+      g.PIw = PI0 + (t & 1) * P1;
       g.LAMr = LAM0 + ((t - 1) & 1) * a.S_l;
       g.LAMw = LAM0 + (t & 1) * a.S_l;
       double mc = -INFINITY;
 
-      // ---- phase A: unobserved roots update their persistent priors in place (aliases (1) and (3)); and every node
-      // with parents folds the lambdas of its children (or its evidence) into lambda_i[x] once (:114-121)
-      for (uint32_t ti = lane; ti < a.nA; ti += 32) {
-        const uint32_t i = taskA[ti];
-        if (ev[i] < 0) mc = pi_messages(g, i, mc);
-      }
+      // ---- phase A, everything that only reads last iteration's lambdas:
+      //  * every node with parents folds its children's lambdas (or its evidence) into lambda_i[x] (:114-121);
+      //  * for nodes with more than two children, the product of the OTHER children's lambdas that each child's pi
+      //    message needs (:172-173), one lane per child instead of one lane per node in phase C;
+      //  * then unobserved roots update their persistent priors in place (aliases (1) and (3))
       for (uint32_t i = lane; i < a.n_nodes; i += 32) {
         const uint32_t* nd = nodes + i * NODE_WORDS;
         if (nd[2] == 0) continue;
@@ -276,54 +281,91 @@ __global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
           LAMN[poff + x] = lam;
         }
       }
+      for (uint32_t e = lane; e < a.n_edges; e += 32) {
+        const uint32_t* ed = edges + e * EDGE_WORDS;
+        if (ed[7] == NO_PP) continue;
+        const uint32_t* nd = nodes + ed[0] * NODE_WORDS;  // the parent whose children are being multiplied
+        if (ev[ed[0]] >= 0) continue;
+        const uint32_t m = nd[4];
+        const uint32_t* ce = g.childe + nd[5];
+        for (uint32_t x = 0; x < ed[3]; ++x) {
+          double p = 0.0;
+          bool first = true;
+          for (uint32_t k2 = 0; k2 < m; ++k2) {
+            const uint32_t e2 = ce[k2];
+            if (e2 == e) continue;
+            const double l = g.LAMr[edges[e2 * EDGE_WORDS + 1] + x];
+            p = first ? l : p * l;
+            first = false;
+          }
+          PPw[ed[7] + x] = p;
+        }
+      }
+      __syncwarp();
+      for (uint32_t ti = lane; ti < a.nA; ti += 32) {
+        const uint32_t i = taskA[ti];
+        if (ev[i] < 0) mc = pi_messages(g, i, mc);
+      }
       __syncwarp();
 
       // ---- phase B: the sums over parent configurations.  Every lane walks its own task list one CPT cell per trip
       // of one flat loop, so the warp's time is the largest per-lane sum of cells, not a product of the largest loop
-      // bounds of 32 differently shaped tasks.
+      // bounds of 32 differently shaped tasks.  Up to four parents the cell is straight-line code: one digit word,
+      // four independent message loads (absent or skipped parents read the constant 1.0), four multiplies.
       uint32_t tp = my_begin;
       bool active = false;
-      uint32_t is_lambda = 0, c = 0, k = 0, kw = 0, j = 0, stride = 1, pc = 1, n_hi = 1;
-      uint32_t lo = 0, hi = 0, x = 0, u = 0;
+      uint32_t flags = 0, c = 0, pc = 1, stride = 1, n_hi = 1, jump = 0, wmask = 0, po0 = 0, po1 = 0, po2 = 0, po3 = 0;
+      uint32_t lo = 0, hi = 0, x = 0, u = 0, q = 0;
       const double* cp = cpt;
-      const uint32_t* ed0 = edges;
       const uint32_t* dg = dig;
       const double* lamn = LAMN;
       double* dst = g.PIw;
       double acc = 0.0, msg = 0.0;
       while (true) {
         while (!active && tp < my_end) {
-          const uint32_t task = taskB[tp++];
-          is_lambda = task & TASK_LAMBDA;
-          uint32_t node;
-          if (is_lambda) {
-            const uint32_t* ed = edges + (task & ~TASK_LAMBDA) * EDGE_WORDS;
-            dst = g.LAMw + ed[1]; stride = ed[2]; pc = ed[3]; node = ed[5]; j = ed[6]; n_hi = ed[7];
-          } else {
-            node = task; j = 0xffffffffu; pc = 1; n_hi = 1;
-            if (ev[node] >= 0) continue;  // an evidence node keeps its one-hot message
-          }
-          const uint32_t* nd = nodes + node * NODE_WORDS;
-          c = nd[0]; k = nd[2]; kw = (k + 3u) >> 2;
-          cp = cpt + nd[1];
-          ed0 = edges + nd[3] * EDGE_WORDS;
-          dg = dig + nd[7];
-          lamn = LAMN + nd[6];
-          if (!is_lambda) { stride = nd[8]; dst = g.PIw + nd[6]; }
-          lo = hi = x = u = 0;
+          const uint4 r0 = taskB[tp * 3], r1 = taskB[tp * 3 + 1], r2 = taskB[tp * 3 + 2];
+          ++tp;
+          flags = r0.y;
+          if (!(flags & TF_LAMBDA) && ev[r0.w] >= 0) continue;  // an evidence node keeps its one-hot message
+          c = flags & 0xffu;
+          pc = (flags >> 16) & 0xffu;
+          cp = cpt + r0.x;
+          stride = r0.z;
+          n_hi = (flags & TF_LAMBDA) ? r0.w : 1u;
+          jump = stride * (pc - 1u);
+          dg = dig + r1.x;
+          dst = ((flags & TF_LAMBDA) ? g.LAMw : g.PIw) + r1.y;
+          lamn = LAMN + r1.z;
+          wmask = r1.w;
+          po0 = r2.x; po1 = r2.y; po2 = r2.z; po3 = r2.w;
+          lo = hi = x = u = q = 0;
           active = true;
         }
         if (!__any_sync(0xffffffffu, active)) break;
         if (active) {
-          const uint32_t q = lo + stride * (u + pc * hi);
           double tv = CPT_SMEM ? cp[x + c * q] : __ldg(cp + x + c * q);
-          tv = times_parent_messages(tv, ed0, dg + q * kw, g.PIr, k, j);
+          if (!(flags & TF_SLOW)) {
+            const uint32_t w = dg[q] & wmask;
+            const double f0 = g.PIr[po0 + (w & 0xffu)];
+            const double f1 = g.PIr[po1 + ((w >> 8) & 0xffu)];
+            const double f2 = g.PIr[po2 + ((w >> 16) & 0xffu)];
+            const double f3 = g.PIr[po3 + (w >> 24)];
+            tv = tv * f0;  // x * 1.0 is exact: absent parents leave no trace
+            tv = tv * f1;
+            tv = tv * f2;
+            tv = tv * f3;
+          } else {
+            const uint32_t k = (flags >> 8) & 0xffu;
+            tv = times_parent_messages(tv, edges + po0 * EDGE_WORDS, dg + q * ((k + 3u) >> 2), g.PIr, k, po1);
+          }
           acc = (lo | hi) ? acc + tv : tv;
+          ++q;
           if (++lo == stride) {
             lo = 0;
+            q += jump;
             if (++hi == n_hi) {
               hi = 0;  // cell (x, u) is complete
-              if (is_lambda) {
+              if (flags & TF_LAMBDA) {
                 const double v = acc * lamn[x];  // broadcast!(*, lx, nn, lambda) then sum!(lx, nn)
                 msg = x ? msg + v : v;
                 if (++x == c) {
@@ -335,6 +377,7 @@ __global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
                 dst[x] = acc;
                 active = (++x != c);
               }
+              q = stride * u;
             }
           }
         }
@@ -365,7 +408,7 @@ __global__ void __launch_bounds__(256) loopy_kernel(const LoopyArgs a) {
       if (qn < 0 || (uint32_t)qn >= a.n_nodes || nodes[qn * NODE_WORDS] > a.out_stride) {
         for (uint32_t x = 0; x < a.out_stride; ++x) o[x] = NAN;
       } else {
-        const double* PIr = PI0 + (iters & 1) * a.S_c;
+        const double* PIr = PI0 + (iters & 1) * P1;
         const double* LAMr = LAM0 + (iters & 1) * a.S_l;
         const uint32_t* nd = nodes + (uint32_t)qn * NODE_WORDS;
         const uint32_t c = nd[0], k = nd[2], m = nd[4], poff = nd[6];
@@ -450,7 +493,7 @@ static int32_t loopy_plan(Net* net) {
       ed[4] = pi_off[(size_t)p];
       ed[5] = (uint32_t)i;
       ed[6] = (uint32_t)(e - net->par_ptr[i]);
-      ed[7] = (uint32_t)((net->cpt_off[i + 1] - net->cpt_off[i]) / net->card[i]) / (stride * (uint32_t)net->card[p]);
+      ed[7] = NO_PP;
       stride *= (uint32_t)net->card[p];
     }
   }
@@ -463,45 +506,85 @@ static int32_t loopy_plan(Net* net) {
       for (int e = net->par_ptr[ch]; e < net->par_ptr[ch + 1]; ++e)
         if (net->par_idx[e] == p) w[P->off_child + (size_t)kk] = (uint32_t)e;
     }
-  // tasks.  Phase A (unobserved roots) is dealt round-robin; phase B is packed onto the 32 lanes by
-  // longest-processing-time-first, so every lane walks about the same number of table cells per iteration.
-  std::vector<std::pair<uint64_t, uint32_t>> A, B, Pm;
+  // products of sibling lambdas are tabulated only where a node has more than two children
+  uint64_t S_pp = 0;
+  for (int p = 0; p < n; ++p) {
+    if (net->child_ptr[p + 1] - net->child_ptr[p] <= 2) continue;
+    for (int kk = net->child_ptr[p]; kk < net->child_ptr[p + 1]; ++kk) {
+      w[P->off_edge + (size_t)w[P->off_child + (size_t)kk] * EDGE_WORDS + 7] = (uint32_t)S_pp;
+      S_pp += (uint64_t)net->card[p];
+    }
+  }
+  P->S_pp = (uint32_t)S_pp;
+  // tasks.  Phase A (unobserved roots) and phase C (pi messages) are dealt round-robin, most expensive first; the
+  // phase-B records are packed onto the 32 lanes by longest-processing-time-first, so every lane walks about the same
+  // number of CPT cells per iteration.
+  struct Rec { uint64_t cost; uint32_t w[TASK_WORDS]; };
+  std::vector<std::pair<uint64_t, uint32_t>> A, Pm;
+  std::vector<Rec> B;
   for (int i = 0; i < n; ++i) {
-    const uint64_t c = (uint64_t)net->card[i], k = (uint64_t)(net->par_ptr[i + 1] - net->par_ptr[i]);
+    const uint32_t c = (uint32_t)net->card[i], k = (uint32_t)(net->par_ptr[i + 1] - net->par_ptr[i]);
     const uint64_t m = (uint64_t)(net->child_ptr[i + 1] - net->child_ptr[i]);
     const uint64_t cells = (uint64_t)(net->cpt_off[i + 1] - net->cpt_off[i]);
-    if (m) (k ? B : A).push_back({cells * (k + 4) + 16, (uint32_t)i});
-    if (m && k) Pm.push_back({c * m * (m + 2), (uint32_t)i});  // the children loop, phase C
-    for (int e = net->par_ptr[i]; e < net->par_ptr[i + 1]; ++e) B.push_back({cells * (k + 4) + 16, TASK_LAMBDA | (uint32_t)e});
+    const uint32_t Q = (uint32_t)(cells / c);
+    if (m && !k) A.push_back({c * m * (m + 2), (uint32_t)i});
+    if (m && k) Pm.push_back({c * m * (m + 2), (uint32_t)i});
+    if (!k) continue;
+    for (int jj = -1; jj < (int)k; ++jj) {  // -1: the node's own pi (only if it has children), else the lambda to parent jj
+      if (jj < 0 && !m) continue;
+      Rec r{};
+      r.cost = cells * (k > 4 ? 3 * k : 8) + 24;
+      const uint32_t* ed = jj < 0 ? nullptr : &w[P->off_edge + (size_t)(net->par_ptr[i] + jj) * EDGE_WORDS];
+      const uint32_t pc = ed ? ed[3] : 1u;
+      r.w[0] = (uint32_t)net->cpt_off[i];
+      r.w[1] = c | (k << 8) | (pc << 16) | (ed ? (uint32_t)TF_LAMBDA : 0u) | (k > 4 ? (uint32_t)TF_SLOW : 0u);
+      r.w[2] = ed ? ed[2] : Q;                             // stride of the parent the message goes to
+      r.w[3] = ed ? Q / (ed[2] * pc) : (uint32_t)i;        // n_hi | node (evidence check)
+      r.w[4] = dig_off[(size_t)i];
+      r.w[5] = ed ? ed[1] : pi_off[(size_t)i];
+      r.w[6] = pi_off[(size_t)i];
+      if (k > 4) {
+        r.w[8] = (uint32_t)net->par_ptr[i];
+        r.w[9] = jj < 0 ? 0xffffffffu : (uint32_t)jj;
+      } else {
+        for (uint32_t t = 0; t < 4; ++t) {
+          const bool use = t < k && (int)t != jj;
+          r.w[8 + t] = use ? pi_off[(size_t)net->par_idx[net->par_ptr[i] + (int)t]] : (uint32_t)S_c;  // S_c: the ONE slot
+          if (use) r.w[7] |= 0xffu << (8 * t);
+        }
+      }
+      B.push_back(r);
+    }
   }
   auto by_cost = [](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) {
     return x.first != y.first ? x.first > y.first : x.second < y.second;
   };
   std::sort(A.begin(), A.end(), by_cost);
-  std::sort(B.begin(), B.end(), by_cost);
   std::sort(Pm.begin(), Pm.end(), by_cost);
+  std::stable_sort(B.begin(), B.end(), [](const Rec& x, const Rec& y) { return x.cost > y.cost; });
   P->off_taskA = (uint32_t)w.size();
   for (auto& t : A) w.push_back(t.second);
   P->off_taskP = (uint32_t)w.size();
   for (auto& t : Pm) w.push_back(t.second);
+  P->nA = (uint32_t)A.size();
   P->nP = (uint32_t)Pm.size();
-  std::vector<std::vector<uint32_t>> lanes(32);
+  P->nB = (uint32_t)B.size();
+  std::vector<std::vector<const Rec*>> lanes(32);
   std::vector<uint64_t> load(32, 0);
-  for (auto& t : B) {
+  for (const Rec& r : B) {
     const size_t l = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
-    lanes[l].push_back(t.second);
-    load[l] += t.first;
+    lanes[l].push_back(&r);
+    load[l] += r.cost;
   }
+  while (w.size() % 4) w.push_back(0u);  // records are read as uint4
   P->off_taskB = (uint32_t)w.size();
   std::vector<uint32_t> lane_ptr(33, 0);
   for (int l = 0; l < 32; ++l) {
-    for (uint32_t t : lanes[(size_t)l]) w.push_back(t);
+    for (const Rec* r : lanes[(size_t)l]) w.insert(w.end(), r->w, r->w + TASK_WORDS);
     lane_ptr[(size_t)l + 1] = lane_ptr[(size_t)l] + (uint32_t)lanes[(size_t)l].size();
   }
   P->off_lane = (uint32_t)w.size();
   for (uint32_t v : lane_ptr) w.push_back(v);
-  P->nA = (uint32_t)A.size();
-  P->nB = (uint32_t)B.size();
   // parent-state digits: row q of node i is (k + 3) / 4 words at dig_off[i] + q * kw, byte j = state of parent j
   P->off_dig = (uint32_t)w.size();
   w.resize(w.size() + (size_t)dig_words + 1, 0u);
@@ -560,6 +643,7 @@ static int32_t loopy_launch(Net* net, const int8_t* ev_dev, const int32_t* query
   a.n_edges = P.n_edges;
   a.S_c = P.S_c;
   a.S_l = P.S_l;
+  a.S_pp = P.S_pp;
   a.off_node = P.off_node; a.off_edge = P.off_edge; a.off_child = P.off_child;
   a.off_taskA = P.off_taskA; a.off_taskB = P.off_taskB; a.off_lane = P.off_lane; a.off_dig = P.off_dig;
   a.off_taskP = P.off_taskP;
@@ -571,15 +655,15 @@ static int32_t loopy_launch(Net* net, const int8_t* ev_dev, const int32_t* query
   const size_t budget = (size_t)dp.max_smem_optin - 1024;
   const size_t plan_b = ((size_t)a.plan_words * 4 + 15) & ~(size_t)15;
   const size_t cpt_b = ((size_t)a.cpt_len * 8 + 15) & ~(size_t)15;
-  const size_t per_warp = (((size_t)4 * P.S_c + (size_t)2 * P.S_l) * 8 + (size_t)net->n + 15) & ~(size_t)15;
+  const size_t per_warp = (((size_t)4 * P.S_c + 2 + (size_t)P.S_pp + (size_t)2 * P.S_l) * 8 + (size_t)net->n + 15) & ~(size_t)15;
   BN_REQUIRE(plan_b + per_warp <= budget, BN_UNSUPPORTED,
              "LoopyBelief: network too large for shared-memory messages (%zu B plan + %zu B per instance)", plan_b, per_warp);
   const bool cpt_smem = plan_b + cpt_b + 4 * per_warp <= budget;
   const size_t shared_b = plan_b + (cpt_smem ? cpt_b : 0);
-  // CTA shape: up to 8 warps (80 registers per thread without spills); pick the warp count that keeps the most
+  // CTA shape: up to 10 warps; pick the warp count that keeps the most
   // warps resident per SM (the staged plan + CPTs are paid once per CTA, the message planes once per warp)
   static const int warps_env = getenv("BN_LOOPY_WARPS") ? atoi(getenv("BN_LOOPY_WARPS")) : 0;
-  const int max_warps = (int)std::min<size_t>(8, (budget - shared_b) / per_warp);
+  const int max_warps = (int)std::min<size_t>(10, (budget - shared_b) / per_warp);
   int warps = 1, best = 0;
   for (int w = 1; w <= max_warps; ++w) {
     const size_t sm = shared_b + (size_t)w * per_warp + 1024;
