@@ -31,12 +31,12 @@ namespace bn {
 struct LoopyPlan {
   std::vector<uint32_t> words;  // [nodes | edges | child edges | tasks A | tasks P | task records B by lane | lane ptr | digit rows]
   uint32_t off_node = 0, off_edge = 0, off_child = 0, off_taskA = 0, off_taskB = 0, off_taskP = 0, off_lane = 0, off_dig = 0;
-  uint32_t nA = 0, nB = 0, nP = 0, n_edges = 0, S_c = 0, S_l = 0, S_pp = 0, max_card = 0;
+  uint32_t nA = 0, nB = 0, nP = 0, n_edges = 0, S_c = 0, S_l = 0, S_pp = 0, S_r = 0, max_card = 0;
   DevBuf<uint32_t> dev;
 };
 void loopy_plan_free(LoopyPlan* p) { delete p; }
 
-enum : uint32_t { NODE_WORDS = 12, EDGE_WORDS = 8, TASK_WORDS = 12, NO_PP = 0xffffffffu };
+enum : uint32_t { NODE_WORDS = 12, EDGE_WORDS = 8, TASK_WORDS = 12, NO_PP = 0xffffffffu, PP_MIN_CHILDREN = 5 };
 // phase-B task record (TASK_WORDS words): everything the flat loop needs, so a lane switches task with three
 // 128-bit loads.  w0 cpt offset | w1 c + k<<8 + pc<<16 + flags<<24 | w2 stride | w3 n_hi (lambda) / node (pi) |
 // w4 digit-row offset | w5 destination offset | w6 offset of the node's lambda_i / pi | w7 digit mask |
@@ -53,7 +53,7 @@ struct LoopyArgs {
   unsigned long long n_inst;
   double tol, delta, eps_delta;
   uint32_t plan_words, cpt_len;
-  uint32_t n_nodes, n_edges, S_c, S_l, S_pp;
+  uint32_t n_nodes, n_edges, S_c, S_l, S_pp, S_r;
   uint32_t off_node, off_edge, off_child, off_taskA, off_taskB, off_taskP, off_lane, off_dig, nA, nB, nP;
   uint32_t shared_bytes, per_warp_bytes, out_stride;
   int32_t nsamples, K;
@@ -110,7 +110,7 @@ __device__ __forceinline__ double pi_messages(const LoopyCtx g, uint32_t i, doub
   const uint32_t* nd = g.nodes + i * NODE_WORDS;
   const uint32_t c = nd[0], k = nd[2], m = nd[4], poff = nd[6];
   const bool root = (k == 0);
-  double* px = root ? g.Rp + poff : g.PIw + poff;
+  double* px = root ? g.Rp + nd[9] : g.PIw + poff;
   const uint32_t* ce = g.childe + nd[5];
   for (uint32_t kk = 0; kk < m; ++kk) {
     double nrm = 0.0;
@@ -118,8 +118,13 @@ __device__ __forceinline__ double pi_messages(const LoopyCtx g, uint32_t i, doub
       double v = px[x];
       if (m > 1) {  // px .*= reduce(.*, lambdas of the other children)
         double p;
-        if (m == 2) p = g.LAMr[g.edges[ce[kk ^ 1u] * EDGE_WORDS + 1] + x];
-        else p = g.PP[g.edges[ce[kk] * EDGE_WORDS + 7] + x];  // folded in phase A
+        if (m >= PP_MIN_CHILDREN) p = g.PP[g.edges[ce[kk] * EDGE_WORDS + 7] + x];  // folded in phase A
+        else {
+          const uint32_t first = kk == 0 ? 1u : 0u;
+          p = g.LAMr[g.edges[ce[first] * EDGE_WORDS + 1] + x];
+          for (uint32_t k2 = first + 1; k2 < m; ++k2)
+            if (k2 != kk) p = p * g.LAMr[g.edges[ce[k2] * EDGE_WORDS + 1] + x];
+        }
         v = v * p;
         px[x] = v;
       }
@@ -201,10 +206,10 @@ __global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   unsigned char* mine = smem_raw + a.shared_bytes + (size_t)warp * a.per_warp_bytes;
-  // planes: PI[0], PI[1] (S_c + 1 each, the last entry is the constant 1.0), R, LAMN, PP, LAM[0], LAM[1]
+  // planes: PI[0], PI[1] (S_c + 1 each, the last entry is the constant 1.0), R (roots only), LAMN, PP, LAM[0], LAM[1]
   const uint32_t P1 = a.S_c + 1u;
   double* PI0 = reinterpret_cast<double*>(mine);
-  double* LAMN = PI0 + 2 * P1 + a.S_c;  // lambda_i[x] of the current iteration
+  double* LAMN = PI0 + 2 * P1 + a.S_r;  // lambda_i[x] of the current iteration
   double* PPw = LAMN + a.S_c;           // products of the sibling lambdas (nodes with more than two children)
   double* LAM0 = PPw + a.S_pp;
   int8_t* ev = reinterpret_cast<int8_t*>(LAM0 + 2 * a.S_l);
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
         const double v = e >= 0 ? ((int)x == e ? 1.0 : 0.0) : u;
         PI0[poff + x] = v;
         PI0[P1 + poff + x] = v;
-        g.Rp[poff + x] = nd[2] == 0 ? (CPT_SMEM ? cpt[nd[1] + x] : __ldg(cpt + nd[1] + x)) : 0.0;
+        if (nd[2] == 0) g.Rp[nd[9] + x] = CPT_SMEM ? cpt[nd[1] + x] : __ldg(cpt + nd[1] + x);
       }
     }
     if (lane == 0) PI0[a.S_c] = PI0[P1 + a.S_c] = 1.0;
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
 
       // ---- phase A, everything that only reads last iteration's lambdas:
       //  * every node with parents folds its children's lambdas (or its evidence) into lambda_i[x] (:114-121);
-      //  * for nodes with more than two children, the product of the OTHER children's lambdas that each child's pi
+      //  * for nodes with at least PP_MIN_CHILDREN children, the product of the OTHER children's lambdas that each child's pi
       //    message needs (:172-173), one lane per child instead of one lane per node in phase C;
       //  * then unobserved roots update their persistent priors in place (aliases (1) and (3))
       for (uint32_t i = lane; i < a.n_nodes; i += 32) {
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
             lam = LAMr[edges[ce[0] * EDGE_WORDS + 1] + x];
             for (uint32_t k2 = 1; k2 < m; ++k2) lam = lam * LAMr[edges[ce[k2] * EDGE_WORDS + 1] + x];
           }
-          const double pi = k == 0 ? g.Rp[poff + x]
+          const double pi = k == 0 ? g.Rp[nd[9] + x]
                                    : pi_entry<CPT_SMEM>(cpt + nd[1], edges + nd[3] * EDGE_WORDS, dig + nd[7], PIr, x, c,
                                                         nd[8], k);
           const double v = lam * pi;
@@ -478,6 +483,7 @@ static int32_t loopy_plan(Net* net) {
     nd[6] = pi_off[(size_t)i];
     nd[7] = dig_off[(size_t)i];
     nd[8] = (uint32_t)((net->cpt_off[i + 1] - net->cpt_off[i]) / net->card[i]);
+    if (nd[2] == 0) { nd[9] = P->S_r; P->S_r += nd[0]; }  // persistent prior of a root (plane R)
   }
   P->off_edge = (uint32_t)w.size();
   w.resize(w.size() + (size_t)std::max(n_edges, 1) * EDGE_WORDS, 0u);
@@ -506,10 +512,10 @@ static int32_t loopy_plan(Net* net) {
       for (int e = net->par_ptr[ch]; e < net->par_ptr[ch + 1]; ++e)
         if (net->par_idx[e] == p) w[P->off_child + (size_t)kk] = (uint32_t)e;
     }
-  // products of sibling lambdas are tabulated only where a node has more than two children
+  // products of sibling lambdas are tabulated only where a node has PP_MIN_CHILDREN or more children
   uint64_t S_pp = 0;
   for (int p = 0; p < n; ++p) {
-    if (net->child_ptr[p + 1] - net->child_ptr[p] <= 2) continue;
+    if (net->child_ptr[p + 1] - net->child_ptr[p] < (int)PP_MIN_CHILDREN) continue;
     for (int kk = net->child_ptr[p]; kk < net->child_ptr[p + 1]; ++kk) {
       w[P->off_edge + (size_t)w[P->off_child + (size_t)kk] * EDGE_WORDS + 7] = (uint32_t)S_pp;
       S_pp += (uint64_t)net->card[p];
@@ -644,6 +650,7 @@ static int32_t loopy_launch(Net* net, const int8_t* ev_dev, const int32_t* query
   a.S_c = P.S_c;
   a.S_l = P.S_l;
   a.S_pp = P.S_pp;
+  a.S_r = P.S_r;
   a.off_node = P.off_node; a.off_edge = P.off_edge; a.off_child = P.off_child;
   a.off_taskA = P.off_taskA; a.off_taskB = P.off_taskB; a.off_lane = P.off_lane; a.off_dig = P.off_dig;
   a.off_taskP = P.off_taskP;
@@ -655,7 +662,7 @@ static int32_t loopy_launch(Net* net, const int8_t* ev_dev, const int32_t* query
   const size_t budget = (size_t)dp.max_smem_optin - 1024;
   const size_t plan_b = ((size_t)a.plan_words * 4 + 15) & ~(size_t)15;
   const size_t cpt_b = ((size_t)a.cpt_len * 8 + 15) & ~(size_t)15;
-  const size_t per_warp = (((size_t)4 * P.S_c + 2 + (size_t)P.S_pp + (size_t)2 * P.S_l) * 8 + (size_t)net->n + 15) & ~(size_t)15;
+  const size_t per_warp = (((size_t)3 * P.S_c + 2 + (size_t)P.S_r + (size_t)P.S_pp + (size_t)2 * P.S_l) * 8 + (size_t)net->n + 15) & ~(size_t)15;
   BN_REQUIRE(plan_b + per_warp <= budget, BN_UNSUPPORTED,
              "LoopyBelief: network too large for shared-memory messages (%zu B plan + %zu B per instance)", plan_b, per_warp);
   const bool cpt_smem = plan_b + cpt_b + 4 * per_warp <= budget;

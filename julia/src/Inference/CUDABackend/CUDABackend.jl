@@ -158,6 +158,51 @@ function infer(im::CUDAExact, inf::InferenceState{BN}) where {BN<:DiscreteBayesN
 end
 
 # ------------------------------------------------------------------------------------------------
+# Loopy belief propagation                           replaces src/Inference/loopy_belief.jl:24-218
+@with_kw struct CUDALoopyBelief <: InferenceMethod
+    nsamples::Int = 500
+    tol::Float64 = 1e-8
+    iters_for_convergence::Int = 6
+    device::Int = 0
+end
+
+"""
+    infer_batch(im::CUDALoopyBelief, bn, queries, evidences) -> Matrix{Float64}
+
+Many (query, evidence) pairs of one network in ONE kernel launch (one warp per pair).  Column `b` holds
+P(queries[b] | evidences[b]), zero-padded to the largest cardinality.  Same numbers as `infer(LoopyBelief(), ...)`.
+"""
+function infer_batch(im::CUDALoopyBelief, bn::DiscreteBayesNet, queries::NodeNames, evidences::Vector{<:Assignment})
+    length(queries) == length(evidences) || throw(ArgumentError("one evidence Assignment per query"))
+    net = device_net(bn; device=im.device)
+    lay = net.layout
+    nn, B = length(lay.names), length(queries)
+    ev = Matrix{Int8}(undef, nn, B)                       # instance-major rows, as the C ABI expects
+    q = Vector{Int32}(undef, B)
+    for b in 1:B
+        inf = InferenceState(bn, queries[b], evidences[b])   # ArgumentError if query ∉ bn or ∈ evidence
+        ev[:, b] = evidence_vector(lay, bn, inf.evidence)
+        q[b] = query_indices(bn, inf.query)[1]
+    end
+    stride = Int32(maximum(lay.card))
+    out = zeros(Float64, stride, B)
+    iters = zeros(Int32, B)
+    GC.@preserve ev q out iters begin
+        _bn_check(ccall((:bn_loopy_infer, libbn_cuda), Int32,
+                        (UInt64, Ptr{Int8}, Ptr{Int32}, UInt64, Int32, Float64, Int32, Int32, Ptr{Float64}, Ptr{Int32}),
+                        net.handle, ev, q, B, im.nsamples, im.tol, im.iters_for_convergence, stride, out, iters))
+    end
+    return out
+end
+
+function infer(im::CUDALoopyBelief, inf::InferenceState{BN}) where {BN<:DiscreteBayesNet}
+    length(inf.query) == 1 || throw(ArgumentError("There can only be one query variable"))   # loopy_belief.jl:26
+    query = first(inf.query)
+    out = infer_batch(im, inf.pgm, [query], [inf.evidence])
+    return Factor([query], out[1:ncategories(inf.pgm, query), 1])
+end
+
+# ------------------------------------------------------------------------------------------------
 # Table samplers                                      replaces src/sampling.jl:24-41,52-57,72-93,153-174
 struct CUDADirectSampler <: BayesNetSampler
     seed::UInt64

@@ -243,6 +243,17 @@ def main():
                 "check": f"max rel err vs oracle VE = {err:.2e} (bar 1e-12); fused == unfused: "
                          f"{bool(np.allclose(res[1][1], res[0][1], rtol=1e-12, atol=0))}"})
 
+    # ---- f3 LoopyBelief batched over evidence sets (C2 net; tools/loopy_bench.py holds the case)
+    import loopy_bench
+    n_inst, n_it = (16384, 50) if not a.quick else (1184, 10)
+    lb = loopy_bench.run(bn, torch, n_inst, n_it, n_check=2)
+    out.append({"row": "f3", "api": "infer(LoopyBelief(), bn, query; evidence), batched over (query, evidence) pairs",
+                "cite": "src/Inference/loopy_belief.jl:24-218",
+                "config": f"C2 net, {n_inst} (query, 10 evidence nodes) pairs x {n_it} iterations (tol < 0), one launch, "
+                          "device-resident evidence rows", "unit": "instance-iterations/s",
+                "gpu": lb["instance_iterations_per_s"], "gpu_ms": lb["ms"], "message_updates_per_s": lb["message_updates_per_s"],
+                "cpu": lb["cpu_baseline"], "check": f"beliefs of the first 2 pairs identical to the oracle: {lb['identical_to_oracle']}"})
+
     for r in out:
         cpu = r["cpu"]["value"]
         print(f"{r['row']:4s} {r['api'][:62]:62s} gpu {r['gpu']:.4g} {r['unit']}  cpu {cpu:.4g} ({r['cpu']['cores']} cores)  x{r['gpu'] / cpu:.0f}  | {r['check']}")
