@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libbn_cuda.so")
 
 BN_OK, BN_BAD_ARG, BN_DIM_MISMATCH, BN_NOT_IN_FACTOR, BN_CUDA_ERR = 0, -1, -2, -3, -4
 BN_ZERO_WEIGHT, BN_OOM, BN_UNSUPPORTED, BN_BOUNDS = -5, -6, -7, -8
+OP_MUL, OP_DIV, OP_ADD, OP_SUB, OP_MAX, OP_MIN = range(6)
 
 
 class DimensionMismatch(ValueError):
@@ -69,6 +70,10 @@ _SIGS = {
     "bn_factor_norm": (C.c_int32, [h64, C.c_int32, f64p]),
     "bn_factor_div_scalar": (C.c_int32, [h64, C.c_double]),
     "bn_factor_eliminate": (C.c_int32, [C.POINTER(h64), C.c_int32, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_join": (C.c_int32, [h64, h64, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_reduce": (C.c_int32, [h64, i32p, C.c_int32, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_normalize_dims": (C.c_int32, [h64, i32p, C.c_int32, C.c_int32]),
+    "bn_factor_broadcast": (C.c_int32, [h64, i32p, C.c_int32, f64p, i32p, C.c_int32]),
     "bn_exact_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_int32, i32p, i32p, f64p]),
     "bn_statistics": (C.c_int32, [h64, u8p, C.c_uint64, i64p]),
     "bn_statistics_dev": (C.c_int32, [h64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),

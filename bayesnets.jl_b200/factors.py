@@ -40,6 +40,9 @@ def _as_names(dims) -> list:
     return list(dims)
 
 
+_OPS = {"*": _lib.OP_MUL, "/": _lib.OP_DIV, "+": _lib.OP_ADD, "-": _lib.OP_SUB, "max": _lib.OP_MAX, "min": _lib.OP_MIN}
+
+
 class Factor:
     """Factor(dims, potential) | Factor(dims, lengths, fill_value=0)   (src/Factors/factors_main.jl:18-56)."""
 
@@ -153,11 +156,53 @@ class Factor:
         check(_lib.lib().bn_factor_product(_lib.h64(self.handle), _lib.h64(other.handle), C.byref(h)))
         return Factor._from_handle(h)
 
-    def _unsupported(self, other):
-        raise NotImplementedError("only `*` is offloaded; / + - go through the same join in the reference "
-                                  "(factors_dims.jl:270-272) but are not on the inference path")
+    # -- / + - = join(op, phi1, phi2, :outer) (factors_dims.jl:185-234,270-272) --------------------
+    def _join(self, other: "Factor", op: int) -> "Factor":
+        """NB the reference makes the larger factor phi1 BEFORE applying op (:189-191), so phi1 / phi2 with a smaller
+        phi1 is phi2 ./ phi1 there; reproduced as is."""
+        if not isinstance(other, Factor):
+            return NotImplemented
+        h = _lib.h64(0)
+        check(_lib.lib().bn_factor_join(_lib.h64(self.handle), _lib.h64(other.handle), C.c_int32(op), C.byref(h)))
+        return Factor._from_handle(h)
 
-    __truediv__ = __add__ = __sub__ = _unsupported
+    def __truediv__(self, other):
+        return self._join(other, _lib.OP_DIV)
+
+    def __add__(self, other):
+        return self._join(other, _lib.OP_ADD)
+
+    def __sub__(self, other):
+        return self._join(other, _lib.OP_SUB)
+
+    def join(self, op, other: "Factor", kind: str = "outer") -> "Factor":
+        """join(op, phi1, phi2, kind) with op one of '*', '/', '+', '-' (inner joins are unimplemented in the
+        reference too, factors_dims.jl:236)."""
+        if kind == "inner":
+            raise RuntimeError("Inner joins are (still) umimplemented")
+        if kind != "outer":
+            raise ValueError(f"{kind} is not a supported join type")
+        return self._join(other, _OPS[op])
+
+    # -- reducedim(op, phi, dims) for * max min (factors_dims.jl:60-85,102-107) --------------------
+    def reducedim(self, op, dims) -> "Factor":
+        dims = _as_names(dims)
+        self._check_dims_valid(dims)
+        ids = np.array([var_id(d) for d in dims], np.int32)
+        h = _lib.h64(0)
+        dp = ids if ids.size else np.zeros(1, np.int32)
+        check(_lib.lib().bn_factor_reduce(_lib.h64(self.handle), ptr(dp, _lib.i32p), C.c_int32(ids.size),
+                                          C.c_int32(_OPS[op]), C.byref(h)))
+        return Factor._from_handle(h)
+
+    def prod(self, dims) -> "Factor":
+        return self.reducedim("*", dims)
+
+    def maximum(self, dims) -> "Factor":
+        return self.reducedim("max", dims)
+
+    def minimum(self, dims) -> "Factor":
+        return self.reducedim("min", dims)
 
     # -- sum(phi, dims) = reducedim(+, ...) (factors_dims.jl:60-85,100) -------------------------
     def sum(self, dims) -> "Factor":
@@ -171,11 +216,16 @@ class Factor:
 
     # -- normalize!(phi; p) / normalize(phi; p) (factors_dims.jl:24-57) -------------------------
     def normalize_(self, dims=None, p: int = 1) -> "Factor":
-        if dims is not None:
-            self._check_dims_valid(list(dict.fromkeys(_as_names(dims))))
-            raise NotImplementedError("normalize!(phi, dims) is not on the inference path")
         if p not in (1, 2):
             raise ValueError(f"p = {p} is not supported")
+        if dims is not None:  # normalize!(phi, dims; p): factors_dims.jl:24-43
+            dims = list(dict.fromkeys(_as_names(dims)))
+            self._check_dims_valid(dims)
+            ids = np.array([var_id(d) for d in dims], np.int32)
+            dp = ids if ids.size else np.zeros(1, np.int32)
+            check(_lib.lib().bn_factor_normalize_dims(_lib.h64(self.handle), ptr(dp, _lib.i32p), C.c_int32(ids.size),
+                                                      C.c_int32(p)))
+            return self
         check(_lib.lib().bn_factor_normalize(_lib.h64(self.handle), C.c_int32(p)))
         return self
 
@@ -236,6 +286,34 @@ class Factor:
                     raise DimensionMismatch(f"broadcast value for {d} has length {vec.size}, dimension has {n}")
             out = out * Factor([d], vec)
         return out if out is not self else self.copy()
+
+    def broadcast_(self, op, dims, values) -> "Factor":
+        """broadcast!(op, phi, dims, values) in place (factors_dims.jl:131-165); op one of '*', '/', '+', '-', 'max', 'min'."""
+        if isinstance(dims, (str, bytes)) or not isinstance(dims, Iterable):
+            dims, values = [dims], [values]
+        dims = list(dims)
+        if len(set(dims)) != len(dims):
+            raise ValueError("Dimensions must be unique")
+        self._check_dims_valid(dims)
+        if len(dims) != len(values):
+            raise ValueError("Number of dimensions does not match number of values to broadcast")
+        vecs = [np.atleast_1d(np.asarray(v, np.float64)) for v in values]
+        for d, v in zip(dims, vecs):
+            n = self._shape[self.dimensions.index(d)]
+            if v.ndim != 1 or v.size not in (1, n):
+                raise DimensionMismatch(f"broadcast value for {d} has length {v.size}, dimension has {n}")
+        if not dims:
+            return self
+        ids = np.array([var_id(d) for d in dims], np.int32)
+        lens = np.array([v.size for v in vecs], np.int32)
+        flat = np.ascontiguousarray(np.concatenate(vecs))
+        check(_lib.lib().bn_factor_broadcast(_lib.h64(self.handle), ptr(ids, _lib.i32p), C.c_int32(ids.size),
+                                             ptr(flat, _lib.f64p), ptr(lens, _lib.i32p), C.c_int32(_OPS[op])))
+        return self
+
+    def broadcast(self, op, dims, values) -> "Factor":
+        """broadcast(op, phi, dims, values) = broadcast!(op, deepcopy(phi), ...) (factors_dims.jl:118-119)."""
+        return self.copy().broadcast_(op, dims, values)
 
     # -- pattern (factors_main.jl:174-199): host-side index bookkeeping ---------------------------
     def pattern(self, dims=None) -> np.ndarray:

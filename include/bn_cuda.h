@@ -184,6 +184,22 @@ int32_t bn_factor_div_scalar(bn_factor_t f, double total);
 int32_t bn_factor_eliminate(const bn_factor_t* factors, int32_t n_factors, const int32_t* sum_dims,
                             int32_t n_sum, bn_factor_t* out);
 
+/* ---- the rest of the Factor algebra (src/Factors/factors_dims.jl), not used by variable elimination -------------
+ * bn_factor_join: join(op, phi1, phi2, :outer) for op in * / + - (:185-234,269-272).  As in the reference the LARGER
+ *   factor becomes phi1 before op is applied (:189-191), so / and - are operand-order dependent exactly like there.
+ * bn_factor_reduce: reducedim(op, phi, dims) for op in + * max min (:60-85,100-107), dims dropped; sequential
+ *   accumulation over the reduced dims in column-major order; max / min propagate NaN like Base.max / Base.min.
+ * bn_factor_normalize_dims: normalize!(phi, dims; p) (:24-43): every slice over `dims` is divided by its sum(abs)
+ *   (p = 1) or sum(abs2) (p = 2 -- no square root, as in the reference); empty dims = no-op.
+ * bn_factor_broadcast: broadcast!(op, phi, dims, values) (:131-165) in place.  values = the vectors back to back,
+ *   value_len[j] = 1 (a scalar) or the length of dims[j] (else BN_DIM_MISMATCH); several dims apply left to right. */
+enum { BN_OP_MUL = 0, BN_OP_DIV = 1, BN_OP_ADD = 2, BN_OP_SUB = 3, BN_OP_MAX = 4, BN_OP_MIN = 5 };
+int32_t bn_factor_join(bn_factor_t f1, bn_factor_t f2, int32_t op, bn_factor_t* out);
+int32_t bn_factor_reduce(bn_factor_t f, const int32_t* dims, int32_t n_dims, int32_t op, bn_factor_t* out);
+int32_t bn_factor_normalize_dims(bn_factor_t f, const int32_t* dims, int32_t n_dims, int32_t p);
+int32_t bn_factor_broadcast(bn_factor_t f, const int32_t* dims, int32_t n_dims, const double* values,
+                            const int32_t* value_len, int32_t op);
+
 /* ---- infer(::ExactInference, ::InferenceState): src/Inference/exact.jl:6-33 ---------------------
  * Variable elimination entirely on the device.  out_dims/out_card: n_query entries (the result's dim
  * order is join-order dependent, as in the reference -- compare by name); out: prod(card) doubles.

@@ -61,6 +61,83 @@ class NpFactor:
             new_v = p1.potential * p2.potential.reshape(())
         return NpFactor(new_dims, new_v)
 
+    # -- join(op, phi1, phi2, :outer) for / + -: src/Factors/factors_dims.jl:185-234,270-272.  The swap to "larger
+    # factor first" (:189-191) happens BEFORE op is applied, so / and - depend on the operand sizes, as in the reference.
+    def join(self, op: str, other: "NpFactor") -> "NpFactor":
+        f = {"*": np.multiply, "/": np.divide, "+": np.add, "-": np.subtract}[op]
+        p1, p2 = self, other
+        if len(p1) < len(p2):
+            p1, p2 = p2, p1
+        common = [d for d in p1.dimensions if d in p2.dimensions]
+        if [p1.size[p1.dimensions.index(d)] for d in common] != [p2.size[p2.dimensions.index(d)] for d in common]:
+            raise DimensionMismatch("Common dimensions must have same size")
+        unique2 = [d for d in p2.dimensions if d not in common]
+        new_dims = p1.dimensions + unique2
+        if p2.potential.ndim == 0:
+            with np.errstate(all="ignore"):
+                return NpFactor(new_dims, f(p1.potential, p2.potential.reshape(())))
+        temp = np.transpose(p2.potential, [p2.dimensions.index(d) for d in common + unique2])
+        index = tuple(slice(None) if d in common else None for d in p1.dimensions)
+        temp = temp[index + (slice(None),) * len(unique2)]
+        a = p1.potential.reshape(p1.size + (1,) * len(unique2), order="F")
+        with np.errstate(all="ignore"):
+            return NpFactor(new_dims, f(a, temp))
+
+    # -- reducedim(op, phi, dims) for + * max min: src/Factors/factors_dims.jl:60-85,100-107
+    def reducedim(self, op: str, dims, pre=None) -> "NpFactor":
+        f = {"+": np.add, "*": np.multiply, "max": np.maximum, "min": np.minimum}[op]  # np.maximum propagates NaN like Base.max
+        dims = [dims] if not isinstance(dims, (list, tuple)) else list(dims)
+        for d in dims:
+            if d not in self.dimensions:
+                raise ValueError(f"{d} is not a valid dimension")
+        axes = sorted(self.dimensions.index(d) for d in dims)
+        keep = [d for d in self.dimensions if d not in dims]
+        src = self.potential if pre is None else pre(self.potential)
+        if not axes:
+            return NpFactor(keep, src.copy())
+        moved = np.moveaxis(src, axes, range(len(axes)))
+        flat = moved.reshape((-1,) + moved.shape[len(axes):], order="F")
+        acc = flat[0].copy()
+        for t in range(1, flat.shape[0]):
+            acc = f(acc, flat[t])
+        return NpFactor(keep, acc)
+
+    # -- normalize!(phi, dims; p): src/Factors/factors_dims.jl:24-43 (p = 2 divides by sum(abs2): no square root)
+    def normalize_dims(self, dims, p: int = 1) -> "NpFactor":
+        dims = list(dict.fromkeys([dims] if not isinstance(dims, (list, tuple)) else dims))
+        if p not in (1, 2):
+            raise ValueError(f"p = {p} is not supported")
+        if not dims:
+            return NpFactor(self.dimensions, self.potential.copy())
+        total = self.reducedim("+", dims, pre=np.abs if p == 1 else np.square)
+        index = tuple(None if d in dims else slice(None) for d in self.dimensions)
+        with np.errstate(all="ignore"):
+            return NpFactor(self.dimensions, self.potential / total.potential[index])
+
+    # -- broadcast(op, phi, dims, values): src/Factors/factors_dims.jl:118-165; several values fold left to right
+    def broadcast(self, op: str, dims, values) -> "NpFactor":
+        f = {"*": np.multiply, "/": np.divide, "+": np.add, "-": np.subtract, "max": np.maximum, "min": np.minimum}[op]
+        if not isinstance(dims, (list, tuple)):
+            dims, values = [dims], [values]
+        if len(set(dims)) != len(dims):
+            raise ValueError("Dimensions must be unique")
+        for d in dims:
+            if d not in self.dimensions:
+                raise ValueError(f"{d} is not a valid dimension")
+        if len(dims) != len(values):
+            raise ValueError("Number of dimensions does not match number of values to broadcast")
+        out = self.potential.copy(order="F")
+        for d, v in zip(dims, values):
+            v = np.atleast_1d(np.asarray(v, np.float64))
+            ax = self.dimensions.index(d)
+            if v.size not in (1, self.size[ax]):
+                raise DimensionMismatch(f"broadcast value for {d} has length {v.size}")
+            shape = [1] * out.ndim
+            shape[ax] = v.size
+            with np.errstate(all="ignore"):
+                out = f(out, v.reshape(shape))
+        return NpFactor(self.dimensions, out)
+
     # -- reducedim(+, phi, dims): src/Factors/factors_dims.jl:60-85,100
     def sum(self, dims) -> "NpFactor":
         dims = [dims] if not isinstance(dims, (list, tuple)) else list(dims)

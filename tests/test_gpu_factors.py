@@ -361,3 +361,86 @@ def test_large_streaming_shapes_bit_exact(bn, seed):
         ref = (na * NpFactor(d1, B1) * NpFactor(d2, B2)).sum(h)
         assert got.dimensions == [names[i] for i in ref.dimensions]
         assert np.array_equal(got.potential, ref.potential), h
+
+
+# ------------------------------------------------------------------- the rest of the Factor algebra (csrc/factor_ops.cu)
+def test_broadcast_reference_suite(bn):
+    """test/test_factors.jl:87-105, same assertions."""
+    phi = F(bn, ["X", "Y"], [[1.0, 2], [3, 4], [5, 6]])
+    got = phi.broadcast("*", ["Y", "X"], [[10, 0.1], 100.0]).potential
+    np.testing.assert_allclose(got, [[1000, 20], [3000, 40], [5000, 60]], rtol=1e-15)
+    assert np.array_equal(phi.potential, [[1.0, 2], [3, 4], [5, 6]])  # broadcast copies, broadcast! mutates
+    with pytest.raises(ValueError):
+        phi.broadcast("*", ["X", "Z"], [[10, 1, 0.1], [1, 2, 3]])
+    with pytest.raises(ValueError):
+        phi.broadcast("*", ["Z", "X", "A"], [2, [10, 1, 0.1], [1, 2, 3]])
+    with pytest.raises(bn.DimensionMismatch):
+        phi.broadcast("*", "X", [2016, 58.0])
+    p3 = F(bn, ["X", "Y", "Z"], np.array([1.0, 2, 3, 2, 3, 4, 4, 6, 7, 8, 10, 16]).reshape((3, 2, 2), order="F"))
+    two = p3.broadcast("+", "Z", [10, 0.1]).broadcast("+", "X", 10.0)
+    one = p3.broadcast("+", ["X", "Z"], [10.0, [10, 0.1]])
+    assert np.array_equal(two.potential, one.potential)
+    red = p3.broadcast("*", "Z", [1, 10.0]).sum(["Y", "Z"])           # :121-129
+    assert red.dimensions == ["X"] and np.array_equal(red.potential, [123.0, 165.0, 237.0])
+    p3.broadcast_("*", "Z", 0.0)
+    assert not p3.potential.any()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_join_reduce_normalize_ops_equal_oracle(bn, seed):
+    """/ + - joins (with the reference's larger-first swap), prod / maximum / minimum, normalize!(phi, dims; p) and
+    every broadcast op on random factors with ragged cardinalities: identical to the numpy restatement."""
+    rng = np.random.default_rng(seed)
+    names = list("abcdefg")
+    da = [str(x) for x in rng.choice(names, size=int(rng.integers(1, 6)), replace=False)]
+    db = [str(x) for x in rng.choice(names, size=int(rng.integers(1, 5)), replace=False)]
+    card = {n: int(rng.integers(1, 5)) for n in names}
+    A = rng.random([card[d] for d in da]) + 0.25
+    B = rng.random([card[d] for d in db]) + 0.25
+    if seed == 3:
+        A.flat[0] = np.nan  # max / min propagate NaN like Base.max
+    fa, fb = F(bn, da, A), F(bn, db, B)
+    oa, ob = NpFactor(da, A), NpFactor(db, B)
+    pairs = [("/", fa / fb, oa.join("/", ob)), ("/", fb / fa, ob.join("/", oa)), ("+", fa + fb, oa.join("+", ob)),
+             ("-", fa - fb, oa.join("-", ob)), ("-", fb - fa, ob.join("-", oa)), ("*", fa.join("*", fb), oa.join("*", ob))]
+    for op, got, want in pairs:
+        assert got.dimensions == want.dimensions
+        assert np.array_equal(got.potential, want.potential, equal_nan=True), op
+    for k in range(1, len(da) + 1):
+        dims = [str(x) for x in rng.choice(da, size=k, replace=False)]
+        for op, fn in (("*", fa.prod), ("max", fa.maximum), ("min", fa.minimum)):
+            got, want = fn(dims), oa.reducedim(op, dims)
+            assert got.dimensions == want.dimensions
+            assert np.array_equal(got.potential, want.potential, equal_nan=True), (op, dims)
+        assert np.array_equal(fa.sum(dims).potential, oa.reducedim("+", dims).potential, equal_nan=True)
+        for p in (1, 2):
+            got, want = fa.normalize(dims, p=p), oa.normalize_dims(dims, p=p)
+            assert np.array_equal(got.potential, want.potential, equal_nan=True), (dims, p)
+    for op in ("*", "/", "+", "-", "max", "min"):
+        d = da[int(rng.integers(0, len(da)))]
+        v = rng.random(card[d]) + 0.5
+        assert np.array_equal(fa.broadcast(op, d, v).potential, oa.broadcast(op, d, v).potential, equal_nan=True), op
+        assert np.array_equal(fa.broadcast(op, d, 0.75).potential, oa.broadcast(op, d, 0.75).potential, equal_nan=True), op
+    with pytest.raises(ValueError):
+        fa.prod("waldo")
+    with pytest.raises(ValueError):
+        fa.normalize("waldo")
+    with pytest.raises(RuntimeError):
+        fa.join("*", fb, kind="inner")
+
+
+def test_factor_ops_large_binary(bn):
+    """2^20-entry binary factors: merged-dim addressing of the gather kernels, in-place normalize over inner and outer dims."""
+    rng = np.random.default_rng(5)
+    dims = [f"v{i}" for i in range(20)]
+    A = rng.random([2] * 20) + 0.1
+    sub = [dims[i] for i in (3, 0, 19, 7)]
+    B = rng.random([2] * 4) + 0.1
+    fa, fb = F(bn, dims, A), F(bn, sub, B)
+    oa, ob = NpFactor(dims, A), NpFactor(sub, B)
+    assert np.array_equal((fa / fb).potential, oa.join("/", ob).potential)
+    assert np.array_equal((fb - fa).potential, ob.join("-", oa).potential)
+    for rd in (["v0", "v1", "v2"], ["v19"], ["v5", "v18", "v9"]):
+        assert np.array_equal(fa.maximum(rd).potential, oa.reducedim("max", rd).potential)
+        assert np.array_equal(fa.prod(rd).potential, oa.reducedim("*", rd).potential)
+        assert np.array_equal(fa.normalize(rd).potential, oa.normalize_dims(rd).potential)

@@ -376,3 +376,47 @@ def test_loopy_oracle_stopping_rule_and_aliasing(golden):
     lbp = loopy_infer(net, net.index["I"], ev)
     exact = exact_infer(net, "I", {"L": 0, "S": 1}).potential
     assert abs(lbp[0] - exact[0]) > 0.05 and lbp[0] < 1e-12      # the root's prior was multiplied in every iteration
+
+
+# ------------------------------------------------------------------------------------- the rest of the Factor algebra
+def test_broadcast_reduce_normalize_dims_golden():
+    """test/test_factors.jl:87-105 (broadcast), :111-130 (reducedim after broadcast), :71-81 (normalize)."""
+    phi = NpFactor(["X", "Y"], np.array([[1.0, 2], [3, 4], [5, 6]]))
+    got = phi.broadcast("*", ["Y", "X"], [[10, 0.1], 100.0]).potential
+    np.testing.assert_allclose(got, [[1000, 20], [3000, 40], [5000, 60]], rtol=1e-15)           # :90-92
+    with pytest.raises(ValueError):
+        phi.broadcast("*", ["X", "Z"], [[10, 1, 0.1], [1, 2, 3]])                               # :94
+    with pytest.raises(ValueError):
+        phi.broadcast("*", ["Z", "X", "A"], [2, [10, 1, 0.1], [1, 2, 3]])                       # :96
+    with pytest.raises(DimensionMismatch):
+        phi.broadcast("*", "X", [2016, 58.0])                                                   # :98
+    p3 = NpFactor(["X", "Y", "Z"], np.array([1.0, 2, 3, 2, 3, 4, 4, 6, 7, 8, 10, 16]).reshape((3, 2, 2), order="F"))
+    two = p3.broadcast("+", "Z", [10, 0.1]).broadcast("+", "X", 10.0)
+    one = p3.broadcast("+", ["X", "Z"], [10.0, [10, 0.1]])
+    assert np.array_equal(two.potential, one.potential)                                         # :104-105
+    red = p3.broadcast("*", "Z", [1, 10.0]).reducedim("+", ["Y", "Z"])
+    assert red.dimensions == ["X"] and np.array_equal(red.potential, [123.0, 165.0, 237.0])     # :121-129
+    assert np.array_equal(p3.broadcast("*", "Z", 0.0).reducedim("+", ["X", "Y", "Z"]).potential, np.array(0.0))  # :119
+    with pytest.raises(ValueError):
+        p3.reducedim("*", "waldo")                                                              # :113
+    n = NpFactor(["a", "b"], np.array([[1.0, 2], [3, 4]]))
+    np.testing.assert_allclose(n.normalize_dims(["a", "b"], p=1).potential, [[0.1, 0.2], [0.3, 0.4]], rtol=1e-15)
+    np.testing.assert_allclose(n.normalize_dims(["a", "b"], p=2).potential, [[1 / 30, 2 / 30], [1 / 10, 4 / 30]], rtol=1e-15)
+    np.testing.assert_allclose(n.normalize_dims("a").potential, [[0.25, 2 / 6], [0.75, 4 / 6]], rtol=1e-15)
+    with pytest.raises(ValueError):
+        n.normalize_dims("waldo")                                                               # :77
+
+
+def test_join_ops_follow_the_reference_swap():
+    """join(op, phi1, phi2) swaps to larger-first before applying op (factors_dims.jl:189-191): a / b with a smaller
+    than b is b ./ a; `*` agrees with the pinned product."""
+    rng = np.random.default_rng(0)
+    a = NpFactor(["x"], rng.random(3) + 0.5)
+    b = NpFactor(["y", "x"], rng.random((2, 3)) + 0.5)
+    assert np.array_equal(a.join("*", b).potential, (a * b).potential)
+    d = a.join("/", b)
+    assert d.dimensions == ["y", "x"]
+    np.testing.assert_array_equal(d.potential, b.potential / a.potential[None, :])
+    np.testing.assert_array_equal(b.join("-", a).potential, b.potential - a.potential[None, :])
+    np.testing.assert_array_equal(a.join("-", b).potential, b.potential - a.potential[None, :])  # the swap
+    np.testing.assert_array_equal(a.join("+", b).potential, b.potential + a.potential[None, :])
