@@ -352,6 +352,56 @@ function LinearAlgebra.normalize!(a::DeviceFactor; p::Int=1)
     return a
 end
 
+# The rest of src/Factors/factors_dims.jl on the device (not used by variable elimination; csrc/factor_ops.cu).
+const _BN_OP = Dict{Any,Int32}((*) => 0, (/) => 1, (+) => 2, (-) => 3, max => 4, min => 5)
+
+"join(op, a, b, :outer) for op in * / + - (factors_dims.jl:185-234,269-272), larger-first swap included."
+function Base.join(op, a::DeviceFactor, b::DeviceFactor, kind::Symbol=:outer)
+    kind == :outer || error("Inner joins are (still) umimplemented")
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_join, libbn_cuda), Int32, (UInt64, UInt64, Int32, Ref{UInt64}), a.handle, b.handle, _BN_OP[op], h))
+    return _wrap(h[])
+end
+Base.:/(a::DeviceFactor, b::DeviceFactor) = join(/, a, b)
+Base.:+(a::DeviceFactor, b::DeviceFactor) = join(+, a, b)
+Base.:-(a::DeviceFactor, b::DeviceFactor) = join(-, a, b)
+
+"reducedim(op, a, dims) for op in + * max min (factors_dims.jl:60-85,100-107)."
+function reducedim(op, a::DeviceFactor, dims::NodeNameUnion)
+    ids = _ids(nodeconvert(NodeNames, dims))
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_reduce, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Int32, Int32, Ref{UInt64}),
+                    a.handle, ids, length(ids), _BN_OP[op], h))
+    return _wrap(h[])
+end
+Base.prod(a::DeviceFactor, dims::NodeNameUnion) = reducedim(*, a, dims)
+Base.maximum(a::DeviceFactor, dims::NodeNameUnion) = reducedim(max, a, dims)
+Base.minimum(a::DeviceFactor, dims::NodeNameUnion) = reducedim(min, a, dims)
+
+"normalize!(a, dims; p) (factors_dims.jl:24-43)."
+function LinearAlgebra.normalize!(a::DeviceFactor, dims::NodeNameUnion; p::Int=1)
+    ids = _ids(unique(nodeconvert(NodeNames, dims)))
+    _bn_check(ccall((:bn_factor_normalize_dims, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Int32, Int32), a.handle, ids, length(ids), p))
+    return a
+end
+
+"broadcast!(op, a, dims, values) in place (factors_dims.jl:131-165); values are Float64 scalars or vectors."
+function Base.broadcast!(op, a::DeviceFactor, dims::NodeNameUnion, values)
+    if isa(dims, NodeName)
+        dims = [dims]; values = [values]
+    end
+    length(dims) == length(values) ||
+        throw(ArgumentError("Number of dimensions does not match number of values to broadcast"))
+    ids = _ids(dims)
+    lens = Int32[length(v) for v in values]
+    flat = Float64[x for v in values for x in v]
+    GC.@preserve ids lens flat begin
+        _bn_check(ccall((:bn_factor_broadcast, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Int32, Ptr{Float64}, Ptr{Int32}, Int32),
+                        a.handle, ids, length(ids), flat, lens, _BN_OP[op]))
+    end
+    return a
+end
+
 "sum(reduce(*, factors), h) in one kernel: the elimination step of src/Inference/exact.jl:27."
 function eliminate(factors::Vector{DeviceFactor}, h::NodeName)
     hs = UInt64[f.handle for f in factors]
