@@ -41,6 +41,21 @@ def allreduce_sum_(t):
     return t
 
 
+def allgather_rows_(local, counts):
+    """Concatenate per-rank row blocks (rank g holds counts[g] rows of equal width) on every rank.  Rows are padded to
+    the largest block so that one all_gather suffices; returns the [sum(counts), width] tensor."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return local
+    most = max(counts)
+    pad = local.new_zeros((most,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in counts]
+    dist.all_gather(parts, pad)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
 class ShardedLikelihoodWeighting:
     """LW inference whose particles are split over the ranks of the default process group.
 
@@ -129,3 +144,45 @@ class ShardedGibbs:
         c = self.out.cpu().numpy()
         with np.errstate(invalid="ignore", divide="ignore"):
             return (c / c.sum()).reshape(self.shape, order="F")
+
+
+class ShardedLoopy:
+    """LoopyBelief over many (query, evidence) pairs, the PAIRS split over the ranks of the default process group:
+    rank g answers pairs [g*B//G, (g+1)*B//G) with one bn_loopy_infer_dev launch; pairs are independent, so there is no
+    data-path collective (weak scaling) -- gather() all-gathers the beliefs only if every rank wants all of them."""
+
+    def __init__(self, bn, queries, evidences, nsamples: int = 500, tol: float = 1e-8, iters_for_convergence: int = 6,
+                 device: int | None = None):
+        import torch
+        self.torch = torch
+        rank, world, local = env_rank_world()
+        self.rank, self.world = rank, world
+        self.device = local if device is None else device
+        self.net = device_net(bn, self.device)
+        lay = self.net.layout
+        self.n_total = len(queries)
+        self.first, self.count = shard_range(self.n_total, rank, world)
+        self.counts = [shard_range(self.n_total, g, world)[1] for g in range(world)]
+        mine = range(self.first, self.first + self.count)
+        ev = np.stack([lay.evidence_vector(evidences[b]) for b in mine]) if self.count else np.zeros((0, lay.n), np.int8)
+        q = np.array([lay.index[queries[b]] for b in mine], np.int32)
+        dev = f"cuda:{self.device}"
+        self.stride = int(lay.card.max())
+        self.ev_d = torch.from_numpy(ev).to(dev)
+        self.q_d = torch.from_numpy(q).to(dev)
+        self.out = torch.zeros((self.count, self.stride), dtype=torch.float64, device=dev)
+        self.iters = torch.zeros(self.count, dtype=torch.int32, device=dev)
+        self.nsamples, self.tol, self.K = int(nsamples), float(tol), int(iters_for_convergence)
+
+    def launch(self):
+        """Enqueue the local shard on torch's current stream; beliefs in self.out [count, max_card]."""
+        _lib.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+        check(_lib.lib().bn_loopy_infer_dev(_lib.h64(self.net.handle), C.c_void_p(self.ev_d.data_ptr()),
+                                            C.c_void_p(self.q_d.data_ptr()), C.c_uint64(self.count), C.c_int32(self.nsamples),
+                                            C.c_double(self.tol), C.c_int32(self.K), C.c_int32(self.stride),
+                                            C.c_void_p(self.out.data_ptr()), C.c_void_p(self.iters.data_ptr())))
+        return self.out
+
+    def gather(self):
+        """All pairs' beliefs on every rank, in pair order."""
+        return allgather_rows_(self.out, self.counts)

@@ -23,6 +23,18 @@ def _free_port():
     return p
 
 
+def _loopy_pairs(lay):
+    rng = np.random.default_rng(3)
+    pairs = []
+    for _ in range(7):  # odd: ragged shards
+        picks = rng.choice(lay.n, size=3, replace=False)
+        ev = np.full(lay.n, -1, np.int8)
+        for i in picks[1:]:
+            ev[i] = rng.integers(0, lay.card[i])
+        pairs.append((int(picks[0]), ev))
+    return pairs
+
+
 def _worker(rank, world, port, n_total, q):
     try:
         sys.path.insert(0, ROOT)
@@ -48,8 +60,18 @@ def _worker(rank, world, port, n_total, q):
         gc, _ = capi.gibbs_infer(on, ev, qi, gcount, 300, 100, 3, seed=4, first_chain=gfirst)
         g = torch.from_numpy(gc.astype(np.float64).ravel(order="F").copy())
         allreduce_sum_(g)
+        # LoopyBelief: (query, evidence) pairs sharded the same way, beliefs all-gathered in pair order
+        from bayesnets_jl_b200.distributed import allgather_rows_
+        from oracle.loopy_np import loopy_infer
+        pairs = _loopy_pairs(lay)
+        lfirst, lcount = shard_range(len(pairs), rank, world)
+        rows = np.zeros((lcount, int(lay.card.max())))
+        for r, (qn, e) in enumerate(pairs[lfirst:lfirst + lcount]):
+            o = loopy_infer(on, qn, e, nsamples=8)
+            rows[r, :len(o)] = o
+        lb = allgather_rows_(torch.from_numpy(rows), [shard_range(len(pairs), g, world)[1] for g in range(world)])
         if rank == 0:
-            q.put((t.numpy().copy(), g.numpy().copy()))
+            q.put((t.numpy().copy(), g.numpy().copy(), lb.numpy().copy()))
         dist.destroy_process_group()
     except Exception as e:  # surface worker failures in the parent
         if rank == 0:
@@ -77,7 +99,7 @@ def test_two_rank_gloo_allreduce_equals_single_stream():
         assert p.exitcode == 0
     if isinstance(got, Exception):
         raise got
-    lw2, g2 = got
+    lw2, g2, lb2 = got
     net = bn.rand_discrete_bn(40, 3, 4, seed=5)
     lay = bn.flatten(net)
     on = FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
@@ -87,6 +109,12 @@ def test_two_rank_gloo_allreduce_equals_single_stream():
     assert lw2[-2] == pytest.approx(sw, rel=1e-12) and lw2[-1] == pytest.approx(sw2, rel=1e-12)
     gc, _ = capi.gibbs_infer(on, ev, qi, 64, 300, 100, 3, seed=4)
     assert np.array_equal(g2, gc.astype(np.float64).ravel(order="F"))
+    from oracle.loopy_np import loopy_infer
+    pairs = _loopy_pairs(lay)
+    assert lb2.shape == (len(pairs), int(lay.card.max()))
+    for b, (qn, e) in enumerate(pairs):
+        o = loopy_infer(on, qn, e, nsamples=8)
+        assert np.array_equal(lb2[b, :len(o)], o) and not lb2[b, len(o):].any()
 
 
 # ------------------------------------------------------------------------------------------ split factors (8e)
