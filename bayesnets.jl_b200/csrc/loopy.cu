@@ -50,6 +50,7 @@ struct LoopyArgs {
   const int32_t* query;
   double* out;
   int32_t* out_iters;
+  unsigned char* scratch;  // message planes of every warp when they do not fit shared memory
   unsigned long long n_inst;
   double tol, delta, eps_delta;
   uint32_t plan_words, cpt_len;
@@ -187,16 +188,30 @@ __device__ __forceinline__ double lambda_finish(const LoopyCtx g, uint32_t loff,
   return delta > mc ? delta : mc;
 }
 
-template <bool CPT_SMEM>
-__global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
+// Where things live.  PLAN_SMEM / CPT_SMEM: the plan (task records, node / edge tables, digit rows) and the CPTs are
+// staged into shared memory once per CTA, else read through L1 / L2.  MSG_SMEM: every warp's message planes are in
+// shared memory, else a slice of a global scratch buffer (L1 / L2 resident: 18 KB per warp on the C2 net).  Same code
+// and results in every combination; what changes is how many warps an SM can hold.
+template <bool PLAN_SMEM, bool CPT_SMEM, bool MSG_SMEM, int MINB = 0>
+__global__ void __launch_bounds__(MINB > 0 ? 256 : 320, MINB) loopy_kernel(const LoopyArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* plan = reinterpret_cast<uint32_t*>(smem_raw);
-  for (uint32_t i = threadIdx.x; i < a.plan_words; i += blockDim.x) plan[i] = a.plan[i];
-  double* cpt_s = reinterpret_cast<double*>(smem_raw + (((size_t)a.plan_words * 4 + 15) & ~(size_t)15));
-  if (CPT_SMEM)
-    for (uint32_t i = threadIdx.x; i < a.cpt_len; i += blockDim.x) cpt_s[i] = a.cpt[i];
-  __syncthreads();
-  const double* cpt = CPT_SMEM ? cpt_s : a.cpt;
+  const uint32_t* plan = a.plan;
+  const double* cpt = a.cpt;
+  {
+    size_t at = 0;
+    if (PLAN_SMEM) {
+      uint32_t* plan_s = reinterpret_cast<uint32_t*>(smem_raw);
+      for (uint32_t i = threadIdx.x; i < a.plan_words; i += blockDim.x) plan_s[i] = a.plan[i];
+      plan = plan_s;
+      at = ((size_t)a.plan_words * 4 + 15) & ~(size_t)15;
+    }
+    if (CPT_SMEM) {
+      double* cpt_s = reinterpret_cast<double*>(smem_raw + at);
+      for (uint32_t i = threadIdx.x; i < a.cpt_len; i += blockDim.x) cpt_s[i] = a.cpt[i];
+      cpt = cpt_s;
+    }
+    if (PLAN_SMEM || CPT_SMEM) __syncthreads();
+  }
   const uint32_t* nodes = plan + a.off_node;
   const uint32_t* edges = plan + a.off_edge;
   const uint32_t* taskA = plan + a.off_taskA;
@@ -205,7 +220,8 @@ __global__ void __launch_bounds__(320) loopy_kernel(const LoopyArgs a) {
   const uint32_t* dig = plan + a.off_dig;
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  unsigned char* mine = smem_raw + a.shared_bytes + (size_t)warp * a.per_warp_bytes;
+  unsigned char* mine = MSG_SMEM ? smem_raw + a.shared_bytes + (size_t)warp * a.per_warp_bytes
+                                 : a.scratch + ((size_t)blockIdx.x * wpc + warp) * a.per_warp_bytes;
   // planes: PI[0], PI[1] (S_c + 1 each, the last entry is the constant 1.0), R (roots only), LAMN, PP, LAM[0], LAM[1]
   const uint32_t P1 = a.S_c + 1u;
   double* PI0 = reinterpret_cast<double*>(mine);
@@ -658,37 +674,68 @@ static int32_t loopy_launch(Net* net, const int8_t* ev_dev, const int32_t* query
   a.out_stride = (uint32_t)out_stride;
   a.nsamples = nsamples;
   a.K = K;
-  // shared memory: plan (+ CPTs when they fit beside at least 4 warps of messages), then per-warp message planes
+  // Placement (measured on the C2 net): the kernel is latency-bound, so residency beats shared-memory
+  // latency -- by default plan, CPTs and message planes all stay in global memory (L1 / L2 resident) and an SM holds
+  // 4 CTAs x 8 warps = 32 instances instead of the 9 whose messages fit its shared memory.  BN_LOOPY_MODE (bit 0 plan,
+  // bit 1 CPTs, bit 2 messages in shared memory), BN_LOOPY_WARPS and BN_LOOPY_CTAS reproduce the other placements.
   const size_t budget = (size_t)dp.max_smem_optin - 1024;
   const size_t plan_b = ((size_t)a.plan_words * 4 + 15) & ~(size_t)15;
   const size_t cpt_b = ((size_t)a.cpt_len * 8 + 15) & ~(size_t)15;
   const size_t per_warp = (((size_t)3 * P.S_c + 2 + (size_t)P.S_r + (size_t)P.S_pp + (size_t)2 * P.S_l) * 8 + (size_t)net->n + 15) & ~(size_t)15;
-  BN_REQUIRE(plan_b + per_warp <= budget, BN_UNSUPPORTED,
-             "LoopyBelief: network too large for shared-memory messages (%zu B plan + %zu B per instance)", plan_b, per_warp);
-  const bool cpt_smem = plan_b + cpt_b + 4 * per_warp <= budget;
-  const size_t shared_b = plan_b + (cpt_smem ? cpt_b : 0);
-  // CTA shape: up to 10 warps; pick the warp count that keeps the most
-  // warps resident per SM (the staged plan + CPTs are paid once per CTA, the message planes once per warp)
-  static const int warps_env = getenv("BN_LOOPY_WARPS") ? atoi(getenv("BN_LOOPY_WARPS")) : 0;
-  const int max_warps = (int)std::min<size_t>(10, (budget - shared_b) / per_warp);
-  int warps = 1, best = 0;
-  for (int w = 1; w <= max_warps; ++w) {
-    const size_t sm = shared_b + (size_t)w * per_warp + 1024;
-    const int resident = (int)std::min<size_t>((size_t)dp.smem_per_sm / sm, (size_t)(2048 / (w * 32))) * w;
-    if (resident >= best) { best = resident; warps = w; }
+  const int warps_env = getenv("BN_LOOPY_WARPS") ? atoi(getenv("BN_LOOPY_WARPS")) : 0;
+  const int ctas_env = getenv("BN_LOOPY_CTAS") ? atoi(getenv("BN_LOOPY_CTAS")) : 0;
+  const int mode_env = getenv("BN_LOOPY_MODE") ? atoi(getenv("BN_LOOPY_MODE")) : -1;
+  a.per_warp_bytes = (uint32_t)per_warp;
+  int warps = 8, per_sm = 4;
+  bool plan_smem, cpt_smem, msg_smem;
+  if (mode_env >= 0) {
+    plan_smem = mode_env & 1; cpt_smem = mode_env & 2; msg_smem = mode_env & 4;
+  } else {
+    plan_smem = cpt_smem = msg_smem = false;
   }
-  if (warps_env > 0) warps = std::min(max_warps, warps_env);
+  size_t shared_b = (plan_smem ? plan_b : 0) + (cpt_smem ? cpt_b : 0);
+  if (msg_smem && shared_b + per_warp > budget) { msg_smem = false; }
+  if (shared_b > budget) { plan_smem = cpt_smem = false; shared_b = 0; }
+  if (msg_smem) {
+    // up to 10 warps; the warp count that keeps the most warps resident per SM (plan + CPTs are paid once per CTA)
+    const int max_warps = (int)std::min<size_t>(10, (budget - shared_b) / per_warp);
+    int best = 0;
+    for (int w = 1; w <= max_warps; ++w) {
+      const size_t sm = shared_b + (size_t)w * per_warp + 1024;
+      const int resident = (int)std::min<size_t>((size_t)dp.smem_per_sm / sm, (size_t)(2048 / (w * 32))) * w;
+      if (resident >= best) { best = resident; warps = w; }
+    }
+    if (warps_env > 0) warps = std::min(max_warps, warps_env);
+  } else if (warps_env > 0) {
+    warps = std::min(10, warps_env);
+  }
   warps = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)warps, n_inst));
   a.shared_bytes = (uint32_t)shared_b;
-  a.per_warp_bytes = (uint32_t)per_warp;
-  const size_t smem = shared_b + (size_t)warps * per_warp;
-  void (*kern)(const LoopyArgs) = cpt_smem ? loopy_kernel<true> : loopy_kernel<false>;
+  const size_t smem = shared_b + (msg_smem ? (size_t)warps * per_warp : 0);
+  void (*kern)(const LoopyArgs);
+  switch ((plan_smem ? 1 : 0) | (cpt_smem ? 2 : 0) | (msg_smem ? 4 : 0)) {
+    case 0: kern = loopy_kernel<false, false, false, 4>; break;  // 64 registers: 4 CTAs x 8 warps per SM
+    case 1: kern = loopy_kernel<true, false, false>; break;
+    case 2: kern = loopy_kernel<false, true, false>; break;
+    case 3: kern = loopy_kernel<true, true, false>; break;
+    case 4: kern = loopy_kernel<false, false, true>; break;
+    case 5: kern = loopy_kernel<true, false, true>; break;
+    case 6: kern = loopy_kernel<false, true, true>; break;
+    default: kern = loopy_kernel<true, true, true>; break;
+  }
   BN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
-  int per_sm = (int)((size_t)dp.smem_per_sm / (smem + 1024));
+  per_sm = (int)std::min<size_t>((size_t)per_sm, (size_t)dp.smem_per_sm / (smem + 1024));
+  if (msg_smem) per_sm = (int)((size_t)dp.smem_per_sm / (smem + 1024));
+  if (ctas_env > 0) per_sm = ctas_env;
   per_sm = std::max(1, std::min(per_sm, 2048 / (warps * 32)));
+  TmpBuf<unsigned char> scratch;
   const uint64_t ctas = (n_inst + (uint64_t)warps - 1) / (uint64_t)warps;
   const int grid = (int)std::min<uint64_t>(ctas, (uint64_t)dp.sm_count * (uint64_t)per_sm);
-  kern<<<grid, warps * 32, smem, tl_stream>>>(a);
+  if (!msg_smem) {
+    BN_CUDA_TRY(scratch.alloc((size_t)grid * (size_t)warps * per_warp));
+    a.scratch = scratch.p;
+  }
+  kern<<<grid, warps * 32, smem, tl_stream>>>(a);  // (a stream-ordered free of `scratch` follows the kernel)
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   return BN_OK;

@@ -173,3 +173,26 @@ def test_loopy_device_entry_point(bn):
         _lib.set_stream(None)
     assert np.array_equal(out_d.cpu().numpy(), want, equal_nan=True)
     assert np.array_equal(it_d.cpu().numpy(), im.last_iters)
+
+
+def test_loopy_placements_and_large_net(bn, monkeypatch):
+    """Plan / CPTs / message planes in shared or global memory (BN_LOOPY_MODE bits 0 / 1 / 2) are the same kernel:
+    every placement is identical to the oracle; a 700-node net, too large for shared memory, runs from global memory."""
+    net, lay, on, queries, evidences = random_instances(bn, 37, 2, 10, 6)
+    outs, its = oracle_batch(on, lay, queries, evidences, nsamples=40)
+    for mode in (0, 1, 2, 3, 4, 5, 7):
+        monkeypatch.setenv("BN_LOOPY_MODE", str(mode))
+        im = bn.LoopyBelief(nsamples=40)
+        got = im.infer_batch(net, queries, evidences)
+        assert list(im.last_iters) == its, mode
+        for b, o in enumerate(outs):
+            assert np.array_equal(got[b, :len(o)], o, equal_nan=True), mode
+    monkeypatch.delenv("BN_LOOPY_MODE")
+    net, lay, on, queries, evidences = random_instances(bn, 700, 8, 2, 30)
+    kw = dict(nsamples=3)
+    im = bn.LoopyBelief(**kw)
+    got = im.infer_batch(net, queries, evidences)
+    outs, its = oracle_batch(on, lay, queries, evidences, **kw)
+    assert list(im.last_iters) == its
+    for b, o in enumerate(outs):
+        assert np.array_equal(got[b, :len(o)], o, equal_nan=True)
