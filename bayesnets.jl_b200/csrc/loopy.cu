@@ -1,12 +1,13 @@
 // loopy.cu -- infer(::LoopyBelief) batched over evidence sets (src/Inference/loopy_belief.jl:24-218).
 //
 // The reference answers one (query, evidence) pair per call with Dict-of-Vector messages on one core.  Here one WARP
-// owns one (query, evidence) instance: all of its lambda / pi messages live in shared memory (double-buffered, fp64),
-// the 32 lanes split one iteration's work into TASKS -- "pi messages of node i" and "lambda message of node i to its
-// j-th parent" -- packed onto the lanes by the host (longest task first onto the least loaded lane); a lane walks its
-// list one CPT cell per trip of ONE flat loop, so lanes with differently shaped tasks do not wait for each other's
-// loop nests.  The CPTs plus a byte table of parent-state digits are staged once per CTA and shared by its warps.
-// Nothing but the evidence rows and the final beliefs touches HBM.
+// owns one (query, evidence) instance: all of its lambda / pi messages are double-buffered fp64 planes private to the
+// warp, the 32 lanes split one iteration's work into TASKS -- "pi messages of node i" and "lambda message of node i to
+// its j-th parent" -- packed onto the lanes by the host (longest task first onto the least loaded lane); a lane walks
+// its list one CPT cell per trip of ONE flat loop, so lanes with differently shaped tasks do not wait for each other's
+// loop nests.  The CPTs, a byte table of parent-state digits and the task records form a read-only plan shared by all
+// warps.  Plan, CPTs and message planes can each live in shared memory or in (L1 / L2 resident) global memory -- a
+// template choice; measured on B200 the all-global placement wins because it lets an SM hold 32 instances.
 //
 // Bug-compatible on purpose.  The reference keeps messages by reference, and three aliases change its numbers
 // (oracle/loopy_np.py spells them out; the kernel reproduces them):
@@ -30,8 +31,8 @@ namespace bn {
 
 struct LoopyPlan {
   std::vector<uint32_t> words;  // [nodes | edges | child edges | tasks A | tasks P | task records B by lane | lane ptr | digit rows]
-  uint32_t off_node = 0, off_edge = 0, off_child = 0, off_taskA = 0, off_taskB = 0, off_taskP = 0, off_lane = 0, off_dig = 0;
-  uint32_t nA = 0, nB = 0, nP = 0, n_edges = 0, S_c = 0, S_l = 0, S_pp = 0, S_r = 0, max_card = 0;
+  uint32_t off_node = 0, off_edge = 0, off_child = 0, off_taskA = 0, off_taskB = 0, off_taskP = 0, off_taskPP = 0, off_lane = 0, off_dig = 0;
+  uint32_t nA = 0, nB = 0, nP = 0, nPP = 0, n_edges = 0, S_c = 0, S_l = 0, S_pp = 0, S_r = 0, max_card = 0;
   DevBuf<uint32_t> dev;
 };
 void loopy_plan_free(LoopyPlan* p) { delete p; }
@@ -55,7 +56,7 @@ struct LoopyArgs {
   double tol, delta, eps_delta;
   uint32_t plan_words, cpt_len;
   uint32_t n_nodes, n_edges, S_c, S_l, S_pp, S_r;
-  uint32_t off_node, off_edge, off_child, off_taskA, off_taskB, off_taskP, off_lane, off_dig, nA, nB, nP;
+  uint32_t off_node, off_edge, off_child, off_taskA, off_taskB, off_taskP, off_taskPP, off_lane, off_dig, nA, nB, nP, nPP;
   uint32_t shared_bytes, per_warp_bytes, out_stride;
   int32_t nsamples, K;
 };
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 256 : 320, MINB) loopy_kernel(const
   const uint32_t* taskA = plan + a.off_taskA;
   const uint4* taskB = reinterpret_cast<const uint4*>(plan + a.off_taskB);
   const uint32_t* taskP = plan + a.off_taskP;
+  const uint32_t* taskPP = plan + a.off_taskPP;
   const uint32_t* dig = plan + a.off_dig;
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -302,25 +304,23 @@ __global__ void __launch_bounds__(MINB > 0 ? 256 : 320, MINB) loopy_kernel(const
           LAMN[poff + x] = lam;
         }
       }
-      for (uint32_t e = lane; e < a.n_edges; e += 32) {
+      for (uint32_t it = lane; it < a.nPP; it += 32) {  // one (child edge, state) pair per lane, most siblings first
+        const uint32_t item = taskPP[it], e = item & 0xffffffu, x = item >> 24;
         const uint32_t* ed = edges + e * EDGE_WORDS;
-        if (ed[7] == NO_PP) continue;
-        const uint32_t* nd = nodes + ed[0] * NODE_WORDS;  // the parent whose children are being multiplied
         if (ev[ed[0]] >= 0) continue;
+        const uint32_t* nd = nodes + ed[0] * NODE_WORDS;  // the parent whose children are being multiplied
         const uint32_t m = nd[4];
         const uint32_t* ce = g.childe + nd[5];
-        for (uint32_t x = 0; x < ed[3]; ++x) {
-          double p = 0.0;
-          bool first = true;
-          for (uint32_t k2 = 0; k2 < m; ++k2) {
-            const uint32_t e2 = ce[k2];
-            if (e2 == e) continue;
-            const double l = g.LAMr[edges[e2 * EDGE_WORDS + 1] + x];
-            p = first ? l : p * l;
-            first = false;
-          }
-          PPw[ed[7] + x] = p;
+        double p = 0.0;
+        bool first = true;
+        for (uint32_t k2 = 0; k2 < m; ++k2) {
+          const uint32_t e2 = ce[k2];
+          if (e2 == e) continue;
+          const double l = g.LAMr[edges[e2 * EDGE_WORDS + 1] + x];
+          p = first ? l : p * l;
+          first = false;
         }
+        PPw[ed[7] + x] = p;
       }
       __syncwarp();
       for (uint32_t ti = lane; ti < a.nA; ti += 32) {
@@ -479,7 +479,7 @@ static int32_t loopy_plan(Net* net) {
     const int64_t Q = (net->cpt_off[i + 1] - net->cpt_off[i]) / net->card[i];
     dig_off[(size_t)i] = (uint32_t)dig_words;
     dig_words += (uint64_t)Q * (uint64_t)((net->par_ptr[i + 1] - net->par_ptr[i] + 3) / 4);
-    if (dig_words > (16ull << 20) || net->cpt_off[n] > (int64_t)0x7fffffff) {
+    if (dig_words > (16ull << 20) || net->cpt_off[n] > (int64_t)0x7fffffff || net->par_ptr[n] >= (1 << 24)) {
       delete P;
       set_error("LoopyBelief: CPTs too wide for the digit table (node %d has %lld parent configurations)", i, (long long)Q);
       return BN_UNSUPPORTED;
@@ -590,6 +590,20 @@ static int32_t loopy_plan(Net* net) {
   for (auto& t : Pm) w.push_back(t.second);
   P->nA = (uint32_t)A.size();
   P->nP = (uint32_t)Pm.size();
+  // (child edge, state) pairs whose sibling products are tabulated, nodes with the most children first
+  {
+    std::vector<std::pair<uint64_t, uint32_t>> items;
+    for (int p = 0; p < n; ++p) {
+      const int m = net->child_ptr[p + 1] - net->child_ptr[p];
+      if (m < (int)PP_MIN_CHILDREN) continue;
+      for (int kk = net->child_ptr[p]; kk < net->child_ptr[p + 1]; ++kk)
+        for (int x = 0; x < net->card[p]; ++x) items.push_back({(uint64_t)m, w[P->off_child + (size_t)kk] | ((uint32_t)x << 24)});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) { return x.first > y.first; });
+    P->off_taskPP = (uint32_t)w.size();
+    for (auto& t : items) w.push_back(t.second);
+    P->nPP = (uint32_t)items.size();
+  }
   P->nB = (uint32_t)B.size();
   std::vector<std::vector<const Rec*>> lanes(32);
   std::vector<uint64_t> load(32, 0);
@@ -669,8 +683,8 @@ static int32_t loopy_launch(Net* net, const int8_t* ev_dev, const int32_t* query
   a.S_r = P.S_r;
   a.off_node = P.off_node; a.off_edge = P.off_edge; a.off_child = P.off_child;
   a.off_taskA = P.off_taskA; a.off_taskB = P.off_taskB; a.off_lane = P.off_lane; a.off_dig = P.off_dig;
-  a.off_taskP = P.off_taskP;
-  a.nA = P.nA; a.nB = P.nB; a.nP = P.nP;
+  a.off_taskP = P.off_taskP; a.off_taskPP = P.off_taskPP;
+  a.nA = P.nA; a.nB = P.nB; a.nP = P.nP; a.nPP = P.nPP;
   a.out_stride = (uint32_t)out_stride;
   a.nsamples = nsamples;
   a.K = K;

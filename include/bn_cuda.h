@@ -222,8 +222,8 @@ int32_t bn_statistics_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_ro
 
 /* ---- infer(::LoopyBelief, ::InferenceState): src/Inference/loopy_belief.jl:24-218 -------------------------
  * Loopy belief propagation, batched: instance b has evidence row evidence[b * n_nodes .. ] (NULL = no evidence
- * anywhere) and ONE query node query[b] (:26); all instances run concurrently, one warp each, messages in shared
- * memory.  nsamples = iteration cap, tol / iters_for_convergence = the reference's early stop (:196; tol < 0 never
+ * anywhere) and ONE query node query[b] (:26); all instances run concurrently, one warp each, messages
+ * L1 / L2 resident.  nsamples = iteration cap, tol / iters_for_convergence = the reference's early stop (:196; tol < 0 never
  * stops).  out[b * out_stride + s] = P(query[b] = s | evidence_b), s < card(query[b]) (rest zero-filled);
  * out_iters[b] (may be NULL) = iterations run.  Reproduces the reference's message aliasing (csrc/loopy.cu header),
  * i.e. the same numbers as the reference, which on nets whose roots have several children are not textbook LBP.
