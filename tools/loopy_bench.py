@@ -69,6 +69,21 @@ def run(bn, torch, n_inst=65536, iters=50, reps=5, n_check=3, n_nodes=100):
            "message_updates_per_s": n_inst * iters * (n_edges + with_children) / t,
            "instances_per_s_at_this_iteration_count": n_inst / t}
     post = out_d.cpu().numpy()
+    # end to end through the host-buffer entry point: evidence rows + queries up, beliefs + iteration counts down
+    out_h = np.zeros((n_inst, stride), np.float64)
+    it_h = np.zeros(n_inst, np.int32)
+
+    def host_call():
+        _lib.check(L.bn_loopy_infer(_lib.h64(dn.handle), _lib.ptr(ev, _lib.i8p), _lib.ptr(q, _lib.i32p), C.c_uint64(n_inst),
+                                    C.c_int32(iters), C.c_double(-1.0), C.c_int32(6), C.c_int32(stride),
+                                    _lib.ptr(out_h, _lib.f64p), _lib.ptr(it_h, _lib.i32p)))
+    host_call()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); host_call(); ts.append(time.perf_counter() - t0)
+    res["e2e"] = {"value": n_inst * iters / float(np.median(ts)), "unit": "instance-iterations/s",
+                  "h2d_bytes_per_call": int(ev.nbytes + q.nbytes), "d2h_bytes_per_call": int(out_h.nbytes + it_h.nbytes),
+                  "api": "bn_loopy_infer (host buffers)", "identical_to_device_call": bool(np.array_equal(out_h, post, equal_nan=True))}
     # default stopping rule (tol 1e-8, cap 500): how many iterations the instances actually need
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
