@@ -9,6 +9,8 @@ Two halves:
                           C factor ops that are timed as the CPU baseline
   * ``oracle.factors_np`` numpy restatement of ``src/Factors`` + ``ExactInference`` + brute-force
                           joint enumeration (independent second opinion on the C code)
+  * ``oracle.loopy_np``   numpy restatement of ``infer(::LoopyBelief)`` that keeps the reference's message aliasing
+                          literally (``capi.loopy_infer`` is the C twin, bit-identical, timed as the CPU baseline)
   * ``oracle.scoring_py`` Dirichlet priors + ``bayesian_score_component`` on the count tables of
                           ``capi.statistics`` (``structure_scoring.jl:17-42``), pinned to the five score
                           values of ``test/test_discrete_bayes_nets.jl:40-44``

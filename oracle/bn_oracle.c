@@ -29,6 +29,7 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+#include <float.h>
 #endif
 
 #define ORC_MAX_CARD 64
@@ -701,6 +702,217 @@ int orc_statistics(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr,
       N[xi[r] + (int64_t)card[i] * j] += 1;
     }
   }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Loopy belief propagation: infer(::LoopyBelief), src/Inference/loopy_belief.jl:24-218, one (query, evidence)
+ * instance after the other (OpenMP over instances).  Second restatement beside oracle/loopy_np.py: the numpy one keeps
+ * the reference's array aliasing literally; this one states its CONSEQUENCES explicitly --
+ *   - a parentless node's pi is its factor's potential, rewritten in place per child, every iteration (:125,:170-175)
+ *     -> R[] persists across iterations;
+ *   - all children of a node receive the array left after the last child's update (:177) -> one pi message per node;
+ *   - from iteration 2 on both message dictionaries hold a root's array: its children read the message of the current
+ *     iteration (nodes run in topological order, roots first) and its own change is norm(px - px, Inf)
+ * -- and tests/test_oracle_golden.py requires the two to agree bit for bit.  Arithmetic order as the reference's calls:
+ * n-ary broadcast `*` is a left fold (factors_dims.jl:131-165), sum! accumulates column-major (:87-98), normalize!(phi)
+ * divides by sum(abs) (:45-57), normalize!(v, 1) multiplies by inv(norm1) (LinearAlgebra.__normalize!), norm(v) and
+ * norm(v, Inf) are generic_norm2 / generic_normInf.
+ * ---------------------------------------------------------------------------------------- */
+static double lbp_norm2_diff(const double* a, const double* b, int n) {
+  double maxabs = 0.0;
+  int nan = 0;
+  for (int i = 0; i < n; ++i) {
+    double d = fabs(a[i] - b[i]);
+    if (d != d) nan = 1; else if (d > maxabs) maxabs = d;
+  }
+  if (nan) return NAN;
+  if (maxabs == 0.0 || isinf(maxabs)) return maxabs;
+  double mm = maxabs * maxabs, s = 0.0;
+  if (isfinite((double)n * mm) && mm != 0.0) {
+    for (int i = 0; i < n; ++i) { double d = a[i] - b[i]; s = s + d * d; }
+    return sqrt(s);
+  }
+  for (int i = 0; i < n; ++i) { double r = fabs(a[i] - b[i]) / maxabs; s = s + r * r; }
+  return maxabs * sqrt(s);
+}
+
+int orc_loopy_infer(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                    const int64_t* cpt_off, const double* cpt, const int8_t* evidence, const int32_t* query, int64_t n_inst,
+                    int32_t nsamples, double tol, int32_t iters_for_convergence, int32_t out_stride, double* out,
+                    int32_t* out_iters) {
+  if (iters_for_convergence < 1 || nsamples < 0) return -1;
+  orc_net bn = {n_nodes, card, par_ptr, par_idx, cpt_off, cpt};
+  orc_children ch = build_children(&bn);
+  const int n = n_nodes, n_edges = par_ptr[n];
+  int64_t S_c = 0, S_l = 0;
+  int64_t* poff = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+  int64_t* loff = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_edges + 1));
+  int max_card = 1;
+  for (int i = 0; i < n; ++i) { poff[i] = S_c; S_c += card[i]; if (card[i] > max_card) max_card = card[i]; }
+  for (int e = 0; e < n_edges; ++e) { loff[e] = S_l; S_l += card[par_idx[e]]; }
+  /* edge (child -> p) of the k-th child of p */
+  int32_t* cedge = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_edges + 1));
+  for (int p = 0; p < n; ++p)
+    for (int kk = ch.ptr[p]; kk < ch.ptr[p + 1]; ++kk) {
+      int c = ch.idx[kk];
+      for (int e = par_ptr[c]; e < par_ptr[c + 1]; ++e) if (par_idx[e] == p) cedge[kk] = e;
+    }
+  const double DELTA = 1.0 / DBL_MAX, EPS_DELTA = DBL_EPSILON / DELTA;
+#pragma omp parallel
+  {
+    double* PI = (double*)malloc(sizeof(double) * (size_t)(2 * S_c + 1));
+    double* R = (double*)malloc(sizeof(double) * (size_t)(S_c + 1));
+    double* LAM = (double*)malloc(sizeof(double) * (size_t)(2 * S_l + 1));
+    double* lam = (double*)malloc(sizeof(double) * (size_t)max_card);
+    double* lx = (double*)malloc(sizeof(double) * (size_t)max_card * (size_t)max_card);
+    int* dig = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t b = 0; b < n_inst; ++b) {
+      const int8_t* ev = evidence ? evidence + b * n : NULL;
+#define EV(i) (ev ? (int)ev[i] : -1)
+      for (int i = 0; i < n; ++i)
+        for (int x = 0; x < card[i]; ++x) {
+          double v = EV(i) >= 0 ? (x == EV(i) ? 1.0 : 0.0) : 1.0 / (double)card[i];   /* :69-85 */
+          PI[poff[i] + x] = PI[S_c + poff[i] + x] = v;
+          R[poff[i] + x] = par_ptr[i + 1] == par_ptr[i] ? cpt[cpt_off[i] + x] : 0.0;
+        }
+      for (int e = 0; e < n_edges; ++e)
+        for (int x = 0; x < card[par_idx[e]]; ++x) LAM[loff[e] + x] = LAM[S_l + loff[e] + x] = 1.0 / (double)card[par_idx[e]];
+      int consec = (INFINITY <= tol) ? iters_for_convergence : 0, iters = 0;
+      for (int t = 1; t <= nsamples; ++t) {
+        iters = t;
+        double* PIr = PI + ((t - 1) & 1) * S_c; double* PIw = PI + (t & 1) * S_c;
+        const double* LAMr = LAM + ((t - 1) & 1) * S_l; double* LAMw = LAM + (t & 1) * S_l;
+        double mc = -INFINITY;
+        for (int i = 0; i < n; ++i) {                                                   /* :100 */
+          const int c = card[i], k = par_ptr[i + 1] - par_ptr[i], m = ch.ptr[i + 1] - ch.ptr[i];
+          const double* cp = cpt + cpt_off[i];
+          int64_t Q = (cpt_off[i + 1] - cpt_off[i]) / c;
+          /* lambda: evidence one-hot, ones, or the fold of the children's messages (:114-121) */
+          for (int x = 0; x < c; ++x) {
+            if (EV(i) >= 0) lam[x] = x == EV(i) ? 1.0 : 0.0;
+            else if (m == 0) lam[x] = 1.0;
+            else {
+              double l = LAMr[loff[cedge[ch.ptr[i]]] + x];
+              for (int k2 = 1; k2 < m; ++k2) l = l * LAMr[loff[cedge[ch.ptr[i] + k2]] + x];
+              lam[x] = l;
+            }
+          }
+          /* lambda messages to the parents (:136-160) */
+          for (int j = 0; j < k; ++j) {
+            const int e = par_ptr[i] + j, pc = card[par_idx[e]];
+            for (int z = 0; z < c * pc; ++z) lx[z] = 0.0;
+            for (int jj = 0; jj < k; ++jj) dig[jj] = 0;
+            for (int64_t q = 0; q < Q; ++q) {                 /* ascending q = column-major over the parents */
+              for (int x = 0; x < c; ++x) {
+                double tv = cp[x + c * q];
+                for (int jj = 0; jj < k; ++jj)
+                  if (jj != j) tv = tv * PIr[poff[par_idx[par_ptr[i] + jj]] + dig[jj]];
+                double* slot = lx + x + c * dig[j];
+                *slot = *slot + tv;                            /* 0 + tv == tv: same as starting the sum at the first term */
+              }
+              for (int jj = 0; jj < k; ++jj) { if (++dig[jj] < card[par_idx[par_ptr[i] + jj]]) break; dig[jj] = 0; }
+            }
+            double total = 0.0;
+            for (int u = 0; u < pc; ++u) {
+              double msg = lx[c * u] * lam[0];
+              for (int x = 1; x < c; ++x) msg = msg + lx[x + c * u] * lam[x];
+              LAMw[loff[e] + u] = msg;
+              total = u ? total + fabs(msg) : fabs(msg);
+            }
+            for (int u = 0; u < pc; ++u) LAMw[loff[e] + u] = LAMw[loff[e] + u] / total;
+            double delta = lbp_norm2_diff(LAMw + loff[e], LAMr + loff[e], pc);
+            if (delta > mc) mc = delta;
+          }
+          /* pi messages to the children (:163-185) */
+          if (EV(i) >= 0 || m == 0) continue;
+          double* px;
+          if (k == 0) px = R + poff[i];
+          else {
+            px = PIw + poff[i];
+            for (int x = 0; x < c; ++x) {
+              double acc = 0.0;
+              for (int jj = 0; jj < k; ++jj) dig[jj] = 0;
+              for (int64_t q = 0; q < Q; ++q) {
+                double tv = cp[x + c * q];
+                for (int jj = 0; jj < k; ++jj) tv = tv * PIr[poff[par_idx[par_ptr[i] + jj]] + dig[jj]];
+                acc = q ? acc + tv : tv;
+                for (int jj = 0; jj < k; ++jj) { if (++dig[jj] < card[par_idx[par_ptr[i] + jj]]) break; dig[jj] = 0; }
+              }
+              px[x] = acc;
+            }
+          }
+          for (int kk = 0; kk < m; ++kk) {
+            double nrm = 0.0;
+            for (int x = 0; x < c; ++x) {
+              double v = px[x];
+              if (m > 1) {
+                double p = 0.0; int first = 1;
+                for (int k2 = 0; k2 < m; ++k2) {
+                  if (k2 == kk) continue;
+                  double l = LAMr[loff[cedge[ch.ptr[i] + k2]] + x];
+                  p = first ? l : p * l; first = 0;
+                }
+                v = v * p; px[x] = v;
+              }
+              nrm = x ? nrm + fabs(v) : fabs(v);
+            }
+            int nan = 0; double dm = 0.0;
+            for (int x = 0; x < c; ++x) {
+              double v = px[x];
+              if (nrm >= DELTA) v = v * (1.0 / nrm);
+              else { v = v * EPS_DELTA; v = v * (1.0 / (nrm * EPS_DELTA)); }
+              px[x] = v;
+              double old = k == 0 ? (t == 1 ? 1.0 / (double)c : v) : PIr[poff[i] + x];
+              double d = fabs(v - old);
+              if (d != d) nan = 1; else if (d > dm) dm = d;
+            }
+            if (!nan && dm > mc) mc = dm;
+          }
+          if (k == 0)
+            for (int x = 0; x < c; ++x) { PIw[poff[i] + x] = px[x]; if (t >= 2) PIr[poff[i] + x] = px[x]; }
+        }
+        consec = (mc <= tol) ? (consec + 1 < iters_for_convergence ? consec + 1 : iters_for_convergence) : 0;
+        if (consec >= iters_for_convergence) break;
+      }
+      /* belief of the query (:201-217) */
+      {
+        const int qn = query[b], c = card[qn], k = par_ptr[qn + 1] - par_ptr[qn], m = ch.ptr[qn + 1] - ch.ptr[qn];
+        const double* PIr = PI + (iters & 1) * S_c; const double* LAMr = LAM + (iters & 1) * S_l;
+        const double* cp = cpt + cpt_off[qn];
+        int64_t Q = (cpt_off[qn + 1] - cpt_off[qn]) / c;
+        double* o = out + b * out_stride; double total = 0.0;
+        for (int x = 0; x < c; ++x) {
+          double l = 1.0;
+          if (m) {
+            l = LAMr[loff[cedge[ch.ptr[qn]]] + x];
+            for (int k2 = 1; k2 < m; ++k2) l = l * LAMr[loff[cedge[ch.ptr[qn] + k2]] + x];
+          }
+          double pi;
+          if (k == 0) pi = R[poff[qn] + x];
+          else {
+            pi = 0.0;
+            for (int jj = 0; jj < k; ++jj) dig[jj] = 0;
+            for (int64_t q = 0; q < Q; ++q) {
+              double tv = cp[x + c * q];
+              for (int jj = 0; jj < k; ++jj) tv = tv * PIr[poff[par_idx[par_ptr[qn] + jj]] + dig[jj]];
+              pi = q ? pi + tv : tv;
+              for (int jj = 0; jj < k; ++jj) { if (++dig[jj] < card[par_idx[par_ptr[qn] + jj]]) break; dig[jj] = 0; }
+            }
+          }
+          o[x] = l * pi;
+          total = x ? total + fabs(o[x]) : fabs(o[x]);
+        }
+        for (int x = 0; x < c; ++x) o[x] = o[x] / total;
+        for (int x = c; x < out_stride; ++x) o[x] = 0.0;
+        if (out_iters) out_iters[b] = iters;
+      }
+#undef EV
+    }
+    free(PI); free(R); free(LAM); free(lam); free(lx); free(dig);
+  }
+  free(poff); free(loff); free(cedge); free(ch.ptr); free(ch.idx);
   return 0;
 }
 

@@ -248,3 +248,25 @@ def statistics(net, data, n_rows=None, pitch=None):
                               C.c_uint64(pitch), _p(out, C.c_int64))
     assert rc == 0
     return out
+
+
+def loopy_infer(net, queries, evidences=None, nsamples=500, tol=1e-8, iters_for_convergence=6):
+    """src/Inference/loopy_belief.jl:24-218 for a batch of (query node index, evidence row) instances (OpenMP over
+    instances) -> (beliefs [n_inst, max_card] zero-padded, iterations [n_inst]).  The C restatement spells out the
+    consequences of the reference's message aliasing; oracle.loopy_np keeps the aliasing itself; the tests require both
+    to agree bit for bit."""
+    args, keep = _net_args(net)
+    q = np.ascontiguousarray(queries, np.int32)
+    nn = np.asarray(net.card).size
+    ev = None
+    if evidences is not None:
+        ev = np.ascontiguousarray(evidences, np.int8).reshape(q.size, nn)
+    stride = int(np.asarray(net.card).max())
+    out = np.zeros((q.size, stride), np.float64)
+    its = np.zeros(q.size, np.int32)
+    rc = lib().orc_loopy_infer(*args, _p(ev, C.c_int8), _p(q, C.c_int32), C.c_int64(q.size), C.c_int32(nsamples),
+                               C.c_double(tol), C.c_int32(iters_for_convergence), C.c_int32(stride),
+                               _p(out, C.c_double), _p(its, C.c_int32))
+    if rc != 0:
+        raise ValueError("iters_for_convergence must be >= 1 and nsamples >= 0")
+    return out, its

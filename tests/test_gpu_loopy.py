@@ -196,3 +196,22 @@ def test_loopy_placements_and_large_net(bn, monkeypatch):
     assert list(im.last_iters) == its
     for b, o in enumerate(outs):
         assert np.array_equal(got[b, :len(o)], o, equal_nan=True)
+
+
+def test_loopy_c2_batch_identical_to_c_oracle(bn):
+    """The bench case itself: 100-node net, 10 evidence nodes per pair, 768 pairs (24 CTAs) -- every belief and iteration
+    count identical to the C restatement (which the CPU tests hold bit-identical to the numpy oracle)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import loopy_bench
+    from oracle import capi
+    net, lay, ev, q = loopy_bench.build_case(bn, 768)
+    on = oracle_net_from_layout(lay)
+    for kw in (dict(nsamples=30, tol=-1.0), dict(nsamples=12, tol=0.05, iters_for_convergence=2)):
+        im = bn.LoopyBelief(**kw)
+        queries = [lay.names[int(i)] for i in q]
+        evidences = [{lay.names[i]: int(e[i]) + 1 for i in np.nonzero(e >= 0)[0]} for e in ev]
+        got = im.infer_batch(net, queries, evidences)
+        want, its = capi.loopy_infer(on, q, ev, **kw)
+        assert np.array_equal(got, want, equal_nan=True)
+        assert np.array_equal(im.last_iters, its)

@@ -420,3 +420,31 @@ def test_join_ops_follow_the_reference_swap():
     np.testing.assert_array_equal(b.join("-", a).potential, b.potential - a.potential[None, :])
     np.testing.assert_array_equal(a.join("-", b).potential, b.potential - a.potential[None, :])  # the swap
     np.testing.assert_array_equal(a.join("+", b).potential, b.potential + a.potential[None, :])
+
+
+@pytest.mark.parametrize("seed,n_nodes,kw", [(0, 12, dict()), (1, 30, dict(nsamples=40)), (2, 60, dict(nsamples=15, tol=-1.0)),
+                                             (3, 8, dict(iters_for_convergence=1, tol=1e-3)), (4, 100, dict(nsamples=6))])
+def test_loopy_c_and_numpy_restatements_agree(seed, n_nodes, kw):
+    """The numpy oracle keeps the reference's aliasing literally, the C one states its consequences: bit-identical
+    beliefs and iteration counts on random nets and evidence (incl. impossible evidence -> NaN)."""
+    import bayesnets_jl_b200 as bn
+    from conftest import oracle_net_from_layout
+    from oracle.loopy_np import loopy_infer
+    net = bn.rand_discrete_bn(n_nodes, 3, 4, seed=seed)
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    rng = np.random.default_rng(seed)
+    B = 6
+    ev = np.full((B, lay.n), -1, np.int8)
+    q = np.zeros(B, np.int32)
+    for b in range(B):
+        picks = rng.choice(lay.n, size=min(lay.n, 1 + (b * n_nodes) // 12), replace=False)
+        q[b] = picks[0]
+        for i in picks[1:]:
+            ev[b, i] = rng.integers(0, lay.card[i])
+    out, its = capi.loopy_infer(on, q, ev, **kw)
+    for b in range(B):
+        want, it = loopy_infer(on, int(q[b]), ev[b], return_iters=True, **kw)
+        assert it == its[b]
+        assert np.array_equal(out[b, :len(want)], want, equal_nan=True), (b, out[b], want)
+        assert not out[b, len(want):].any()

@@ -252,7 +252,8 @@ def main():
                 "config": f"C2 net, {n_inst} (query, 10 evidence nodes) pairs x {n_it} iterations (tol < 0), one launch, "
                           "device-resident evidence rows", "unit": "instance-iterations/s",
                 "gpu": lb["instance_iterations_per_s"], "gpu_ms": lb["ms"], "message_updates_per_s": lb["message_updates_per_s"],
-                "cpu": lb["cpu_baseline"], "check": f"beliefs of the first 2 pairs identical to the oracle: {lb['identical_to_oracle']}"})
+                "cpu": lb["cpu_baseline"], "check": f"beliefs identical to the numpy oracle (2 pairs): {lb['identical_to_oracle']}, to the C oracle "
+                         f"({lb['identical_to_c_oracle']['pairs']} pairs): {lb['identical_to_c_oracle']['identical']}"})
 
     for r in out:
         cpu = r["cpu"]["value"]
