@@ -11,6 +11,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence
 
+import math
+
 import numpy as np
 
 Assignment = dict  # Dict{Symbol,Any}: src/ProbabilisticGraphicalModels/assignments.jl:1
@@ -182,6 +184,16 @@ class BayesNet:
         r = 1.0
         for c in self.cpds:
             r *= c.pdf(a)
+        return r
+
+    def logpdf(self, assignment: dict | None = None, /, **kw) -> float:  # :322-328
+        """logpdf(bn, assignment): one row, evaluated where the assignment lives (the host), like the reference.
+        A whole data table goes through `logpdf(bn, df)` (learning.py), i.e. the counting kernel."""
+        a = dict(assignment or {}, **kw)
+        r = 0.0
+        for c in self.cpds:
+            p = c.pdf(a)
+            r += math.log(p) if p > 0 else (-math.inf if p == 0 else math.nan)
         return r
 
 

@@ -274,6 +274,58 @@ static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_r
   return BN_OK;
 }
 
+
+// logpdf(bn, df) (src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-99 over src/bayes_nets.jl:322-328):
+// the reference adds log P(x_i | pa_i) row by row, node by node.  Grouping equal terms, the same sum is the dot product
+// of the table's sufficient statistics with the log CPTs, sum_b N[b] * log(cpt[b]) over the bins with N[b] > 0 -- so
+// the n_rows x n_nodes part is the counting kernel above and what remains is a few thousand terms: one CTA, one term
+// per thread per trip, folded in a fixed order (deterministic; no fp atomics).  A bin with N > 0 and cpt = 0 gives
+// -Inf, as log(0) does in the reference's sum; bins never seen contribute nothing (the reference never evaluates them).
+__global__ void __launch_bounds__(1024, 1) logl_kernel(const unsigned long long* __restrict__ counts,
+                                                        const double* __restrict__ cpt, uint32_t n_bins,
+                                                        double* __restrict__ out) {
+  __shared__ double part[1024];
+  double acc = 0.0;
+  for (uint32_t b = threadIdx.x; b < n_bins; b += 1024) {
+    const unsigned long long c = counts[b];
+    if (c) acc += (double)c * log(cpt[b]);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = part[0];
+}
+
+static int32_t logpdf_launch(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch, double* out_dev) {
+  const size_t n_bins = (size_t)net->cpt_off[net->n];
+  TmpBuf<unsigned long long> d_counts;
+  BN_CUDA_TRY(d_counts.alloc(n_bins + 1));
+  BN_TRY(statistics_launch(net, data_dev, n_rows, pitch, d_counts.p));
+  logl_kernel<<<1, 1024, 0, tl_stream>>>(d_counts.p, net->d_cpt.p, (uint32_t)n_bins, out_dev);
+  count_launch();
+  BN_CUDA_TRY(cudaGetLastError());
+  return BN_OK;
+}
+
+// host table -> pitched device copy, states validated on the way (a state >= card would be counted out of bounds)
+static int32_t upload_table(Net* net, const uint8_t* states, uint64_t n_rows, TmpBuf<uint8_t>& d_states, uint64_t* pitch) {
+  for (int i = 0; i < net->n; ++i) {
+    const uint8_t* col = states + (size_t)i * n_rows;
+    const uint8_t c = (uint8_t)net->card[i];
+    for (uint64_t r = 0; r < n_rows; ++r)
+      BN_REQUIRE(col[r] < c, BN_BOUNDS, "row %llu: state %d of node %d outside 0:%d", (unsigned long long)r, (int)col[r], i,
+                 (int)c - 1);
+  }
+  *pitch = (n_rows + 15) / 16 * 16;
+  BN_CUDA_TRY(d_states.alloc((size_t)net->n * *pitch + 16));
+  if (n_rows)
+    BN_CUDA_TRY(cudaMemcpy2DAsync(d_states.p, *pitch, states, n_rows, n_rows, (size_t)net->n, cudaMemcpyHostToDevice, tl_stream));
+  return BN_OK;
+}
+
 }  // namespace bn
 
 using namespace bn;
@@ -292,23 +344,35 @@ int32_t bn_statistics(bn_net_t h, const uint8_t* states, uint64_t n_rows, int64_
   BN_REQUIRE(net && out_counts && (states || n_rows == 0), BN_BAD_ARG, "bn_statistics: bad arguments");
   BN_CUDA_TRY(cudaSetDevice(net->device));
   const size_t n_bins = (size_t)net->cpt_off[net->n];
-  // states must be valid (< card) or the kernel would count out of bounds: check on the host while copying
-  for (int i = 0; i < net->n; ++i) {
-    const uint8_t* col = states + (size_t)i * n_rows;
-    const uint8_t c = (uint8_t)net->card[i];
-    for (uint64_t r = 0; r < n_rows; ++r)
-      BN_REQUIRE(col[r] < c, BN_BOUNDS, "row %llu: state %d of node %d outside 0:%d", (unsigned long long)r, (int)col[r], i,
-                 (int)c - 1);
-  }
-  const uint64_t pitch = (n_rows + 15) / 16 * 16;
+  uint64_t pitch = 0;
   TmpBuf<uint8_t> d_states;
   TmpBuf<unsigned long long> d_out;
-  BN_CUDA_TRY(d_states.alloc((size_t)net->n * pitch + 16));
+  BN_TRY(upload_table(net, states, n_rows, d_states, &pitch));
   BN_CUDA_TRY(d_out.alloc(n_bins + 1));
-  if (n_rows)
-    BN_CUDA_TRY(cudaMemcpy2DAsync(d_states.p, pitch, states, n_rows, n_rows, (size_t)net->n, cudaMemcpyHostToDevice, tl_stream));
   BN_TRY(statistics_launch(net, d_states.p, n_rows, pitch, d_out.p));
   BN_CUDA_TRY(cudaMemcpyAsync(out_counts, d_out.p, n_bins * sizeof(int64_t), cudaMemcpyDeviceToHost, tl_stream));
+  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_logpdf_dev(bn_net_t h, const uint8_t* states_dev, uint64_t n_rows, uint64_t pitch, double* out_logl_dev) {
+  Net* net = get_net(h);
+  BN_REQUIRE(net && out_logl_dev && (states_dev || n_rows == 0), BN_BAD_ARG, "bn_logpdf_dev: bad arguments");
+  BN_CUDA_TRY(cudaSetDevice(net->device));
+  return logpdf_launch(net, states_dev, n_rows, pitch, out_logl_dev);
+}
+
+int32_t bn_logpdf(bn_net_t h, const uint8_t* states, uint64_t n_rows, double* out_logl) {
+  Net* net = get_net(h);
+  BN_REQUIRE(net && out_logl && (states || n_rows == 0), BN_BAD_ARG, "bn_logpdf: bad arguments");
+  BN_CUDA_TRY(cudaSetDevice(net->device));
+  uint64_t pitch = 0;
+  TmpBuf<uint8_t> d_states;
+  TmpBuf<double> d_out;
+  BN_TRY(upload_table(net, states, n_rows, d_states, &pitch));
+  BN_CUDA_TRY(d_out.alloc(1));
+  BN_TRY(logpdf_launch(net, d_states.p, n_rows, pitch, d_out.p));
+  BN_CUDA_TRY(cudaMemcpyAsync(out_logl, d_out.p, sizeof(double), cudaMemcpyDeviceToHost, tl_stream));
   BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
   return BN_OK;
 }

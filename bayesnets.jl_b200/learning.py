@@ -8,6 +8,8 @@ Mirrors, name for name:
   UniformPrior / BDeuPrior        src/DiscreteBayesNet/dirichlet_priors.jl
   bayesian_score_component(s)     src/DiscreteBayesNet/structure_scoring.jl:17-42,75-94,133-160
   bayesian_score                  src/DiscreteBayesNet/structure_scoring.jl:95-125
+  logpdf(bn, df) / pdf(bn, df)    src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-104 (the data
+                                  log-likelihood: the table's counts dotted with the log CPTs, bn_logpdf[_dev])
   fit(DiscreteBayesNet, data, edges)   src/learning.jl:1-64 + src/CPDs/categorical_cpd.jl:109-152 (MLE per parental
                                   instantiation; an instantiation never seen gets the uniform Categorical)
 
@@ -288,3 +290,58 @@ def fit_from_device_table(bn_structure: BayesNet, states_dev_ptr: int, n_rows: i
     lay, counts = statistics_device(bn_structure, states_dev_ptr, n_rows, pitch)
     plist = [lay.parents(i) for i in range(lay.n)]
     return BayesNet(_cpds_from_counts(lay.names, plist, lay.card, _split(lay, counts)))
+
+
+# ------------------------------------------------------------------------------------------------ data likelihood
+def logpdf(bn: BayesNet, data, device=None) -> float:
+    """logpdf(bn, assignment) (src/bayes_nets.jl:322-328) or logpdf(bn, df::DataFrame)
+    (ProbabilisticGraphicalModels.jl:83-99): sum over rows of sum over nodes of log P(x_i | pa_i).  Columns are taken
+    BY NAME (`a[name] = df[i, name]`, :91); extra columns are ignored, a missing one raises KeyError.  A value outside
+    1:ncategories gives pdf 0 for its own node (-> -Inf) but is a BoundsError as a parent (categorical_cpd.jl:36-46)."""
+    if isinstance(data, dict):
+        return bn.logpdf(data)
+    from .device_layout import device_net
+    net = device_net(bn, default_device() if device is None else device)
+    lay = net.layout
+    mat = _matrix_from_frame(data, lay.names)
+    if mat.shape[0] == 0 or mat.shape[1] == 0:
+        return 0.0
+    card = np.asarray(lay.card)
+    bad = (mat < 1) | (mat > card[:, None])
+    if bad.any():
+        is_parent = np.zeros(lay.n, bool)
+        is_parent[np.asarray(lay.par_idx[:lay.par_ptr[-1]], np.int64)] = True
+        if bad[is_parent].any():
+            raise IndexError("BoundsError: a parent's value lies outside 1:ncategories")
+        return -math.inf
+    if (card > 255).any():
+        raise NotImplementedError("more than 255 states per variable")
+    table = np.ascontiguousarray(mat - 1, np.uint8)
+    out = np.zeros(1, np.float64)
+    check(_lib.lib().bn_logpdf(_lib.h64(net.handle), ptr(table, _lib.u8p), C.c_uint64(table.shape[1]), ptr(out, _lib.f64p)))
+    return float(out[0])
+
+
+def pdf(bn: BayesNet, data, device=None) -> float:
+    """pdf(bn, assignment) (src/bayes_nets.jl:311-317) or pdf(bn, df) = exp(logpdf(bn, df)) (:104)."""
+    if isinstance(data, dict):
+        return bn.pdf(data)
+    return math.exp(logpdf(bn, data, device=device))
+
+
+def logpdf_device(bn_or_net, states_dev_ptr: int, n_rows: int, pitch: int | None = None, out_dev_ptr: int | None = None):
+    """Log-likelihood of a DEVICE-resident uint8 node-major table (what bn_sample_dev writes) under the network:
+    returns the value, or enqueues it into `out_dev_ptr` (one double) and returns None without synchronising."""
+    from .device_layout import device_net
+    net = bn_or_net if isinstance(bn_or_net, DeviceNet) else device_net(bn_or_net)
+    pitch = n_rows if pitch is None else pitch
+    if out_dev_ptr is not None:
+        check(_lib.lib().bn_logpdf_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
+                                       C.c_uint64(pitch), C.c_void_p(out_dev_ptr)))
+        return None
+    import torch  # plumbing only: a device buffer for the result
+    out = torch.empty(1, dtype=torch.float64, device=f"cuda:{net.device}")
+    _lib.set_stream(torch.cuda.current_stream(net.device).cuda_stream)
+    check(_lib.lib().bn_logpdf_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
+                                   C.c_uint64(pitch), C.c_void_p(out.data_ptr())))
+    return float(out.cpu()[0])

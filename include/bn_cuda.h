@@ -220,6 +220,17 @@ int32_t bn_statistics(bn_net_t net, const uint8_t* states, uint64_t n_rows, int6
 int32_t bn_statistics_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_rows, uint64_t pitch,
                           int64_t* out_counts_dev);
 
+/* ---- logpdf(bn, df::DataFrame) / pdf(bn, df): src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-104
+ *      over logpdf(bn, assignment), src/bayes_nets.jl:322-328 ---------------------------------------------------
+ * Log-likelihood of a data table under `net`: sum over rows and nodes of log P(x_i | pa_i).  Same table layout and
+ * 0xFF-row rule as bn_statistics.  Computed as sum_b N[b] * log(cpt[b]) over the bins with N[b] > 0, N = the table's
+ * sufficient statistics (one pass of the counting kernel, then one small deterministic reduction); a row the net
+ * gives probability 0 makes the result -Inf, as in the reference.  Zero rows -> 0.0.  bn_logpdf validates
+ * states < card (BN_BOUNDS); the _dev variant trusts the table, writes one double to out_logl_dev and enqueues on
+ * the current stream. */
+int32_t bn_logpdf(bn_net_t net, const uint8_t* states, uint64_t n_rows, double* out_logl);
+int32_t bn_logpdf_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_rows, uint64_t pitch, double* out_logl_dev);
+
 /* ---- infer(::LoopyBelief, ::InferenceState): src/Inference/loopy_belief.jl:24-218 -------------------------
  * Loopy belief propagation, batched: instance b has evidence row evidence[b * n_nodes .. ] (NULL = no evidence
  * anywhere) and ONE query node query[b] (:26); all instances run concurrently, one warp each, messages

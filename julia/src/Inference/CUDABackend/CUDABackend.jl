@@ -435,3 +435,32 @@ function cuda_statistics(bn::DiscreteBayesNet, data::AbstractMatrix{<:Integer})
     end
     return [reshape(counts[lay.cpt_off[i]+1:lay.cpt_off[i+1]], Int(lay.card[i]), :) for i in 1:n]
 end
+
+# ---------------------------------------------------------------------------------------------------------------
+# logpdf(bn, df) / pdf(bn, df) on the device
+#                      replaces src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-104 for a DiscreteBayesNet
+# The reference adds log P(x_i | pa_i) row by row; the device counts the table once (bn_statistics' kernel) and
+# returns sum_b N[b] * log(cpt[b]).  Columns are taken by name like `a[name] = df[i, name]` (:91).
+function cuda_logpdf(bn::DiscreteBayesNet, df::DataFrame)
+    net = device_net(bn)
+    lay = net.layout
+    n, m = length(lay.names), nrow(df)
+    states = Matrix{UInt8}(undef, m, n)                    # node-major on the device = one column per node
+    isparent = falses(n); isparent[lay.par_idx .+ 1] .= true
+    impossible = false
+    for (i, name) in enumerate(lay.names), r in 1:m
+        x = df[r, name]
+        if !(1 <= x <= lay.card[i])                        # pdf(Categorical, x) = 0 outside the support ...
+            isparent[i] && throw(BoundsError(1:lay.card[i], x))   # ... but a parent's value indexes the CPT (categorical_cpd.jl:36-46)
+            impossible = true; x = 1
+        end
+        states[r, i] = UInt8(x - 1)
+    end
+    impossible && return -Inf
+    out = Ref{Float64}(0.0)
+    GC.@preserve states begin
+        _bn_check(ccall((:bn_logpdf, libbn_cuda), Int32, (UInt64, Ptr{UInt8}, UInt64, Ref{Float64}), net.handle, states, m, out))
+    end
+    return out[]
+end
+cuda_pdf(bn::DiscreteBayesNet, df::DataFrame) = exp(cuda_logpdf(bn, df))

@@ -706,6 +706,35 @@ int orc_statistics(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * logpdf(bn, df::DataFrame): src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-99 -- `logl = 0.0`,
+ * then for each row in order `logl += logpdf(bn, a)`, where logpdf(bn, a) (src/bayes_nets.jl:322-328) starts at 0.0
+ * and adds logpdf(cpd, a) = log(cpd(a).p[a[name]]) for the cpds in topological order (src/CPDs/cpds.jl:110,
+ * CPT row = src/CPDs/categorical_cpd.jl:36-46).  Same order of additions here, single thread; rows whose first byte
+ * is 0xFF are skipped as in orc_statistics.  pdf(bn, df) = exp(logpdf(bn, df)) (:104).
+ * ---------------------------------------------------------------------------------------- */
+int orc_logpdf_table(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                     const int64_t* cpt_off, const double* cpt, const uint8_t* data, uint64_t n_rows, uint64_t pitch,
+                     double* out) {
+  double logl = 0.0;
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    if (data[r] == 0xFF) continue;
+    double row = 0.0;
+    for (int i = 0; i < n_nodes; ++i) {
+      int64_t j = 0, stride = 1;
+      for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) {
+        const int p = par_idx[k];
+        j += stride * data[(uint64_t)p * pitch + r];
+        stride *= card[p];
+      }
+      row += log(cpt[cpt_off[i] + data[(uint64_t)i * pitch + r] + (int64_t)card[i] * j]);
+    }
+    logl += row;
+  }
+  *out = logl;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Loopy belief propagation: infer(::LoopyBelief), src/Inference/loopy_belief.jl:24-218, one (query, evidence)
  * instance after the other (OpenMP over instances).  Second restatement beside oracle/loopy_np.py: the numpy one keeps
  * the reference's array aliasing literally; this one states its CONSEQUENCES explicitly --

@@ -250,6 +250,21 @@ def statistics(net, data, n_rows=None, pitch=None):
     return out
 
 
+def logpdf_table(net, data, n_rows=None, pitch=None) -> float:
+    """logpdf(bn, df): src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-99 (row by row, node by
+    node, same order of additions as the reference).  data: uint8 [n_nodes, pitch] node-major, 0-based states."""
+    args, keep = _net_args(net)
+    d = np.ascontiguousarray(data, np.uint8)
+    if d.ndim == 2:
+        assert d.shape[0] == int(np.asarray(net.card).size)
+        pitch = d.shape[1] if pitch is None else pitch
+        n_rows = d.shape[1] if n_rows is None else n_rows
+    out = np.zeros(1, np.float64)
+    rc = lib().orc_logpdf_table(*args, _p(d, C.c_uint8), C.c_uint64(n_rows), C.c_uint64(pitch), _p(out, C.c_double))
+    assert rc == 0
+    return float(out[0])
+
+
 def loopy_infer(net, queries, evidences=None, nsamples=500, tol=1e-8, iters_for_convergence=6):
     """src/Inference/loopy_belief.jl:24-218 for a batch of (query node index, evidence row) instances (OpenMP over
     instances) -> (beliefs [n_inst, max_card] zero-padded, iterations [n_inst]).  The C restatement spells out the

@@ -174,3 +174,135 @@ def test_statistics_many_parents_and_empty_tables(bn, n_rows):
         ref = capi.statistics(oracle_net_from_layout(lay), table, n_rows=n_rows, pitch=max(n_rows, 1)) if n_rows else \
             np.zeros_like(out)
         assert np.array_equal(out, ref), (wide, n_rows)
+
+
+# ------------------------------------------------------------------------------------------ logpdf(bn, df)
+# Tolerance: the oracle adds n_rows x n_nodes logs one after the other like the reference (rounding error grows with
+# the number of terms, ~sqrt(terms) * 1e-16 relative); the device adds a few thousand count-weighted terms.  Both are
+# held to 1e-12 relative of each other at the sizes below (<= 3e7 terms) and the device value to 1e-13 of an exactly
+# rounded sum (math.fsum) of the same count-weighted terms.
+def _exact_logl(lay, table):
+    import math
+    counts = capi.statistics(oracle_net_from_layout(lay), table)
+    return math.fsum(int(c) * math.log(p) for c, p in zip(counts, np.asarray(lay.cpt)) if c)
+
+
+def test_logpdf_reference_values(bn, golden, tmp_path):
+    """pdf / logpdf through the public API on the reference's XDSL net (test/test_io.jl:13-18 joint values)."""
+    import math
+    from test_host import write_xdsl
+    path = str(tmp_path / "sample_bn.xdsl")
+    write_xdsl(path, golden)
+    net = bn.readxdsl(path)
+    rows = golden["xdsl"]["joint_1based"]
+    for s, f, p in rows:
+        assert bn.pdf(net, {"Success": s, "Forecast": f}) == pytest.approx(p, rel=1e-14)
+        assert bn.logpdf(net, {"Success": s, "Forecast": f}) == pytest.approx(math.log(p), rel=1e-14)
+        one = pd.DataFrame({"Success": [s], "Forecast": [f]})
+        assert bn.logpdf(net, one) == pytest.approx(math.log(p), rel=1e-14)
+        assert bn.pdf(net, one) == pytest.approx(p, rel=1e-13)
+    df = pd.DataFrame({"Forecast": [f for _, f, _ in rows] * 3, "extra": 0, "Success": [s for s, _, _ in rows] * 3})
+    want = 3 * math.fsum(math.log(p) for _, _, p in rows)
+    assert bn.logpdf(net, df) == pytest.approx(want, rel=1e-14)  # columns by name, extra column ignored
+    assert bn.pdf(net, df) == pytest.approx(math.exp(want), rel=1e-12)
+    assert bn.logpdf(net, df.iloc[:0]) == 0.0
+    with pytest.raises(KeyError):
+        bn.logpdf(net, df[["Success"]])
+    # a leaf value outside its support has pdf 0 (-> -Inf); as a parent it is a BoundsError
+    leaf = [n for n in net.names() if not net.children(n)][0]
+    root = [n for n in net.names() if net.children(n)][0]
+    bad = df.copy()
+    bad.loc[2, leaf] = 9
+    assert bn.logpdf(net, bad) == -math.inf and bn.pdf(net, bad) == 0.0
+    bad = df.copy()
+    bad.loc[2, root] = 9
+    with pytest.raises(IndexError):
+        bn.logpdf(net, bad)
+
+
+@pytest.mark.parametrize("seed,n_nodes,n_rows", [(0, 12, 1), (1, 30, 1000), (2, 100, 4096), (3, 100, 50_001),
+                                                 (4, 200, 150_017), (5, 7, 2_000_003)])
+def test_logpdf_host_table_equals_oracle(bn, seed, n_nodes, n_rows):
+    """Random nets, tables sampled from the net by the oracle (so no zero-probability rows), through bn_logpdf."""
+    from bayesnets_jl_b200 import _lib
+    net = bn.rand_discrete_bn(n_nodes, 3, 5, seed=seed)
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    table, _, _ = capi.sample(on, n_rows, seed=seed + 20)
+    dn = bn.device_net(net)
+    out = np.zeros(1)
+    _lib.check(_lib.lib().bn_logpdf(_lib.h64(dn.handle), _lib.ptr(table, _lib.u8p), C.c_uint64(n_rows), _lib.ptr(out, _lib.f64p)))
+    assert np.isfinite(out[0]) and out[0] < 0
+    assert out[0] == pytest.approx(capi.logpdf_table(on, table), rel=1e-12)
+    assert out[0] == pytest.approx(_exact_logl(lay, table), rel=1e-13)
+    # the DataFrame front end (1-based states, by name) gives the same value
+    if n_rows <= 50_001:
+        df = pd.DataFrame({nm: table[i].astype(np.int64) + 1 for i, nm in enumerate(lay.names)})
+        assert bn.logpdf(net, df) == out[0]
+    bad = table.copy()
+    bad[min(3, n_nodes - 1), n_rows // 2] = 250
+    with pytest.raises(IndexError):
+        _lib.check(_lib.lib().bn_logpdf(_lib.h64(dn.handle), _lib.ptr(bad, _lib.u8p), C.c_uint64(n_rows), _lib.ptr(out, _lib.f64p)))
+
+
+def test_logpdf_zero_probability_rows_and_empty_table(bn):
+    """A row the net gives probability 0 makes the sum -Inf (log(0) in the reference's loop); bins with cpt = 0 that
+    no row visits contribute nothing; zero rows give 0.0."""
+    import math
+    from bayesnets_jl_b200 import _lib
+    a = bn.DiscreteCPD("a", [0.5, 0.5, 0.0])
+    b = bn.DiscreteCPD("b", ["a"], [3], [[1.0, 0.0], [0.25, 0.75], [0.5, 0.5]])
+    net = bn.BayesNet([a, b])
+    ok = pd.DataFrame({"a": [1, 2, 2, 1], "b": [1, 2, 1, 1]})
+    assert bn.logpdf(net, ok) == pytest.approx(4 * math.log(0.5) + math.log(0.75) + math.log(0.25), rel=1e-14)
+    assert bn.logpdf(net, pd.DataFrame({"a": [1, 2, 1], "b": [1, 2, 2]})) == -math.inf  # P(b=2 | a=1) = 0
+    assert bn.logpdf(net, pd.DataFrame({"a": [3], "b": [1]})) == -math.inf            # P(a=3) = 0
+    assert bn.pdf(net, pd.DataFrame({"a": [3], "b": [1]})) == 0.0
+    dn = bn.device_net(net)
+    out = np.full(1, 7.0)
+    _lib.check(_lib.lib().bn_logpdf(_lib.h64(dn.handle), None, C.c_uint64(0), _lib.ptr(out, _lib.f64p)))
+    assert out[0] == 0.0
+
+
+def test_sample_then_logpdf_on_device(bn):
+    """rand(bn, n) left in HBM -> bn_logpdf_dev: equals the oracle on the same table (aligned and unaligned row
+    counts, pitched table), skips rejection-failed rows, and -logl / n_rows estimates the net's entropy."""
+    import torch
+    from bayesnets_jl_b200 import _lib
+    net = bn.rand_discrete_bn(40, 3, 4, seed=3)
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    dn = bn.device_net(net)
+    L = _lib.lib()
+    _lib.set_stream(torch.cuda.current_stream(0).cuda_stream)
+    per_row = []
+    for n_rows in (1 << 19, (1 << 17) + 5):
+        tab = torch.empty((lay.n, n_rows), dtype=torch.uint8, device="cuda:0")
+        _lib.check(L.bn_sample_dev(_lib.h64(dn.handle), None, C.c_int32(0), C.c_int32(1), C.c_uint64(0), C.c_uint64(n_rows),
+                                   C.c_uint64(11), C.c_void_p(tab.data_ptr()), None, None))
+        got = bn.logpdf_device(net, tab.data_ptr(), n_rows)
+        host = tab.cpu().numpy()
+        assert got == pytest.approx(capi.logpdf_table(on, host), rel=1e-12)
+        assert got == pytest.approx(_exact_logl(lay, host), rel=1e-13)
+        per_row.append(got / n_rows)
+        # enqueue-only form writes the same double into a caller's device buffer
+        out = torch.zeros(1, dtype=torch.float64, device="cuda:0")
+        assert bn.logpdf_device(net, tab.data_ptr(), n_rows, out_dev_ptr=out.data_ptr()) is None
+        assert float(out.cpu()[0]) == got
+    assert per_row[0] == pytest.approx(per_row[1], rel=5e-3)  # both estimate -H(bn)
+    # pitched table: rows 0..n_rows-1 of a wider allocation
+    n_rows, pitch = 10_000, 10_240
+    wide = torch.zeros((lay.n, pitch), dtype=torch.uint8, device="cuda:0")
+    wide[:, :n_rows] = tab[:, :n_rows]
+    got = bn.logpdf_device(net, wide.data_ptr(), n_rows, pitch=pitch)
+    assert got == pytest.approx(capi.logpdf_table(on, np.ascontiguousarray(tab[:, :n_rows].cpu().numpy())), rel=1e-12)
+    # rejection sampling with evidence that sometimes fails: failed rows (0xFF) are not part of the likelihood
+    ev = lay.evidence_vector({lay.names[5]: 1, lay.names[17]: 2})
+    n_rows = 1 << 16
+    tab = torch.empty((lay.n, n_rows), dtype=torch.uint8, device="cuda:0")
+    ok = torch.empty(n_rows, dtype=torch.uint8, device="cuda:0")
+    _lib.check(L.bn_sample_dev(_lib.h64(dn.handle), _lib.ptr(ev, _lib.i8p), C.c_int32(1), C.c_int32(2), C.c_uint64(0),
+                               C.c_uint64(n_rows), C.c_uint64(5), C.c_void_p(tab.data_ptr()), None, C.c_void_p(ok.data_ptr())))
+    assert 0 < int(ok.sum().item()) < n_rows
+    got = bn.logpdf_device(net, tab.data_ptr(), n_rows)
+    assert got == pytest.approx(capi.logpdf_table(on, tab.cpu().numpy()), rel=1e-12)

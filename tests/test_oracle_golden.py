@@ -181,6 +181,43 @@ def test_xdsl_joint_and_posteriors(golden):
     np.testing.assert_allclose(exact_infer(net, "Success", {"Forecast": 2}).potential, [1 / 13, 12 / 13], rtol=1e-14)
 
 
+def test_logpdf_table_on_xdsl_joint(golden):
+    """logpdf(bn, df) restatement (ProbabilisticGraphicalModels.jl:83-99) against the six pdf(bn, ...) products of
+    test/test_io.jl:13-18: a table holding those six assignments has log-likelihood sum(log(p)); single rows give
+    log(p) each; a table that repeats rows adds them; zero rows give 0.0."""
+    import math
+    net = xdsl_net(golden)
+    idx = {n: i for i, n in enumerate(net.names)}
+    rows = golden["xdsl"]["joint_1based"]
+    tab = np.zeros((2, len(rows)), np.uint8)
+    for r, (s, f, p) in enumerate(rows):
+        tab[idx["Success"], r], tab[idx["Forecast"], r] = s - 1, f - 1
+        one = np.ascontiguousarray(tab[:, r:r + 1])
+        assert capi.logpdf_table(net, one) == pytest.approx(math.log(p), rel=1e-14)
+    want = math.fsum(math.log(p) for _, _, p in rows)
+    assert capi.logpdf_table(net, tab) == pytest.approx(want, rel=1e-14)
+    assert capi.logpdf_table(net, np.tile(tab, (1, 7))) == pytest.approx(7 * want, rel=1e-13)
+    assert capi.logpdf_table(net, tab[:, :0], n_rows=0, pitch=16) == 0.0
+    # rows marked 0xFF in their first byte are skipped, like orc_statistics
+    marked = tab.copy()
+    marked[0, 2] = 0xFF
+    assert capi.logpdf_table(net, marked) == pytest.approx(want - math.log(rows[2][2]), rel=1e-14)
+
+
+def test_logpdf_table_equals_counts_dot_log_cpt():
+    """The identity the device path uses: sum over rows of log P(row) = sum_b N[b] * log(cpt[b]) over bins seen."""
+    import math
+    rng = np.random.default_rng(5)
+    nodes = [["a", [], [[0.2, 0.5, 0.3]]], ["b", ["a"], [[0.1, 0.9], [0.6, 0.4], [0.5, 0.5]]],
+             ["c", ["a", "b"], [list(rng.dirichlet(np.ones(4))) for _ in range(6)]]]
+    net = net_from(nodes)
+    tab, _, _ = capi.sample(net, 5000, seed=3)
+    counts = capi.statistics(net, tab)
+    cpt = np.asarray(net.cpt)
+    want = math.fsum(int(c) * math.log(p) for c, p in zip(counts, cpt) if c)
+    assert capi.logpdf_table(net, tab) == pytest.approx(want, rel=1e-12)
+
+
 def test_exact_matches_enumeration_on_asia_and_student(golden):
     asia = net_from(golden["asia"]["nodes"])
     np.testing.assert_allclose(exact_infer(asia, "T", {"X": 1}).potential, [0.907589116841376, 0.092410883158624], rtol=1e-12)

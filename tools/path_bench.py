@@ -147,7 +147,28 @@ def main():
                 "gpu": n_rows / (ms * 1e-3), "gpu_ms": ms, "hbm_read_GBs": n_rows * lay.n / (ms * 1e-3) / 1e9,
                 "cpu": {"value": n_cpu / dt, "cores": cores, "kind": "port", "sample": f"{n_cpu} rows (OpenMP over nodes)"},
                 "check": f"counts of the first {n_cpu} rows identical to the oracle: {same}"})
-    del st, w, ok, cnt
+    # ---- f5 logpdf(bn, df): the table's log-likelihood = its counts . log CPTs (counting kernel + one small reduction)
+    ll = torch.empty(1, dtype=torch.float64, device="cuda:0")
+
+    def fn_logpdf():
+        _lib.check(L.bn_logpdf_dev(_lib.h64(dn.handle), C.c_void_p(st.data_ptr()), C.c_uint64(n_rows), C.c_uint64(n_rows),
+                                   C.c_void_p(ll.data_ptr())))
+    ms = ev_time(torch, fn_logpdf)
+    capi.logpdf_table(on, host_tab)
+    t0 = time.perf_counter()
+    lref = capi.logpdf_table(on, host_tab)
+    dt = time.perf_counter() - t0
+    _lib.check(L.bn_logpdf_dev(_lib.h64(dn.handle), C.c_void_p(st.data_ptr()), C.c_uint64(n_cpu), C.c_uint64(n_rows),
+                               C.c_void_p(ll.data_ptr())))
+    lgot = float(ll.cpu()[0])
+    out.append({"row": "f5", "api": "logpdf(bn, df): data log-likelihood of a table",
+                "cite": "src/ProbabilisticGraphicalModels/ProbabilisticGraphicalModels.jl:83-104, src/bayes_nets.jl:322-328",
+                "config": f"C2 net, device-resident {n_rows} rows x {lay.n} nodes (uint8) from rand(bn, n)", "unit": "rows/s",
+                "gpu": n_rows / (ms * 1e-3), "gpu_ms": ms, "hbm_read_GBs": n_rows * lay.n / (ms * 1e-3) / 1e9,
+                "cpu": {"value": n_cpu / dt, "cores": 1, "kind": "port",
+                        "sample": f"{n_cpu} rows (row-by-row sum like the reference, one thread)"},
+                "check": f"first {n_cpu} rows: device {lgot!r} vs oracle {lref!r}, rel diff {abs(lgot - lref) / abs(lref):.2e}"})
+    del st, w, ok, cnt, ll
 
     # ---- a8 gibbs_sample: 4096 chains x 16 kept samples, burn-in 50 sweeps, thinning 1 (C2 net)
     nch, ns, bi, th = (4096, 16, 50, 1) if not a.quick else (256, 4, 10, 1)
