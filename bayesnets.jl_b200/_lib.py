@@ -66,6 +66,9 @@ _SIGS = {
     "bn_factor_product": (C.c_int32, [h64, h64, C.POINTER(h64)]),
     "bn_factor_sum": (C.c_int32, [h64, i32p, C.c_int32, C.POINTER(h64)]),
     "bn_factor_slice": (C.c_int32, [h64, i32p, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_setindex": (C.c_int32, [h64, i32p, i32p, C.c_int32, f64p, C.c_int64]),
+    "bn_factor_permutedims": (C.c_int32, [h64, i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_factor_push": (C.c_int32, [h64, C.c_int32, C.c_int32, C.POINTER(h64)]),
     "bn_factor_normalize": (C.c_int32, [h64, C.c_int32]),
     "bn_factor_norm": (C.c_int32, [h64, C.c_int32, f64p]),
     "bn_factor_div_scalar": (C.c_int32, [h64, C.c_double]),

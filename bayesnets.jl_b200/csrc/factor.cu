@@ -976,6 +976,61 @@ int32_t bn_factor_slice(bn_factor_t h, const int32_t* dims, const int32_t* state
   return BN_OK;
 }
 
+// permutedims(phi, perm): src/Factors/factors_main.jl:160-166.  out.dims[i] = phi.dims[perm[i]] (0-based positions):
+// a 1-operand contraction whose output dim order is the permuted one (a strided gather on the read side, coalesced
+// 128-bit stores on the write side).
+int32_t bn_factor_permutedims(bn_factor_t h, const int32_t* perm, int32_t n, bn_factor_t* out) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out && (perm || n == 0), BN_BAD_ARG, "bn_factor_permutedims: bad arguments");
+  BN_REQUIRE(n == (int32_t)f->dims.size(), BN_BAD_ARG, "no valid permutation of dimensions (%d entries for %zu dims)", n,
+             f->dims.size());
+  std::vector<char> seen((size_t)n, 0);
+  std::vector<int32_t> od, oc;
+  bool identity = true;
+  for (int i = 0; i < n; ++i) {
+    BN_REQUIRE(perm[i] >= 0 && perm[i] < n && !seen[(size_t)perm[i]], BN_BAD_ARG, "no valid permutation of dimensions");
+    seen[(size_t)perm[i]] = 1;
+    identity = identity && perm[i] == i;
+    od.push_back(f->dims[(size_t)perm[i]]);
+    oc.push_back(f->card[(size_t)perm[i]]);
+  }
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  Factor* o = nullptr;
+  BN_TRY(new_factor(od, oc, f->device, &o));
+  int32_t rc = BN_OK;
+  if (identity || f->len <= 1) {
+    cudaError_t e = cudaMemcpyAsync(o->data.p, f->data.p, (size_t)f->len * 8, cudaMemcpyDeviceToDevice, tl_stream);
+    if (e != cudaSuccess) { delete o; BN_CUDA_TRY(e); }
+  } else {
+    rc = contract(f->device, {Operand{f->data.p, f->dims, f->card}}, od, oc, {}, {}, o->data.p);
+  }
+  if (rc != BN_OK) { delete o; return rc; }
+  *out = register_factor(o);
+  return BN_OK;
+}
+
+// push!(phi, dim, length): src/Factors/factors_main.jl:148-158 over duplicate (auxiliary.jl:50-65) -- a new LAST
+// dimension along which the whole table is repeated: a 1-operand contraction with an output dim the operand lacks
+// (stride 0), so the operand is read once per tile and stored `length` times.
+int32_t bn_factor_push(bn_factor_t h, int32_t dim, int32_t length, bn_factor_t* out) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && out, BN_BAD_ARG, "bn_factor_push: bad arguments");
+  BN_REQUIRE(find_dim(f->dims, dim) < 0, BN_BAD_ARG, "Dimension %d already exists", dim);
+  BN_REQUIRE(length >= 1, BN_BAD_ARG, "bn_factor_push: length %d", length);
+  BN_REQUIRE(f->len * (long long)length < (1ll << 31), BN_UNSUPPORTED, "factor with %lld entries (max 2^31 - 1)",
+             f->len * (long long)length);
+  std::vector<int32_t> od = f->dims, oc = f->card;
+  od.push_back(dim);
+  oc.push_back(length);
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  Factor* o = nullptr;
+  BN_TRY(new_factor(od, oc, f->device, &o));
+  int32_t rc = contract(f->device, {Operand{f->data.p, f->dims, f->card}}, od, oc, {}, {}, o->data.p);
+  if (rc != BN_OK) { delete o; return rc; }
+  *out = register_factor(o);
+  return BN_OK;
+}
+
 // norm pass shared by normalize! and the split-factor entry points: total (device) = sum |x|^p, deterministic
 static int32_t norm_total(Factor* f, int32_t pnorm, double** total_dev, int* grid_out) {
   const long long grid_ll = std::max<long long>(1, (f->len / 2 + NORM_CHUNK - 1) / NORM_CHUNK);

@@ -84,6 +84,20 @@ __global__ void __launch_bounds__(GTHR) reduce_kernel(const GatherParams p) {
   }
 }
 
+// setindex!(phi, v, assignment): phi[slab] = v (one value) or .= v (an array over the slab, column-major).
+// o runs over the slab's cells; sa = strides of phi along the free dims, base = offset of the pinned states.
+__global__ void __launch_bounds__(GTHR) slab_store_kernel(const GatherParams p, long long base, double scalar) {
+  for (long long o = (long long)blockIdx.x * GTHR + threadIdx.x; o < p.n_out; o += (long long)gridDim.x * GTHR) {
+    long long r = o, off = base;
+    for (int d = 0; d < p.nd; ++d) {
+      const long long q = r / p.card[d];
+      off += (r - q * p.card[d]) * p.sa[d];
+      r = q;
+    }
+    p.out[off] = p.b ? p.b[o] : scalar;
+  }
+}
+
 int find(const std::vector<int32_t>& v, int32_t x) {
   for (size_t i = 0; i < v.size(); ++i)
     if (v[i] == x) return (int)i;
@@ -283,6 +297,53 @@ int32_t bn_factor_broadcast(bn_factor_t h, const int32_t* dims, int32_t n, const
     at += (size_t)value_len[j];
   }
   BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));  // `values` is a host buffer the caller may reuse
+  return BN_OK;
+}
+
+// setindex!(phi, v, a::Assignment): src/Factors/factors_access.jl:39-46 with _translate_index (:48-72): dims of the
+// assignment that phi lacks are ignored, unassigned dims are Colons.  n_values == 1 stores one value into every cell of
+// the slab (`phi.potential[idx...] = v` / `.= v`), n_values == the slab's size stores an array over the free dims in
+// column-major order (`.= v` with an array of the slab's shape); anything else is the DimensionMismatch `.=` throws.
+int32_t bn_factor_setindex(bn_factor_t h, const int32_t* dims, const int32_t* states, int32_t n_assign,
+                           const double* values, int64_t n_values) {
+  Factor* f = get_factor(h);
+  BN_REQUIRE(f && values && n_values >= 1, BN_BAD_ARG, "bn_factor_setindex: bad arguments");
+  BN_REQUIRE(n_assign == 0 || (dims && states), BN_BAD_ARG, "bn_factor_setindex: NULL assignment");
+  const std::vector<long long> fst = strides_of(f->card);
+  long long base = 0, slab = 1;
+  std::vector<int32_t> fc;
+  std::vector<long long> fs, zero;
+  for (size_t i = 0; i < f->dims.size(); ++i) {
+    int hit = -1;
+    for (int j = 0; j < n_assign; ++j) if (dims[j] == f->dims[i]) hit = j;
+    if (hit >= 0) {
+      BN_REQUIRE(states[hit] >= 0 && states[hit] < f->card[i], BN_BOUNDS, "BoundsError: state %d for dim %d (size %d)",
+                 states[hit], f->dims[i], f->card[i]);
+      base += fst[i] * states[hit];
+    } else {
+      fc.push_back(f->card[i]);
+      fs.push_back(fst[i]);
+      zero.push_back(0);
+      slab *= f->card[i];
+    }
+  }
+  BN_REQUIRE(n_values == 1 || n_values == slab, BN_DIM_MISMATCH,
+             "DimensionMismatch: cannot broadcast %lld values into a slab of %lld cells", (long long)n_values, slab);
+  BN_REQUIRE((int)fc.size() <= GD, BN_UNSUPPORTED, "factor op over %zu variables (max %d)", fc.size(), GD);
+  BN_CUDA_TRY(cudaSetDevice(f->device));
+  GatherParams p{};
+  p.nd = push_dims(p, 0, fc, fs, zero);
+  p.n_out = slab;
+  p.out = f->data.p;
+  TmpBuf<double> vals;
+  if (n_values > 1) {
+    BN_CUDA_TRY(vals.upload(values, (size_t)n_values, tl_stream));
+    p.b = vals.p;
+  }
+  slab_store_kernel<<<grid_for(f->device, slab), GTHR, 0, tl_stream>>>(p, base, values[0]);
+  count_launch();
+  BN_CUDA_TRY(cudaGetLastError());
+  if (n_values > 1) BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));  // `values` is a host buffer the caller may reuse
   return BN_OK;
 }
 

@@ -265,6 +265,84 @@ class Factor:
             return float(self.potential.reshape(-1, order="F")[a - 1])
         return self.pattern(a)
 
+    # -- phi[assignment] = v (setindex!, factors_access.jl:39-46) -----------------------------------
+    def __setitem__(self, a, v) -> None:
+        if not isinstance(a, dict):
+            raise TypeError("Factor[...] = v takes an Assignment (dict)")
+        dims, states, free = [], [], []
+        for i, d in enumerate(self.dimensions):
+            if d in a and not (a[d] is Ellipsis or (isinstance(a[d], slice) and a[d] == slice(None))):
+                x = a[d]
+                if not isinstance(x, (int, np.integer)) or isinstance(x, bool):
+                    raise TypeError(f"Invalid state for dimension {d}")
+                if x < 1 or x > self._shape[i]:
+                    raise IndexError(f"BoundsError({d}, {x})")
+                dims.append(var_id(d))
+                states.append(int(x) - 1)
+            else:
+                free.append(self._shape[i])
+        vals = np.asarray(v, np.float64)
+        if vals.ndim > 0:  # `.= v`: an array broadcasts over the slab; accepted here: a scalar-like or the slab's shape
+            if vals.size != 1 and tuple(x for x in vals.shape if x != 1) != tuple(x for x in free if x != 1):
+                raise DimensionMismatch(f"array could not be broadcast to match destination: {vals.shape} into {tuple(free)}")
+        flat = np.ascontiguousarray(vals.reshape(-1, order="F"))
+        di = np.array(dims if dims else [0], np.int32)
+        si = np.array(states if states else [0], np.int32)
+        check(_lib.lib().bn_factor_setindex(_lib.h64(self.handle), ptr(di, _lib.i32p), ptr(si, _lib.i32p),
+                                            C.c_int32(len(dims)), ptr(flat, _lib.f64p), C.c_int64(flat.size)))
+
+    # -- in-place variants rebind the device table, as the reference rebinds phi.potential ----------
+    def _replace(self, other: "Factor") -> "Factor":
+        if self._fin is not None:
+            self._fin()  # frees the old table
+        h = other.handle
+        other._fin.detach()
+        self._adopt(h)
+        return self
+
+    def permutedims(self, perm) -> "Factor":
+        """permutedims(phi, perm) (factors_main.jl:160-166); perm holds 1-based positions like Julia's."""
+        perm = [int(x) for x in perm]
+        if sorted(perm) != list(range(1, len(self.dimensions) + 1)):
+            raise ValueError("no valid permutation of dimensions")  # Base.permutedims: ArgumentError
+        pi = np.array([x - 1 for x in perm] if perm else [0], np.int32)
+        h = _lib.h64(0)
+        check(_lib.lib().bn_factor_permutedims(_lib.h64(self.handle), ptr(pi, _lib.i32p), C.c_int32(len(perm)), C.byref(h)))
+        return Factor._from_handle(h)
+
+    def permutedims_(self, perm) -> "Factor":
+        return self._replace(self.permutedims(perm))
+
+    def push_(self, dim, length: int) -> "Factor":
+        """push!(phi, dim, length) (factors_main.jl:148-158): appends a dimension along which the table repeats."""
+        if dim in self.dimensions:
+            raise RuntimeError(f"Dimension {dim} already exists")  # error(...), :150
+        h = _lib.h64(0)
+        check(_lib.lib().bn_factor_push(_lib.h64(self.handle), C.c_int32(var_id(dim)), C.c_int32(int(length)), C.byref(h)))
+        return self._replace(Factor._from_handle(h))
+
+    def sum_(self, dims) -> "Factor":      # sum!, prod!, maximum!, minimum! (factors_dims.jl:87-107)
+        return self._replace(self.sum(dims))
+
+    def prod_(self, dims) -> "Factor":
+        return self._replace(self.prod(dims))
+
+    def maximum_(self, dims) -> "Factor":
+        return self._replace(self.maximum(dims))
+
+    def minimum_(self, dims) -> "Factor":
+        return self._replace(self.minimum(dims))
+
+    def similar(self) -> "Factor":
+        """similar(phi) (factors_main.jl:93): same dims and sizes, contents unspecified (zeros here)."""
+        return Factor(self.dimensions, list(self._shape))
+
+    def indexin(self, dims):
+        """indexin(dim(s), phi) (factors_main.jl:134-135): 1-based positions, None where absent."""
+        if isinstance(dims, (str, bytes)) or not isinstance(dims, Iterable):
+            return self.dimensions.index(dims) + 1 if dims in self.dimensions else None
+        return [self.dimensions.index(d) + 1 if d in self.dimensions else None for d in dims]
+
     # -- broadcast(*, phi, dims, values) (factors_dims.jl:130-168): a product with 1-d factors ----
     def broadcast_mul(self, dims, values) -> "Factor":
         if isinstance(dims, (str, bytes)) or not isinstance(dims, Iterable):

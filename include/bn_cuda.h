@@ -171,6 +171,16 @@ int32_t bn_factor_sum(bn_factor_t f, const int32_t* sum_dims, int32_t n_sum, bn_
 /* phi[assignment] (getindex): src/Factors/factors_access.jl:19-35,48-72; dims not in phi are ignored. */
 int32_t bn_factor_slice(bn_factor_t f, const int32_t* dims, const int32_t* states, int32_t n_assign,
                         bn_factor_t* out);
+/* phi[assignment] = v (setindex!): src/Factors/factors_access.jl:39-46 over _translate_index (:48-72); dims not in phi
+ * are ignored, unassigned dims are Colons.  n_values == 1: every cell of the slab gets values[0]; n_values == the slab's
+ * size: an array over the free dims, column-major (`.= v`); otherwise BN_DIM_MISMATCH.  In place.  values: host. */
+int32_t bn_factor_setindex(bn_factor_t f, const int32_t* dims, const int32_t* states, int32_t n_assign,
+                           const double* values, int64_t n_values);
+/* permutedims(phi, perm): src/Factors/factors_main.jl:160-166; out.dims[i] = phi.dims[perm[i]], perm 0-based. */
+int32_t bn_factor_permutedims(bn_factor_t f, const int32_t* perm, int32_t n, bn_factor_t* out);
+/* push!(phi, dim, length): src/Factors/factors_main.jl:148-158 (duplicate, auxiliary.jl:50-65): a new last dimension
+ * along which the table is repeated; BN_BAD_ARG if phi already has `dim`. */
+int32_t bn_factor_push(bn_factor_t f, int32_t dim, int32_t length, bn_factor_t* out);
 /* normalize!(phi; p): src/Factors/factors_dims.jl:45-57 (p in {1,2}; p=2 divides by sum(abs2)). */
 int32_t bn_factor_normalize(bn_factor_t f, int32_t p);
 /* The two halves of normalize!, for a factor that is split over several GPUs (bayesnets.jl_b200/sharded_factors.py):

@@ -402,6 +402,65 @@ function Base.broadcast!(op, a::DeviceFactor, dims::NodeNameUnion, values)
     return a
 end
 
+# getindex / setindex! with an Assignment (factors_access.jl:19-46): dims the factor lacks are ignored, unassigned dims
+# are Colons; states are 1-based here and 0-based across the ABI.
+function _assignment_args(a::DeviceFactor, asg::Assignment)
+    ids = Int32[]; states = Int32[]
+    for d in a.dimensions
+        haskey(asg, d) || continue
+        isa(asg[d], Integer) || throw(TypeError(:getindex, "Invalid state for dimension $d", Int, asg[d]))
+        push!(ids, var_id(d)); push!(states, Int32(asg[d] - 1))
+    end
+    return ids, states
+end
+
+function Base.getindex(a::DeviceFactor, asg::Assignment)
+    ids, states = _assignment_args(a, asg)
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_slice, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Ptr{Int32}, Int32, Ref{UInt64}),
+                    a.handle, ids, states, length(ids), h))
+    return _wrap(h[])
+end
+
+"phi[assignment] = v: one value for every cell of the slab, or an array of the slab's shape (`.= v`)."
+function Base.setindex!(a::DeviceFactor, v, asg::Assignment)
+    ids, states = _assignment_args(a, asg)
+    vals = Float64[x for x in v]                               # column-major, like the slab
+    GC.@preserve ids states vals begin
+        _bn_check(ccall((:bn_factor_setindex, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64}, Int64),
+                        a.handle, ids, states, length(ids), vals, length(vals)))
+    end
+    return v
+end
+
+"permutedims(phi, perm) / permutedims!(phi, perm) (factors_main.jl:160-166)."
+function Base.permutedims(a::DeviceFactor, perm)
+    p0 = Int32[p - 1 for p in perm]
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_permutedims, libbn_cuda), Int32, (UInt64, Ptr{Int32}, Int32, Ref{UInt64}),
+                    a.handle, p0, length(p0), h))
+    return _wrap(h[])
+end
+function _rebind!(a::DeviceFactor, b::DeviceFactor)           # in-place ops rebind the table, as the reference rebinds phi.potential
+    ccall((:bn_factor_free, libbn_cuda), Int32, (UInt64,), a.handle)
+    a.handle, a.dimensions = b.handle, b.dimensions
+    b.handle = UInt64(0)                                       # handle 0 is never issued: b's finalizer gets BN_BAD_ARG back and ignores it
+    return a
+end
+Base.permutedims!(a::DeviceFactor, perm) = _rebind!(a, permutedims(a, perm))
+
+"push!(phi, dim, length) (factors_main.jl:148-158): a new last dimension along which the table repeats."
+function Base.push!(a::DeviceFactor, dim::NodeName, length::Int)
+    dim in a.dimensions && error("Dimension $(dim) already exists")
+    h = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_factor_push, libbn_cuda), Int32, (UInt64, Int32, Int32, Ref{UInt64}), a.handle, _ids([dim])[1], length, h))
+    return _rebind!(a, _wrap(h[]))
+end
+Base.sum!(a::DeviceFactor, dims::NodeNameUnion) = _rebind!(a, sum(a, dims))
+Base.prod!(a::DeviceFactor, dims::NodeNameUnion) = _rebind!(a, prod(a, dims))
+Base.maximum!(a::DeviceFactor, dims::NodeNameUnion) = _rebind!(a, maximum(a, dims))
+Base.minimum!(a::DeviceFactor, dims::NodeNameUnion) = _rebind!(a, minimum(a, dims))
+
 "sum(reduce(*, factors), h) in one kernel: the elimination step of src/Inference/exact.jl:27."
 function eliminate(factors::Vector{DeviceFactor}, h::NodeName)
     hs = UInt64[f.handle for f in factors]

@@ -186,6 +186,39 @@ class NpFactor:
                 keep.append(d)
         return NpFactor(keep, self.potential[tuple(idx)])
 
+    # -- setindex!(phi, v, Assignment): src/Factors/factors_access.jl:39-46 (0-based states here).  Dims of the
+    #    assignment that phi lacks are ignored and unassigned dims are Colons (_translate_index, :48-72); with a Colon
+    #    the value is broadcast into the slab (`.= v`), otherwise one cell is set.  In place, like the reference.
+    def setindex(self, v, assignment: dict) -> "NpFactor":
+        idx = []
+        for i, d in enumerate(self.dimensions):
+            if d in assignment:
+                a = assignment[d]
+                if not isinstance(a, (int, np.integer)):
+                    raise TypeError(f"Invalid state for dimension {d}")
+                if a < 0 or a >= self.size[i]:
+                    raise IndexError(f"BoundsError({d}, {a})")
+                idx.append(int(a))
+            else:
+                idx.append(slice(None))
+        self.potential[tuple(idx)] = v
+        return self
+
+    # -- permutedims(phi, perm): src/Factors/factors_main.jl:160-166 (perm = 0-based positions here)
+    def permutedims(self, perm) -> "NpFactor":
+        perm = [int(x) for x in perm]
+        if sorted(perm) != list(range(len(self.dimensions))):
+            raise ValueError("no valid permutation of dimensions")  # Base.permutedims: ArgumentError
+        return NpFactor([self.dimensions[i] for i in perm], np.asfortranarray(np.transpose(self.potential, perm)))
+
+    # -- push!(phi, dim, length): src/Factors/factors_main.jl:148-158 over duplicate, auxiliary.jl:50-65: a new LAST
+    #    dimension along which the whole table is repeated
+    def push(self, dim, length: int) -> "NpFactor":
+        if dim in self.dimensions:
+            raise RuntimeError(f"Dimension {dim} already exists")
+        pot = np.asfortranarray(np.repeat(self.potential[..., None], int(length), axis=-1))
+        return NpFactor(list(self.dimensions) + [dim], pot)
+
     def permuted_to(self, dims) -> np.ndarray:
         """Potential with axes reordered to `dims` (for order-independent comparison)."""
         return np.transpose(self.potential, [self.dimensions.index(d) for d in dims])

@@ -76,6 +76,17 @@ def main():
             "assignment_1based": {"Y": 2, "K": 16, "Z": 1},
             "expected": [2.0, 3.0, 4.0],
         },
+        "setindex": {
+            "cite": "test/test_factors.jl:138-154 (same phi as getindex; :147-152 the two assignments)",
+            "dims": ["X", "Y", "Z"], "card": [3, 2, 2],
+            "potential": [1, 2, 3, 2, 3, 4, 4, 6, 7, 8, 10, 16],
+            "steps": [
+                {"assignment_1based": {"X": 2, "Y": 1, "Z": 2}, "value": 1600.0,
+                 "check_index_1based": [2, 1, 2], "expected": 1600.0},
+                {"assignment_1based": {"X": 1, "Y": 2}, "value": 2016,
+                 "check_slab_1based": {"X": 1, "Y": 2}, "expected_slab": [2016.0, 2016.0]},
+            ],
+        },
         "inference_acb": {
             "cite": "test/test_inference.jl:36-74",
             "nodes": [["a", [], [[1.0, 0.0]]], ["b", [], [[0.0, 1.0]]],

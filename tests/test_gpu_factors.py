@@ -444,3 +444,93 @@ def test_factor_ops_large_binary(bn):
         assert np.array_equal(fa.maximum(rd).potential, oa.reducedim("max", rd).potential)
         assert np.array_equal(fa.prod(rd).potential, oa.reducedim("*", rd).potential)
         assert np.array_equal(fa.normalize(rd).potential, oa.normalize_dims(rd).potential)
+
+
+# ------------------------------------------------------------------ setindex!, permutedims, push! (row a9)
+def test_setindex_golden(bn, golden):
+    """test/test_factors.jl:147-152 through the mirror: one cell, then a slab over the unassigned dim."""
+    g = golden["setindex"]
+    pot = np.array(g["potential"], np.float64).reshape(g["card"], order="F")
+    f = F(bn, g["dims"], pot)
+    want = NpFactor(g["dims"], pot.copy())
+    for st in g["steps"]:
+        f[st["assignment_1based"]] = st["value"]
+        want.setindex(st["value"], {k: v - 1 for k, v in st["assignment_1based"].items()})
+        assert np.array_equal(f.potential, want.potential)
+    assert f.potential[1, 0, 1] == 1600.0
+    assert f.potential[0, 1, :].tolist() == [2016.0, 2016.0]
+    with pytest.raises(IndexError):
+        f[{"Y": 16}] = 1.0
+    with pytest.raises(TypeError):
+        f[{"Y": "waldo"}] = 1.0
+    before = f.potential
+    f[{"X": 3, "K": 16}] = np.array([[1.0, 2.0], [3.0, 4.0]])  # `.= v` with an array of the slab's shape; K ignored
+    before[2, :, :] = [[1.0, 2.0], [3.0, 4.0]]
+    assert np.array_equal(f.potential, before)
+    with pytest.raises(bn.DimensionMismatch):
+        f[{"X": 3}] = np.array([1.0, 2.0, 3.0])
+    f[{}] = 0.5  # every dim a Colon: fill
+    assert (f.potential == 0.5).all()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_setindex_permutedims_push_random_vs_oracle(bn, seed):
+    """Random mixed-radix factors: slab stores (scalar and array), permutations and push! are pure data movement, so
+    the device tables must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(seed)
+    nd = int(rng.integers(1, 7))
+    card = [int(rng.integers(1, 6)) for _ in range(nd)]
+    dims = [f"v{seed}_{i}" for i in range(nd)]
+    pot = rng.random(card)
+    f, o = F(bn, dims, pot), NpFactor(dims, np.asfortranarray(pot.copy()))
+    for _ in range(4):
+        k = int(rng.integers(0, nd + 1))
+        pick = list(rng.choice(nd, k, replace=False))
+        a = {dims[i]: int(rng.integers(1, card[i] + 1)) for i in pick}
+        slab = [card[i] for i in range(nd) if i not in pick]
+        v = float(rng.random()) if rng.random() < 0.5 else rng.random(slab)
+        f[a] = v
+        o.setindex(v, {d: s - 1 for d, s in a.items()})
+        assert np.array_equal(f.potential, o.potential)
+    perm = list(rng.permutation(nd))
+    fp, op = f.permutedims([p + 1 for p in perm]), o.permutedims(perm)
+    assert fp.dimensions == op.dimensions and np.array_equal(fp.potential, op.potential)
+    assert np.array_equal(f.potential, o.potential)  # permutedims leaves phi alone
+    f.permutedims_([p + 1 for p in perm])
+    assert f.dimensions == op.dimensions and np.array_equal(f.potential, op.potential)
+    length = int(rng.integers(1, 5))
+    f.push_("new", length)
+    o2 = op.push("new", length)
+    assert f.dimensions == o2.dimensions and np.array_equal(f.potential, o2.potential)
+    with pytest.raises(RuntimeError):
+        f.push_("new", 2)
+    with pytest.raises(ValueError):
+        f.permutedims([1] * len(f.dimensions) if len(f.dimensions) > 1 else [2])
+    assert f.indexin("new") == len(f.dimensions) and f.indexin(["new", "waldo"]) == [len(f.dimensions), None]
+    s = f.similar()
+    assert s.dimensions == f.dimensions and s.size() == f.size()
+    f.sum_("new")  # sum! rebinds the table
+    assert f.dimensions == op.dimensions
+    np.testing.assert_allclose(f.potential, op.potential * length, rtol=1e-14)
+
+
+def test_permutedims_and_push_large_binary(bn):
+    """2^22-entry binary factor: reverse all dims / rotate (the gather side of the contraction kernel), push a 4-state
+    dim (2^24 outputs); a permutation applied twice with its inverse returns the table."""
+    rng = np.random.default_rng(11)
+    k = 22
+    dims = [f"b{i}" for i in range(k)]
+    a = rng.random((2,) * k)
+    f = F(bn, dims, a)
+    rev = list(range(k, 0, -1))
+    r = f.permutedims(rev)
+    assert r.dimensions == dims[::-1]
+    assert np.array_equal(r.potential, np.transpose(a, [p - 1 for p in rev]))
+    assert np.array_equal(r.permutedims(rev).potential, a)
+    rot = list(range(8, k + 1)) + list(range(1, 8))
+    assert np.array_equal(f.permutedims(rot).potential, np.transpose(a, [p - 1 for p in rot]))
+    f.push_("q", 4)
+    got = f.potential
+    assert got.shape == (2,) * k + (4,)
+    for j in range(4):
+        assert np.array_equal(got[..., j], a)

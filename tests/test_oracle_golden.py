@@ -98,6 +98,50 @@ def test_getindex_golden(golden):
         NpFactor(g["dims"], pot).slice({"Y": "waldo"})
 
 
+def test_setindex_golden(golden):
+    """test/test_factors.jl:147-152: phi[X=>2, Y=>1, Z=>2] = 1600.0 sets one cell; phi[X=>1, Y=>2] = 2016 fills the
+    slab over the unassigned dim."""
+    g = golden["setindex"]
+    f = NpFactor(g["dims"], np.array(g["potential"], np.float64).reshape(g["card"], order="F"))
+    untouched = f.potential.copy()
+    st = g["steps"][0]
+    f.setindex(st["value"], {k: v - 1 for k, v in st["assignment_1based"].items()})
+    i = tuple(x - 1 for x in st["check_index_1based"])
+    assert f.potential[i] == st["expected"]
+    untouched[i] = st["expected"]
+    assert np.array_equal(f.potential, untouched)
+    st = g["steps"][1]
+    f.setindex(st["value"], {k: v - 1 for k, v in st["assignment_1based"].items()})
+    assert f.potential[0, 1, :].tolist() == st["expected_slab"]
+    untouched[0, 1, :] = st["expected_slab"]
+    assert np.array_equal(f.potential, untouched)
+    with pytest.raises(IndexError):
+        f.setindex(1.0, {"Y": 15})
+    with pytest.raises(TypeError):
+        f.setindex(1.0, {"Y": "waldo"})
+    f.setindex(7.0, {"K": 3})  # a dim phi lacks is ignored: every dim is a Colon -> fill
+    assert (f.potential == 7.0).all()
+
+
+def test_permutedims_and_push_restatements():
+    """permutedims (factors_main.jl:160-166) and push! / duplicate (:148-158, auxiliary.jl:50-65, whose docstring
+    example repeats [1 3; 2 4] three times along a new last dim)."""
+    f = NpFactor(["A", "B"], np.array([[1.0, 3.0], [2.0, 4.0]]))
+    d = f.push("C", 3)
+    assert d.dimensions == ["A", "B", "C"] and d.potential.shape == (2, 2, 3)
+    for k in range(3):
+        assert np.array_equal(d.potential[:, :, k], f.potential)
+    with pytest.raises(RuntimeError):
+        f.push("A", 2)
+    g = NpFactor(["X", "Y", "Z"], np.arange(24, dtype=np.float64).reshape((2, 3, 4), order="F"))
+    h = g.permutedims([2, 0, 1])
+    assert h.dimensions == ["Z", "X", "Y"] and h.potential.shape == (4, 2, 3)
+    assert h.potential[3, 1, 2] == g.potential[1, 2, 3]
+    assert np.array_equal(h.permutedims([1, 2, 0]).potential, g.potential)
+    with pytest.raises(ValueError):
+        g.permutedims([0, 0, 1])
+
+
 def test_factor_constructor_errors():
     """test/test_factors.jl:6-8."""
     with pytest.raises(ValueError):

@@ -231,6 +231,27 @@ def main():
                     "cpu": {"value": nbytes / dt / 1e9, "cores": cores, "kind": "port", "sample": "same operands"},
                     "check": ("bit-identical to the oracle: " if row != "a12" else "within 1e-12 of the oracle: ") + str(same)})
 
+    # ---- a9 data movement: permutedims (rotate the dims by 7: a strided gather) and push! (repeat along a new dim)
+    from oracle.factors_np import NpFactor
+    rot = list(range(8, k + 1)) + list(range(1, 8))
+    nf_a = NpFactor(names, np.asfortranarray(A))
+    for row, name, cite, gfn, cfn, nbytes in [
+            ("a9p", "permutedims(phi, rotate by 7) of 2^%d" % k, "src/Factors/factors_main.jl:160-166",
+             lambda: fa.permutedims(rot), lambda: nf_a.permutedims([r - 1 for r in rot]).potential, 8 * 2 * N),
+            ("a9d", "push!(phi, dim, 4) of 2^%d" % k, "src/Factors/factors_main.jl:148-158",
+             lambda: fa.copy().push_("pbq", 4), lambda: nf_a.push("pbq", 4).potential, 8 * (N + 4 * N))]:
+        ms = ev_time(torch, gfn)
+        if row == "a9d":
+            ms -= ev_time(torch, lambda: fa.copy())  # the copy that keeps fa intact is not part of push!
+        t0 = time.perf_counter()
+        cval = cfn()
+        dt = time.perf_counter() - t0
+        same = bool(np.array_equal(gfn().potential, cval))
+        out.append({"row": row, "api": name, "cite": cite, "config": "single Python-level op incl. result allocation",
+                    "unit": "GB/s", "gpu": nbytes / (ms * 1e-3) / 1e9, "gpu_ms": ms,
+                    "cpu": {"value": nbytes / dt / 1e9, "cores": 1, "kind": "port", "sample": "same operand (numpy oracle)"},
+                    "check": "identical to the oracle: " + str(same)})
+
     # ---- a13 ExactInference end to end on the C5 net (one 2^24-entry CPT)
     kk = 23 if not a.quick else 15
     lay5 = c5_layout(bn, k=kk)
