@@ -23,6 +23,7 @@ from .learning import (BDeuPrior, DirichletPrior, UniformPrior, bayesian_score, 
                        bayesian_score_components, fit, fit_from_device_table, logpdf, logpdf_device, pdf, statistics,
                        statistics_device)
 from .sampling import (BayesNetSampler, DirectSampler, GibbsSampler, LikelihoodWeightedSampler,  # noqa: F401
-                       RejectionSampler, get_weighted_dataframe, get_weighted_sample, gibbs_sample, rand)
+                       RejectionSampler, get_weighted_dataframe, get_weighted_sample, gibbs_sample, rand,
+                       sample_weighted_dataframe)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

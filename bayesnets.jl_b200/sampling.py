@@ -83,6 +83,26 @@ def get_weighted_sample(bn, evidence: dict | None = None, seed=None, device=None
     return {n: int(states[i, 0]) + 1 for i, n in enumerate(lay.names)}, float(w[0])
 
 
+def sample_weighted_dataframe(weighted_dataframe: pd.DataFrame, a: dict | None = None, u: float | None = None) -> dict:
+    """sample_weighted_dataframe[!] (src/sampling.jl:126-127,182-197): one row drawn by a cumulative scan of the
+    `potential` column against a uniform `u` (drawn here when not given); host-side, one row."""
+    p = np.asarray(weighted_dataframe["potential"], np.float64)
+    n = len(p)
+    if n == 0:
+        raise IndexError("BoundsError: empty weighted dataframe")  # p[1], :186
+    u = float(np.random.default_rng().random()) if u is None else float(u)
+    i, c = 0, p[0]
+    while c < u and i < n - 1:
+        i += 1
+        c += p[i]
+    a = {} if a is None else a
+    for col in weighted_dataframe.columns:
+        if col != "potential":
+            v = weighted_dataframe[col].iloc[i]
+            a[col] = int(v) if isinstance(v, (int, np.integer)) else v
+    return a
+
+
 def _lib_kind(name: str) -> int:
     return {"ancestral": 0, "rejection": 1, "weighted": 2}[name]
 

@@ -238,3 +238,18 @@ def test_specialised_lw_source_compiles_without_a_gpu(bn):
     big, _, _ = spec_source(lay, {}, ["N1", "N2", "N3", "N4", "N6"], prune=True, compile=False)
     ncell = int(np.prod([lay.card[lay.index[f"N{i}"]] for i in (1, 2, 3, 4, 6)]))
     assert ("atomicAdd(&bins[cell], w)" in big) == (ncell > 16)
+
+
+def test_sample_weighted_dataframe_scan(bn):
+    """src/sampling.jl:182-197: cumulative scan `while c < u && i < n`; the last row absorbs rounding."""
+    import pandas as pd
+    df = pd.DataFrame({"a": [1, 2, 3], "b": [2, 2, 1], "potential": [0.2, 0.5, 0.3]})
+    assert bn.sample_weighted_dataframe(df, u=0.0) == {"a": 1, "b": 2}
+    assert bn.sample_weighted_dataframe(df, u=0.2) == {"a": 1, "b": 2}   # c < u is false at c == u
+    assert bn.sample_weighted_dataframe(df, u=0.21) == {"a": 2, "b": 2}
+    assert bn.sample_weighted_dataframe(df, u=0.71) == {"a": 3, "b": 1}
+    assert bn.sample_weighted_dataframe(df, u=1.5) == {"a": 3, "b": 1}
+    a = {"z": 9}
+    assert bn.sample_weighted_dataframe(df, a) is a and a["z"] == 9 and set(a) == {"z", "a", "b"}
+    with pytest.raises(IndexError):
+        bn.sample_weighted_dataframe(df.iloc[:0])
