@@ -82,6 +82,7 @@ _SIGS = {
     "bn_statistics_dev": (C.c_int32, [h64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "bn_logpdf": (C.c_int32, [h64, u8p, C.c_uint64, f64p]),
     "bn_logpdf_dev": (C.c_int32, [h64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "bn_logpdf_counts_dev": (C.c_int32, [h64, C.c_void_p, C.c_void_p]),
     "bn_loopy_infer": (C.c_int32, [h64, i8p, i32p, C.c_uint64, C.c_int32, C.c_double, C.c_int32, C.c_int32, f64p, i32p]),
     "bn_loopy_infer_dev": (C.c_int32, [h64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_double, C.c_int32,
                                        C.c_int32, C.c_void_p, C.c_void_p]),

@@ -362,6 +362,17 @@ int32_t bn_logpdf_dev(bn_net_t h, const uint8_t* states_dev, uint64_t n_rows, ui
   return logpdf_launch(net, states_dev, n_rows, pitch, out_logl_dev);
 }
 
+int32_t bn_logpdf_counts_dev(bn_net_t h, const int64_t* counts_dev, double* out_logl_dev) {
+  Net* net = get_net(h);
+  BN_REQUIRE(net && counts_dev && out_logl_dev, BN_BAD_ARG, "bn_logpdf_counts_dev: bad arguments");
+  BN_CUDA_TRY(cudaSetDevice(net->device));
+  logl_kernel<<<1, 1024, 0, tl_stream>>>(reinterpret_cast<const unsigned long long*>(counts_dev), net->d_cpt.p,
+                                         (uint32_t)net->cpt_off[net->n], out_logl_dev);
+  count_launch();
+  BN_CUDA_TRY(cudaGetLastError());
+  return BN_OK;
+}
+
 int32_t bn_logpdf(bn_net_t h, const uint8_t* states, uint64_t n_rows, double* out_logl) {
   Net* net = get_net(h);
   BN_REQUIRE(net && out_logl && (states || n_rows == 0), BN_BAD_ARG, "bn_logpdf: bad arguments");

@@ -146,6 +146,60 @@ class ShardedGibbs:
             return (c / c.sum()).reshape(self.shape, order="F")
 
 
+class ShardedTableStatistics:
+    """The learn-from-samples loop with the table's ROWS split over the ranks of the default process group:
+    rank g draws rows [g*R//G, (g+1)*R//G) of one global row index space (the Philox counter is the global row index,
+    so the union of the shards IS the single-GPU table), counts its shard where it lies (bn_statistics_dev) and the
+    int64 count tensors are all-reduced -- integers, so every rank holds exactly the single-GPU counts.  The data
+    log-likelihood is then the counts dotted with the log CPTs (bn_logpdf_counts_dev): the same bits on every rank and
+    for every number of ranks.  No data-path collective besides that one all-reduce of cpt_len int64."""
+
+    def __init__(self, bn, n_rows_total: int, seed: int = 0, device: int | None = None):
+        import torch
+        self.torch = torch
+        rank, world, local = env_rank_world()
+        self.rank, self.world = rank, world
+        self.device = local if device is None else device
+        self.net = device_net(bn, self.device)
+        lay = self.net.layout
+        self.n_rows_total = int(n_rows_total)
+        self.first, self.count = shard_range(self.n_rows_total, rank, world)
+        self.seed = int(seed)
+        dev = f"cuda:{self.device}"
+        self.table = torch.empty((lay.n, max(self.count, 1)), dtype=torch.uint8, device=dev)  # pitch = row count
+        self.counts = torch.zeros(int(lay.cpt_off[-1]), dtype=torch.int64, device=dev)
+        self.logl = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def sample(self):
+        """rand(bn, n): this rank's rows, left in HBM (node-major uint8, one column of `count` bytes per node)."""
+        _lib.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+        if self.count:
+            check(_lib.lib().bn_sample_dev(_lib.h64(self.net.handle), None, C.c_int32(0), C.c_int32(1), C.c_uint64(self.first),
+                                           C.c_uint64(self.count), C.c_uint64(self.seed), C.c_void_p(self.table.data_ptr()),
+                                           None, None))
+        return self.table
+
+    def launch(self):
+        """Count the local shard only (no collective); int64 counts in self.counts."""
+        _lib.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+        check(_lib.lib().bn_statistics_dev(_lib.h64(self.net.handle), C.c_void_p(self.table.data_ptr()), C.c_uint64(self.count),
+                                           C.c_uint64(max(self.count, 1)), C.c_void_p(self.counts.data_ptr())))
+        return self.counts
+
+    def step(self):
+        """sample -> count -> all-reduce: the whole table's sufficient statistics on every rank."""
+        self.sample()
+        self.launch()
+        return allreduce_sum_(self.counts)
+
+    def logpdf(self) -> float:
+        """logpdf(bn, table) of the WHOLE table from the all-reduced counts (call after step())."""
+        _lib.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
+        check(_lib.lib().bn_logpdf_counts_dev(_lib.h64(self.net.handle), C.c_void_p(self.counts.data_ptr()),
+                                              C.c_void_p(self.logl.data_ptr())))
+        return float(self.logl.cpu()[0])
+
+
 class ShardedLoopy:
     """LoopyBelief over many (query, evidence) pairs, the PAIRS split over the ranks of the default process group:
     rank g answers pairs [g*B//G, (g+1)*B//G) with one bn_loopy_infer_dev launch; pairs are independent, so there is no

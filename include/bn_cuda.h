@@ -240,6 +240,10 @@ int32_t bn_statistics_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_ro
  * the current stream. */
 int32_t bn_logpdf(bn_net_t net, const uint8_t* states, uint64_t n_rows, double* out_logl);
 int32_t bn_logpdf_dev(bn_net_t net, const uint8_t* states_dev, uint64_t n_rows, uint64_t pitch, double* out_logl_dev);
+/* The second half alone: log-likelihood from sufficient statistics already on the device (bn_statistics_dev's
+ * layout), e.g. counts all-reduced over the ranks of a row-sharded table -- every rank then gets the same bits as one
+ * GPU counting the whole table.  Enqueues on the current stream. */
+int32_t bn_logpdf_counts_dev(bn_net_t net, const int64_t* counts_dev, double* out_logl_dev);
 
 /* ---- infer(::LoopyBelief, ::InferenceState): src/Inference/loopy_belief.jl:24-218 -------------------------
  * Loopy belief propagation, batched: instance b has evidence row evidence[b * n_nodes .. ] (NULL = no evidence

@@ -70,8 +70,14 @@ def _worker(rank, world, port, n_total, q):
             o = loopy_infer(on, qn, e, nsamples=8)
             rows[r, :len(o)] = o
         lb = allgather_rows_(torch.from_numpy(rows), [shard_range(len(pairs), g, world)[1] for g in range(world)])
+        # table rows sharded the same way: rank g draws rows [first, first + count) of one global row index space and
+        # counts them; the int64 counts are all-reduced (ShardedTableStatistics' contract)
+        tfirst, tcount = shard_range(10_001, rank, world)
+        rows_u8, _, _ = capi.sample(on, tcount, seed=6, first=tfirst)
+        tc = torch.from_numpy(capi.statistics(on, rows_u8))
+        allreduce_sum_(tc)
         if rank == 0:
-            q.put((t.numpy().copy(), g.numpy().copy(), lb.numpy().copy()))
+            q.put((t.numpy().copy(), g.numpy().copy(), lb.numpy().copy(), tc.numpy().copy()))
         dist.destroy_process_group()
     except Exception as e:  # surface worker failures in the parent
         if rank == 0:
@@ -99,7 +105,7 @@ def test_two_rank_gloo_allreduce_equals_single_stream():
         assert p.exitcode == 0
     if isinstance(got, Exception):
         raise got
-    lw2, g2, lb2 = got
+    lw2, g2, lb2, tc2 = got
     net = bn.rand_discrete_bn(40, 3, 4, seed=5)
     lay = bn.flatten(net)
     on = FlatNet(list(lay.names), lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, dict(lay.index))
@@ -109,6 +115,8 @@ def test_two_rank_gloo_allreduce_equals_single_stream():
     assert lw2[-2] == pytest.approx(sw, rel=1e-12) and lw2[-1] == pytest.approx(sw2, rel=1e-12)
     gc, _ = capi.gibbs_infer(on, ev, qi, 64, 300, 100, 3, seed=4)
     assert np.array_equal(g2, gc.astype(np.float64).ravel(order="F"))
+    whole, _, _ = capi.sample(on, 10_001, seed=6)
+    assert tc2.dtype == np.int64 and np.array_equal(tc2, capi.statistics(on, whole))
     from oracle.loopy_np import loopy_infer
     pairs = _loopy_pairs(lay)
     assert lb2.shape == (len(pairs), int(lay.card.max()))

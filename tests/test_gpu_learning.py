@@ -306,3 +306,27 @@ def test_sample_then_logpdf_on_device(bn):
     assert 0 < int(ok.sum().item()) < n_rows
     got = bn.logpdf_device(net, tab.data_ptr(), n_rows)
     assert got == pytest.approx(capi.logpdf_table(on, tab.cpu().numpy()), rel=1e-12)
+
+
+def test_sharded_table_statistics_single_rank(bn):
+    """distributed.ShardedTableStatistics at world size 1 (no process group: the all-reduce is the identity): sample ->
+    count -> logpdf on the device equals the oracle on the same table; a shard [first, first + count) of the global
+    row space holds exactly those rows of the whole table (what the 2-rank gloo test and tools/table_scaling.py rely on)."""
+    import torch
+    from bayesnets_jl_b200.distributed import ShardedTableStatistics
+    net = bn.rand_discrete_bn(40, 3, 4, seed=3)
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    n_rows = 100_003
+    sh = ShardedTableStatistics(net, n_rows, seed=21, device=0)
+    counts = sh.step().cpu().numpy()
+    whole, _, _ = capi.sample(on, n_rows, seed=21)
+    assert np.array_equal(sh.table.cpu().numpy(), whole)
+    assert np.array_equal(counts, capi.statistics(on, whole))
+    assert sh.logpdf() == pytest.approx(capi.logpdf_table(on, whole), rel=1e-12)
+    # a middle shard of the same global row space
+    sh.first, sh.count = 33_334, 33_335
+    sh.table = torch.empty((lay.n, sh.count), dtype=torch.uint8, device="cuda:0")
+    sh.sample()
+    assert np.array_equal(sh.table.cpu().numpy(), whole[:, 33_334:33_334 + 33_335])
+    assert np.array_equal(sh.launch().cpu().numpy(), capi.statistics(on, np.ascontiguousarray(whole[:, 33_334:33_334 + 33_335])))
