@@ -70,6 +70,18 @@ def build_cases(bn, k, nrot, rng):
         _lib.check(L.bn_factor_normalize(_lib.h64(a.handle), C.c_int32(1)))
         return None
 
+    def permute(a, perm):
+        out = _lib.h64(0)
+        _lib.check(L.bn_factor_permutedims(_lib.h64(a.handle), _lib.ptr(perm, _lib.i32p), C.c_int32(len(perm)), C.byref(out)))
+        return Raw(out)
+
+    def push(a, dim, length):
+        out = _lib.h64(0)
+        _lib.check(L.bn_factor_push(_lib.h64(a.handle), C.c_int32(dim), C.c_int32(length), C.byref(out)))
+        return Raw(out)
+
+    rot = np.array(list(range(7, k)) + list(range(7)), np.int32)  # out dim i = in dim (i + 7) mod k
+    qdim = bn.factors.var_id(names[k + 1])
     d0, dk, dm, d4 = ids(0), ids(k - 1), ids(k // 2), ids(1, 5, 11, k - 2)
     cases = [
         ("P1 2^%d x 2^%d interleaved" % (k, k // 2), lambda s: product(s["A"], s["B12"]), 8 * (2 * N + (1 << (k // 2)))),
@@ -80,6 +92,8 @@ def build_cases(bn, k, nrot, rng):
         ("S3 sum middle", lambda s: fsum(s["A"], dm), 8 * (N + N // 2)),
         ("S4 sum 4 dims", lambda s: fsum(s["A"], d4), 8 * (N + N // 16)),
         ("N1 normalize", lambda s: norm(s["A"]), 8 * 3 * N),
+        ("T1 permutedims rotate by 7", lambda s: permute(s["A"], rot), 8 * 2 * N),
+        ("D1 push! 2^%d x 2 -> 2^%d" % (k - 1, k), lambda s: push(s["A23"], qdim, 2), 8 * (N // 2 + N)),
         ("E1 fused eliminate 3 factors", lambda s: elim([s["A"], s["Eb"], s["Ec"]], d0),
          8 * (N + 2 * (1 << 12) + N // 2)),
     ]
