@@ -977,8 +977,8 @@ int32_t bn_factor_slice(bn_factor_t h, const int32_t* dims, const int32_t* state
 }
 
 // permutedims(phi, perm): src/Factors/factors_main.jl:160-166.  out.dims[i] = phi.dims[perm[i]] (0-based positions):
-// a 1-operand contraction whose output dim order is the permuted one (a strided gather on the read side, coalesced
-// 128-bit stores on the write side).
+// the tiled transpose of permute.cu; shapes its tiling does not cover go through a 1-operand contraction whose output
+// dim order is the permuted one (a strided gather on the read side).
 int32_t bn_factor_permutedims(bn_factor_t h, const int32_t* perm, int32_t n, bn_factor_t* out) {
   Factor* f = get_factor(h);
   BN_REQUIRE(f && out && (perm || n == 0), BN_BAD_ARG, "bn_factor_permutedims: bad arguments");
@@ -1002,7 +1002,11 @@ int32_t bn_factor_permutedims(bn_factor_t h, const int32_t* perm, int32_t n, bn_
     cudaError_t e = cudaMemcpyAsync(o->data.p, f->data.p, (size_t)f->len * 8, cudaMemcpyDeviceToDevice, tl_stream);
     if (e != cudaSuccess) { delete o; BN_CUDA_TRY(e); }
   } else {
-    rc = contract(f->device, {Operand{f->data.p, f->dims, f->card}}, od, oc, {}, {}, o->data.p);
+    static const bool no_tiled = getenv("BN_NO_TILED_PERMUTE") != nullptr;
+    bool handled = false;
+    if (!no_tiled) rc = permute_tiled(f->device, f->data.p, f->card, perm, o->data.p, &handled);
+    if (rc == BN_OK && !handled)
+      rc = contract(f->device, {Operand{f->data.p, f->dims, f->card}}, od, oc, {}, {}, o->data.p);
   }
   if (rc != BN_OK) { delete o; return rc; }
   *out = register_factor(o);

@@ -534,3 +534,35 @@ def test_permutedims_and_push_large_binary(bn):
     assert got.shape == (2,) * k + (4,)
     for j in range(4):
         assert np.array_equal(got[..., j], a)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_permutedims_tiled_transpose_random_shapes(bn, seed):
+    """The tiled transpose (csrc/permute.cu) over shapes that exercise its planner: many small mixed-radix dims (tile
+    and remaining dims unmerged), size-1 dims, a random permutation of 20 binary dims (13+ remaining dims, one lane
+    each), large odd cards, identity-like permutations; plus the contraction-kernel fallback (BN_NO_TILED_PERMUTE is
+    read once per process, so the fallback is reached through shapes the tiling refuses: a 255 x 255 leading pair)."""
+    rng = np.random.default_rng(100 + seed)
+    if seed == 0:
+        card = [2] * 20
+    elif seed == 1:
+        card = [255, 255, 3, 2]          # A x B tile would be 65025 entries -> fallback path
+    elif seed == 2:
+        card = [7, 1, 5, 3, 1, 11, 2, 13, 3, 2]
+    elif seed == 3:
+        card = [64, 3, 64, 5, 2]
+    else:
+        nd = int(rng.integers(2, 13))
+        card = [int(rng.integers(1, 6)) for _ in range(nd)]
+    nd = len(card)
+    dims = [f"t{seed}_{i}" for i in range(nd)]
+    a = rng.random(card)
+    f = F(bn, dims, a)
+    perms = [list(rng.permutation(nd)) for _ in range(3)]
+    perms.append(list(range(nd)))                      # identity
+    perms.append(list(range(nd))[::-1])                # full reversal
+    perms.append([0] + list(range(nd - 1, 0, -1)))     # leading dim stays
+    for perm in perms:
+        g = f.permutedims([int(x) + 1 for x in perm])
+        assert g.dimensions == [dims[i] for i in perm]
+        assert np.array_equal(g.potential, np.transpose(a, perm))
