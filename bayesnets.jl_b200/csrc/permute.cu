@@ -34,7 +34,7 @@ constexpr int PT_MAXR = 32;    // remaining dims (merged): one lane each
 constexpr int PT_TILE_MAX = 4096;
 constexpr int PT_TILE_AIM = 2048;
 constexpr int PT_U = 8;        // loads in flight per thread per pass
-constexpr int PT_PASSES = PT_TILE_MAX / (PT_THR * PT_U);  // register-held passes of the prefetched tile
+// the prefetched tile is held in PASSES x PT_U registers per thread: PASSES = 1 for tiles <= 2048 entries, else 2
 
 struct PermuteParams {
   const double* in;
@@ -49,7 +49,8 @@ struct PermuteParams {
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) { return j ^ (((j >> 4) ^ (j >> 8) ^ (j >> 12)) & 15u); }
 
-__global__ void __launch_bounds__(PT_THR, 4) permute_kernel(const PermuteParams p) {
+template <int PASSES, int MINB>
+__global__ void __launch_bounds__(PT_THR, MINB) permute_kernel(const PermuteParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* tile = reinterpret_cast<double*>(smem_raw);              // [T16] (T rounded up to 16)
   const int T16 = (p.T + 15) & ~15;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(PT_THR, 4) permute_kernel(const PermuteParams 
   };
   // Software pipeline over this CTA's tiles: the loads of tile k+1 are issued (into registers) BEFORE tile k is
   // stored from shared memory, so the read latency of one tile hides behind the write phase of the other.
-  // T <= PT_THR * PT_U * PT_PASSES entries per tile.
+  // T <= PT_THR * PT_U * PASSES entries per tile.
   uint32_t t = blockIdx.x;
   if (t >= p.n_tiles) return;
   int par = 0;
@@ -126,13 +127,13 @@ __global__ void __launch_bounds__(PT_THR, 4) permute_kernel(const PermuteParams 
     const bool more = tn < p.n_tiles;
     if (more) tile_bases(tn, par ^ 1);
     __syncthreads();  // tile t resident in shared memory; bases of tile tn visible
-    double v[PT_PASSES][PT_U];
+    double v[PASSES][PT_U];
     long long bo_next = 0;
     if (more) {
       const double* __restrict__ src = p.in + s_base[par ^ 1][0];
       bo_next = s_base[par ^ 1][1];
 #pragma unroll
-      for (int w = 0; w < PT_PASSES; ++w)
+      for (int w = 0; w < PASSES; ++w)
 #pragma unroll
         for (int u = 0; u < PT_U; ++u) {
           const int j = tid + (w * PT_U + u) * PT_THR;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(PT_THR, 4) permute_kernel(const PermuteParams 
     if (!more) break;
     __syncthreads();  // every slot of tile t has been read
 #pragma unroll
-    for (int w = 0; w < PT_PASSES; ++w)
+    for (int w = 0; w < PASSES; ++w)
 #pragma unroll
       for (int u = 0; u < PT_U; ++u) {
         const int j = tid + (w * PT_U + u) * PT_THR;
@@ -282,14 +283,17 @@ int32_t permute_tiled(int device, const double* in, const std::vector<int32_t>& 
   }
   p.n_tiles = (uint32_t)pre;
   const size_t smem = (size_t)((T + 15) & ~15ll) * 8 + (size_t)T * 10 + 16;
-  BN_CUDA_TRY(cudaFuncSetAttribute(permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((size_t)PT_TILE_MAX * 20 + 256)));
+  // resident CTAs per SM: measured at 2^24 entries (rotation of 24 binary dims, 2048-entry tiles): 4 CTAs 0.76 of the
+  // HBM peak, 5 CTAs 0.74, 6 CTAs 0.63 -- more CTAs open more DRAM pages at once
+  static const int ctas_env = getenv("BN_PERMUTE_CTAS") ? atoi(getenv("BN_PERMUTE_CTAS")) : 4;
+  void (*kern)(const PermuteParams) = T <= PT_THR * PT_U ? permute_kernel<1, 4> : permute_kernel<2, 4>;
+  BN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)PT_TILE_MAX * 18 + 256)));
   const DevProps& dp = dev_props(device);
   int per_sm = 0;
-  BN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, permute_kernel, PT_THR, smem));
-  if (per_sm < 1) per_sm = 1;
+  BN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT_THR, smem));
+  per_sm = std::max(1, std::min(per_sm, ctas_env));
   const int grid = (int)std::min<long long>((long long)p.n_tiles, (long long)dp.sm_count * per_sm);
-  permute_kernel<<<grid, PT_THR, smem, tl_stream>>>(p);
+  kern<<<grid, PT_THR, smem, tl_stream>>>(p);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   *handled = true;
