@@ -20,7 +20,8 @@ from .inference import (ExactInference, GibbsSamplingFull, GibbsSamplingNodewise
                         InferenceState, LikelihoodWeightingInference, LoopyBelief, infer)
 from .io import read_text, readxdsl, write_text  # noqa: F401
 from .learning import (BDeuPrior, DirichletPrior, UniformPrior, bayesian_score, bayesian_score_component,  # noqa: F401
-                       bayesian_score_components, fit, fit_from_device_table, logpdf, logpdf_device, pdf, statistics,
+                       bayesian_score_components, count, fit, fit_from_device_table, logpdf, logpdf_device, pdf, statistics,
+                       table,
                        statistics_device)
 from .sampling import (BayesNetSampler, DirectSampler, GibbsSampler, LikelihoodWeightedSampler,  # noqa: F401
                        RejectionSampler, get_weighted_dataframe, get_weighted_sample, gibbs_sample, rand,

@@ -345,3 +345,54 @@ def logpdf_device(bn_or_net, states_dev_ptr: int, n_rows: int, pitch: int | None
     check(_lib.lib().bn_logpdf_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
                                    C.c_uint64(pitch), C.c_void_p(out.data_ptr())))
     return float(out.cpu()[0])
+
+
+# ------------------------------------------------------------------------------------------------ count / table
+def count(bn: BayesNet, *args, device=None):
+    """Base.count(bn, name, data) -> DataFrame of the observed (parents..., name) assignments and their counts, rows in
+    order of first appearance (`unique(t)`), columns `parents(bn, name)..., name, count`; count(bn, data) -> one such
+    frame per node (src/DiscreteBayesNet/discrete_bayes_net.jl:101-121).  The tally is statistics(bn, name, data) on the
+    device (the reference compares every unique row with every row); the host only lists the rows that occur."""
+    import pandas as pd
+    if len(args) == 1:
+        return [count(bn, nm, args[0], device=device) for nm in bn.names()]
+    name, data = args
+    varnames = list(bn.parents(name)) + [name]
+    t = data[varnames]
+    tu = t.drop_duplicates(ignore_index=True)
+    if len(tu) == 0:
+        return tu.assign(count=np.zeros(0, np.int64))
+    N = statistics(bn, name, data, device=device)  # r x q, parental instantiations over the parents in ASCENDING node order
+    names = bn.names()
+    order = sorted(bn.parents(name), key=names.index)
+    ncat = {p: infer_number_of_instantiations(data.iloc[:, names.index(p)]) for p in order}
+    j = np.zeros(len(tu), np.int64)
+    stride = 1
+    for p in order:
+        j += stride * (np.asarray(tu[p], np.int64) - 1)
+        stride *= ncat[p]
+    return tu.assign(count=N[np.asarray(tu[name], np.int64) - 1, j])
+
+
+def table(bn: BayesNet, name, assignment: dict | None = None, /, **kw):
+    """table(bn, name[, assignment]) -> DataFrame of the node's CPT: columns `parents..., name, potential`, first parent
+    fastest, the node's own state slowest (src/DiscreteBayesNet/discrete_bayes_net.jl:49-91); with an assignment, only
+    the rows consistent with it (:88-91).  Host-side formatting of the CPT the device tables are built from."""
+    import pandas as pd
+    cpd = bn.get(name)
+    pn = [int(x) for x in cpd.parental_ncategories]
+    r = cpd.ncategories()
+    q = int(np.prod(pn)) if pn else 1
+    cols = {}
+    inner = 1
+    for p, c in zip(cpd.parents, pn):
+        cols[p] = np.tile(np.repeat(np.arange(1, c + 1), inner), (q // (inner * c)) * r)
+        inner *= c
+    cols[name] = np.repeat(np.arange(1, r + 1), q)
+    cols["potential"] = np.array([cpd.distributions[jj][k] for k in range(r) for jj in range(q)], np.float64)
+    df = pd.DataFrame(cols)
+    a = dict(assignment or {}, **kw)
+    for k, v in a.items():
+        if k in df.columns:
+            df = df[df[k] == v]
+    return df.reset_index(drop=True)

@@ -330,3 +330,30 @@ def test_sharded_table_statistics_single_rank(bn):
     sh.sample()
     assert np.array_equal(sh.table.cpu().numpy(), whole[:, 33_334:33_334 + 33_335])
     assert np.array_equal(sh.launch().cpu().numpy(), capi.statistics(on, np.ascontiguousarray(whole[:, 33_334:33_334 + 33_335])))
+
+
+def test_count_reference_values(bn, golden):
+    """Base.count: test/test_discrete_bayes_nets.jl:18-29 (a -> b, 8 rows) and test/test_learning.jl:5-38,85 (A -> B,
+    A -> C, B -> C, 12 rows: 7 observed (A, B, C) rows, in order of first appearance)."""
+    net = bn.BayesNet()
+    net.push(bn.DiscreteCPD("a", [0.4, 0.6]))
+    net.push(bn.DiscreteCPD("b", ["a"], [2], [[0.5, 0.5], [0.2, 0.8]]))
+    data = pd.DataFrame({"a": [1, 1, 1, 1, 2, 2, 2, 2], "b": [1, 2, 1, 2, 1, 1, 1, 2]})
+    T = bn.count(net, "a", data)
+    assert list(T.columns) == ["a", "count"] and T["a"].tolist() == [1, 2] and T["count"].tolist() == [4, 4]
+    T = bn.count(net, "b", data)
+    assert len(T) == 4 and list(T.columns) == ["a", "b", "count"]
+    got = {(int(r.a), int(r.b)): int(r.count) for r in T.itertuples()}
+    assert got == {(1, 1): 2, (2, 1): 3, (1, 2): 2, (2, 2): 1}
+    assert T[["a", "b"]].values.tolist() == [[1, 1], [1, 2], [2, 1], [2, 2]]  # unique(): order of first appearance
+    g = golden["statistics_abc"]
+    data = pd.DataFrame(g["data"])
+    net3 = bn.fit(data, tuple(tuple(e) for e in g["edges"]))
+    TA = bn.count(net3, "A", data)
+    assert TA.shape == (3, 2) and TA["count"].tolist() == [4, 4, 4]
+    TC = bn.count(net3, "C", data)
+    assert TC.shape == (7, 4)
+    rows = {(int(r.A), int(r.B), int(r.C)): int(r.count) for r in TC.itertuples()}
+    assert rows == {(1, 1, 1): 3, (1, 2, 2): 1, (2, 2, 1): 2, (2, 2, 2): 1, (2, 1, 1): 1, (3, 1, 1): 3, (3, 2, 2): 1}
+    assert len(bn.count(net3, data)) == 3
+    assert int(TC["count"].sum()) == len(data)

@@ -253,3 +253,18 @@ def test_sample_weighted_dataframe_scan(bn):
     assert bn.sample_weighted_dataframe(df, a) is a and a["z"] == 9 and set(a) == {"z", "a", "b"}
     with pytest.raises(IndexError):
         bn.sample_weighted_dataframe(df.iloc[:0])
+
+
+def test_table_matches_reference_values(bn):
+    """test/test_discrete_bayes_nets.jl:5-16: table(bn, :a), table(bn, :b) -- parents fastest, own state slowest."""
+    net = bn.BayesNet()
+    net.push(bn.DiscreteCPD("a", [0.4, 0.6]))
+    net.push(bn.DiscreteCPD("b", ["a"], [2], [[0.5, 0.5], [0.2, 0.8]]))
+    ta = bn.table(net, "a")
+    assert list(ta.columns) == ["a", "potential"] and ta["a"].tolist() == [1, 2] and ta["potential"].tolist() == [0.4, 0.6]
+    tb = bn.table(net, "b")
+    assert list(tb.columns) == ["a", "b", "potential"]
+    assert tb["a"].tolist() == [1, 2, 1, 2] and tb["b"].tolist() == [1, 1, 2, 2]
+    assert tb["potential"].tolist() == [0.5, 0.2, 0.5, 0.8]
+    assert bn.table(net, "b", a=2)["potential"].tolist() == [0.2, 0.8]
+    assert bn.table(net, "b", {"a": 1, "b": 2})["potential"].tolist() == [0.5]
