@@ -165,6 +165,120 @@ __global__ void __launch_bounds__(PT_THR, MINB) permute_kernel(const PermutePara
   }
 }
 
+// The same kernel moving PAIRS: when the tile's first read dim and first write dim are both even (binary nets: always)
+// entries 2jj, 2jj + 1 are neighbours in the input (read order) resp. in the output (write order), so both global
+// sides are 128-bit accesses and the tables shrink to one entry per pair.  A pair's two slots differ only in bit 0
+// (the swizzle touches the low 4 bits with a mask that depends on j >> 4), so the read phase parks a pair with one
+// 128-bit shared store, swapped when the first slot is odd.
+__global__ void __launch_bounds__(PT_THR, 4) permute_pairs_kernel(const PermuteParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);                // [T16]
+  const int T16 = (p.T + 15) & ~15;
+  const int P = p.T >> 1;                                            // pairs per tile (<= PT_THR * PT_U)
+  int32_t* rd_off = reinterpret_cast<int32_t*>(tile + T16);          // [P] input offset of pair jj (read order)
+  int32_t* wr_off = rd_off + P;                                      // [P] output offset of pair jj (write order)
+  uint32_t* wr_slot = reinterpret_cast<uint32_t*>(wr_off + P);       // [P] its two slots, 16 bits each
+  __shared__ long long s_base[2][2];
+  const int tid = threadIdx.x;
+  for (int jj = tid; jj < P; jj += PT_THR) {
+    uint32_t r = 2u * (uint32_t)jj;
+    int32_t off = 0;
+    for (int d = 0; d < p.nt; ++d) {
+      const uint32_t q = r / (uint32_t)p.rcard[d];
+      off += (int32_t)(r - q * (uint32_t)p.rcard[d]) * p.ris[d];
+      r = q;
+    }
+    rd_off[jj] = off;
+    r = 2u * (uint32_t)jj;
+    int32_t oo = 0, rj = 0;
+    for (int d = 0; d < p.nt; ++d) {
+      const uint32_t q = r / (uint32_t)p.wcard[d];
+      const int32_t dg = (int32_t)(r - q * (uint32_t)p.wcard[d]);
+      oo += dg * p.wos[d];
+      rj += dg * p.wrs[d];
+      r = q;
+    }
+    wr_off[jj] = oo;
+    wr_slot[jj] = swz((uint32_t)rj) | (swz((uint32_t)(rj + p.wrs[0])) << 16);  // next value of the first write dim
+  }
+  auto tile_bases = [&](uint32_t t, int par) {
+    if (tid < 32) {
+      long long bi = 0, bo = 0;
+      if (tid < p.nr) {
+        const uint32_t dg = (t / p.tpre[tid]) % p.tcard[tid];
+        bi = (long long)dg * p.tis[tid];
+        bo = (long long)dg * p.tos[tid];
+      }
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        bi += __shfl_xor_sync(0xffffffffu, bi, s);
+        bo += __shfl_xor_sync(0xffffffffu, bo, s);
+      }
+      if (tid == 0) { s_base[par][0] = bi; s_base[par][1] = bo; }
+    }
+  };
+  auto park = [&](const double2 (&v)[PT_U]) {
+#pragma unroll
+    for (int u = 0; u < PT_U; ++u) {
+      const int jj = tid + u * PT_THR;
+      if (jj < P) {
+        const uint32_t sl = swz(2u * (uint32_t)jj);
+        *reinterpret_cast<double2*>(tile + (sl & ~1u)) = (sl & 1u) ? make_double2(v[u].y, v[u].x) : v[u];
+      }
+    }
+  };
+  uint32_t t = blockIdx.x;
+  if (t >= p.n_tiles) return;
+  int par = 0;
+  tile_bases(t, par);
+  __syncthreads();
+  long long bo_cur = s_base[par][1];
+  {
+    const double* __restrict__ src = p.in + s_base[par][0];
+    double2 v[PT_U];
+#pragma unroll
+    for (int u = 0; u < PT_U; ++u) {
+      const int jj = tid + u * PT_THR;
+      if (jj < P) v[u] = __ldcs(reinterpret_cast<const double2*>(src + rd_off[jj]));
+    }
+    park(v);
+  }
+  for (;;) {
+    const uint32_t tn = t + gridDim.x;
+    const bool more = tn < p.n_tiles;
+    if (more) tile_bases(tn, par ^ 1);
+    __syncthreads();  // tile t resident in shared memory; bases of tile tn visible
+    double2 v[PT_U];
+    long long bo_next = 0;
+    if (more) {
+      const double* __restrict__ src = p.in + s_base[par ^ 1][0];
+      bo_next = s_base[par ^ 1][1];
+#pragma unroll
+      for (int u = 0; u < PT_U; ++u) {
+        const int jj = tid + u * PT_THR;
+        if (jj < P) v[u] = __ldcs(reinterpret_cast<const double2*>(src + rd_off[jj]));
+      }
+    }
+    {
+      double* __restrict__ dst = p.out + bo_cur;
+#pragma unroll
+      for (int u = 0; u < PT_U; ++u) {
+        const int jj = tid + u * PT_THR;
+        if (jj < P) {
+          const uint32_t sl = wr_slot[jj];
+          __stcs(reinterpret_cast<double2*>(dst + wr_off[jj]), make_double2(tile[sl & 0xffffu], tile[sl >> 16]));
+        }
+      }
+    }
+    if (!more) break;
+    __syncthreads();  // every slot of tile t has been read
+    park(v);
+    t = tn;
+    bo_cur = bo_next;
+    par ^= 1;
+  }
+}
+
 struct MDim {
   long long card, is, os;  // size, input stride, output stride
 };
@@ -286,7 +400,12 @@ int32_t permute_tiled(int device, const double* in, const std::vector<int32_t>& 
   // resident CTAs per SM: measured at 2^24 entries (rotation of 24 binary dims, 2048-entry tiles): 4 CTAs 0.76 of the
   // HBM peak, 5 CTAs 0.74, 6 CTAs 0.63 -- more CTAs open more DRAM pages at once
   static const int ctas_env = getenv("BN_PERMUTE_CTAS") ? atoi(getenv("BN_PERMUTE_CTAS")) : 4;
-  void (*kern)(const PermuteParams) = T <= PT_THR * PT_U ? permute_kernel<1, 4> : permute_kernel<2, 4>;
+  // 128-bit accesses on both global sides when the first read dim and the first write dim are even and contiguous
+  static const bool no_pairs = getenv("BN_PERMUTE_NO_PAIRS") != nullptr;
+  const bool pairs = !no_pairs && p.nt >= 1 && (p.rcard[0] % 2) == 0 && p.ris[0] == 1 && (p.wcard[0] % 2) == 0 && p.wos[0] == 1 &&
+                     (reinterpret_cast<uintptr_t>(in) % 16) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0;
+  void (*kern)(const PermuteParams) = pairs ? permute_pairs_kernel
+                                            : (T <= PT_THR * PT_U ? permute_kernel<1, 4> : permute_kernel<2, 4>);
   BN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)PT_TILE_MAX * 18 + 256)));
   const DevProps& dp = dev_props(device);
   int per_sm = 0;
