@@ -333,6 +333,12 @@ class Factor:
     def minimum_(self, dims) -> "Factor":
         return self._replace(self.minimum(dims))
 
+    def rand_(self, seed=None) -> "Factor":
+        """rand!(phi) (factors_main.jl:140-143): fill with uniform [0, 1) values.  The reference draws from Julia's global
+        RNG (a stream no reference test pins); here the values come from numpy and go down as one full-slab setindex!."""
+        self[{}] = np.random.default_rng(seed).random(self._shape if self._shape else ())
+        return self
+
     def similar(self) -> "Factor":
         """similar(phi) (factors_main.jl:93): same dims and sizes, contents unspecified (zeros here)."""
         return Factor(self.dimensions, list(self._shape))
