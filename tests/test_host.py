@@ -268,3 +268,28 @@ def test_table_matches_reference_values(bn):
     assert tb["potential"].tolist() == [0.5, 0.2, 0.5, 0.8]
     assert bn.table(net, "b", a=2)["potential"].tolist() == [0.2, 0.8]
     assert bn.table(net, "b", {"a": 1, "b": 2})["potential"].tolist() == [0.5]
+
+
+def test_mle_cpds_from_counts_match_reference_cpd_tests(bn, oracle):
+    """test/test_cpds.jl:21-33,41-45,51-60: fit(DiscreteCPD, ...) = relative frequencies per parental instantiation.
+    Host logic only (learning._cpds_from_counts); the counts come from the oracle here, from the statistics kernel
+    on the device (tests/test_gpu_learning.py holds the two equal)."""
+    from bayesnets_jl_b200.learning import _cpds_from_counts, _split, _structure_layout
+    from conftest import oracle_net_from_layout
+
+    def fit_counts(plist, ncat, mat, names):
+        lay = _structure_layout(plist, ncat, names)
+        counts = oracle.capi.statistics(oracle_net_from_layout(lay), np.ascontiguousarray(np.asarray(mat) - 1, np.uint8))
+        return _cpds_from_counts(names, plist, ncat, _split(lay, counts))
+
+    (cpd,) = fit_counts([[]], [3], [[1, 2, 1, 2, 3]], ["a"])
+    assert cpd.parents == [] and cpd.distributions[0].tolist() == [0.4, 0.4, 0.2]
+    (cpd,) = fit_counts([[]], [3], [[1, 2, 1, 2, 2]], ["a"])               # ncategories=3, state 3 never seen
+    assert cpd.pdf({"a": 1}) == 0.4 and cpd.pdf({"a": 2}) == pytest.approx(0.6) and cpd.pdf({"a": 3}) == 0.0
+    a, b = fit_counts([[], [0]], [3, 2], [[1, 2, 1, 2, 3], [1, 1, 2, 1, 2]], ["a", "b"])
+    assert b.parents == ["a"] and b.parental_ncategories == [3]
+    assert b({"a": 1}).tolist() == [0.5, 0.5] and b({"a": 2}).tolist() == [1.0, 0.0] and b({"a": 3}).tolist() == [0.0, 1.0]
+    # parental_ncategories=[3], target_ncategories=5 -> 15 parameters; an instantiation never seen is uniform
+    a, b = fit_counts([[], [0]], [3, 5], [[1, 2, 1, 2, 2], [1, 1, 2, 1, 2]], ["a", "b"])
+    assert sum(len(d) for d in b.distributions) == 15
+    assert b({"a": 3}).tolist() == [0.2] * 5
