@@ -9,7 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbn_cuda.so")
 
 BN_OK, BN_BAD_ARG, BN_DIM_MISMATCH, BN_NOT_IN_FACTOR, BN_CUDA_ERR = 0, -1, -2, -3, -4
-BN_ZERO_WEIGHT, BN_OOM, BN_UNSUPPORTED, BN_BOUNDS = -5, -6, -7, -8
+BN_ZERO_WEIGHT, BN_OOM, BN_UNSUPPORTED, BN_BOUNDS, BN_NCCL_ERR = -5, -6, -7, -8, -9
+BN_MAX_CARD = 128
+BN_COMM_ID_BYTES = 128
+DTYPE_F64, DTYPE_I64 = 0, 1
+REDUCE_SUM, REDUCE_MAX = 0, 1
 OP_MUL, OP_DIV, OP_ADD, OP_SUB, OP_MAX, OP_MIN = range(6)
 
 
@@ -33,6 +37,23 @@ _SIGS = {
     "bn_device_count": (C.c_int32, [i32p]),
     "bn_set_stream": (C.c_int32, [C.c_void_p]),
     "bn_launch_count": (C.c_uint64, []),
+    "bn_synchronize": (C.c_int32, []),
+    "bn_dev_alloc": (C.c_int32, [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "bn_dev_free": (C.c_int32, [C.c_int32, C.c_void_p]),
+    "bn_dev_memset": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint64]),
+    "bn_dev_upload": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bn_dev_download": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "bn_comm_init_all": (C.c_int32, [i32p, C.c_int32, C.POINTER(h64)]),
+    "bn_comm_unique_id": (C.c_int32, [u8p]),
+    "bn_comm_init_rank": (C.c_int32, [u8p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(h64)]),
+    "bn_comm_info": (C.c_int32, [h64, i32p, i32p, i32p]),
+    "bn_comm_destroy": (C.c_int32, [h64]),
+    "bn_comm_shard": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "bn_comm_allreduce": (C.c_int32, [h64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "bn_comm_allreduce_dev": (C.c_int32, [h64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "bn_comm_barrier": (C.c_int32, [h64]),
+    "bn_net_create_comm": (C.c_int32, [C.c_int32, i32p, i32p, i32p, i64p, f64p, h64, C.POINTER(h64)]),
+    "bn_spec_cache_stats": (C.c_int32, [C.POINTER(C.c_uint64)]),
     "bn_net_create": (C.c_int32, [C.c_int32, i32p, i32p, i32p, i64p, f64p, C.c_int32, C.POINTER(h64)]),
     "bn_net_destroy": (C.c_int32, [h64]),
     "bn_lw_infer": (C.c_int32, [h64, i8p, i32p, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, f64p, f64p]),
@@ -125,6 +146,8 @@ def check(rc: int) -> None:
         raise MemoryError(msg)
     if rc == BN_UNSUPPORTED:
         raise NotImplementedError(msg)
+    if rc == BN_NCCL_ERR:
+        raise BNCudaError(f"NCCL: {msg}")
     raise BNCudaError(f"libbn_cuda status {rc}: {msg}")
 
 
@@ -156,7 +179,73 @@ def launch_count() -> int:
     return int(lib().bn_launch_count())
 
 
+class DeviceBuffer:
+    """A plain device allocation (bn_dev_alloc) for the *_dev entry points: what the host mirror uses where a caller
+    without a CUDA array library needs device-resident results.  Freed by close() / garbage collection."""
+
+    def __init__(self, nbytes: int, device: int = 0, zero: bool = False):
+        import weakref
+        p = C.c_void_p(0)
+        check(lib().bn_dev_alloc(C.c_int32(device), C.c_uint64(int(nbytes)), C.byref(p)))
+        self.ptr, self.nbytes, self.device = int(p.value or 0), int(nbytes), int(device)
+        self._fin = weakref.finalize(self, DeviceBuffer._free, self.device, self.ptr)
+        if zero:
+            self.zero_()
+
+    @staticmethod
+    def _free(device, p):
+        try:
+            lib().bn_dev_free(C.c_int32(device), C.c_void_p(p))
+        except Exception:
+            pass
+
+    def close(self):
+        self._fin()
+
+    def zero_(self):
+        check(lib().bn_dev_memset(C.c_void_p(self.ptr), C.c_int32(0), C.c_uint64(self.nbytes)))
+        return self
+
+    def upload(self, arr):
+        import numpy as np
+        a = np.ascontiguousarray(arr)
+        if a.nbytes > self.nbytes:
+            raise ValueError(f"upload of {a.nbytes} bytes into a {self.nbytes}-byte device buffer")
+        check(lib().bn_dev_upload(C.c_void_p(self.ptr), C.c_void_p(a.ctypes.data), C.c_uint64(a.nbytes)))
+        return self
+
+    def download(self, dtype, count: int | None = None):
+        """Copy back as a numpy array (synchronises the calling thread's current stream)."""
+        import numpy as np
+        dt = np.dtype(dtype)
+        n = self.nbytes // dt.itemsize if count is None else int(count)
+        out = np.empty(n, dt)
+        check(lib().bn_dev_download(C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr), C.c_uint64(n * dt.itemsize)))
+        return out
+
+
+def synchronize() -> None:
+    """Wait for everything this thread enqueued on its current stream (the *_dev entry points are asynchronous)."""
+    check(lib().bn_synchronize())
+
+
+def spec_cache_stats() -> dict:
+    """Counters of the network-specialised kernel cache since load: NVRTC compiles (of which on a background thread),
+    cubins found in the on-disk cache."""
+    v = (C.c_uint64 * 4)()
+    check(lib().bn_spec_cache_stats(v))
+    return {"nvrtc_compiles": int(v[0]), "background_compiles": int(v[1]), "disk_hits": int(v[2]), "kernels_loaded": int(v[3])}
+
+
 def device_count() -> int:
     n = C.c_int32(0)
     check(lib().bn_device_count(C.byref(n)))
     return n.value
+
+
+def device_count_or_zero() -> int:
+    """device_count() that reports 0 instead of raising on a machine without a CUDA driver / device."""
+    try:
+        return device_count()
+    except BNCudaError:
+        return 0

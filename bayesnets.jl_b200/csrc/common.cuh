@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -94,12 +95,14 @@ struct PoolBuf {
   T* p = nullptr;
   size_t n = 0;
   bool owns = true;  // false: a read-only view of memory owned elsewhere (borrow)
+  cudaStream_t s = nullptr;  // the stream the allocation was made on; the free is ordered on the same stream, so a
+                             // finalizer running after bn_set_stream() switched streams cannot free under a kernel
   PoolBuf() = default;
   PoolBuf(const PoolBuf&) = delete;
   PoolBuf& operator=(const PoolBuf&) = delete;
   ~PoolBuf() { release(); }
   void release() {
-    if (p && owns) cudaFreeAsync(p, tl_stream);
+    if (p && owns) cudaFreeAsync(p, s);
     p = nullptr; n = 0; owns = true;
   }
   void borrow(T* ptr, size_t count) {
@@ -109,13 +112,14 @@ struct PoolBuf {
   cudaError_t alloc(size_t count) {
     release();
     n = count;
-    return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), tl_stream);
+    s = tl_stream;
+    return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), s);
   }
-  cudaError_t upload(const T* host, size_t count, cudaStream_t s) {
+  cudaError_t upload(const T* host, size_t count, cudaStream_t st) {
     cudaError_t e = alloc(count);
     if (e != cudaSuccess) return e;
     if (count == 0) return cudaSuccess;
-    return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
   }
 };
 // Per-call temporaries of the host-buffer entry points (bn_sample, bn_gibbs_*, bn_statistics): pool allocations, so a
@@ -130,11 +134,21 @@ void spec_cache_clear(Net* net);
 struct LoopyPlan;  // loopy.cu: message layout + task list of the LoopyBelief kernel (depends on the structure only)
 void loopy_plan_free(LoopyPlan* p);
 
+struct Comm;  // comm.cu: NCCL communicator(s) + one stream per local device
+
+// Threading contract (include/bn_cuda.h): any number of host threads / streams may use one net concurrently.  Per-call
+// staging (programs, tables, evidence bytes, results) is allocated from the stream-ordered pool per call, never shared;
+// the only mutable per-net state is the kernel cache below, guarded by `mu`.
 struct Net {
-  ~Net() { spec_cache_clear(this); loopy_plan_free(loopy); }
+  ~Net();
   LoopyPlan* loopy = nullptr;
+  std::mutex mu;  // guards spec_cache, spec_demand, loopy
   std::unordered_map<std::string, SpecKernel*> spec_cache;
   std::unordered_map<std::string, double> spec_demand;  // work requested per key before its kernel was compiled
+  // multi-GPU (comm.cu): a net created with bn_net_create_comm is the replica on the communicator's first local
+  // device and owns the replicas on the other local devices; sharded entry points fan out over all of them
+  Comm* comm = nullptr;       // not owned
+  std::vector<Net*> peers;    // owned replicas on local devices 1..n_local-1
   int device = 0;
   int n = 0;
   // host copies (planning is host-side)
@@ -145,10 +159,24 @@ struct Net {
   // device copies
   DevBuf<int32_t> d_card;
   DevBuf<double> d_cpt;
-  // scratch reused across calls (grown on demand)
-  DevBuf<uint8_t> scratch;
-  DevBuf<double> result;
 };
+
+// RAII: run a scope on another (device, stream) pair, e.g. a peer replica of a multi-GPU net
+struct StreamScope {
+  cudaStream_t saved;
+  explicit StreamScope(cudaStream_t s) : saved(tl_stream) { tl_stream = s; }
+  ~StreamScope() { tl_stream = saved; }
+};
+
+// comm.cu: fan a sharded job [first, first + n) out over the local GPUs of net->comm (launch(replica, local index, lo,
+// count, out) runs with the replica's device and stream current and zeroes + fills n_out doubles), then ONE
+// ncclAllReduce(sum, fp64); out_dev0 lives on the first local device and is ordered on the caller's stream.
+int32_t comm_fanout(Net* net, uint64_t first, uint64_t n, size_t n_out, double* out_dev0,
+                    const std::function<int32_t(Net*, int, uint64_t, uint64_t, double*)>& launch);
+int32_t comm_sync_peers(Net* net);
+void comm_describe(const Net* net, int* world, int* first_rank, int* n_local);
+cudaStream_t comm_stream(const Net* net, int local_index);
+void comm_shard_of(const Net* net, int local_index, uint64_t first, uint64_t n, uint64_t* lo, uint64_t* cnt);
 
 struct Factor {
   int device = 0;
@@ -158,6 +186,9 @@ struct Factor {
 };
 
 Net* get_net(bn_net_t h);
+bn_net_t register_net(Net* net);
+int32_t make_net(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                 const int64_t* cpt_off, const double* cpt, int32_t device, Net** out);
 void build_children(Net* net);
 Factor* get_factor(bn_factor_t h);
 bn_factor_t register_factor(Factor* f);
@@ -189,6 +220,7 @@ struct SampleProgram {
   uint32_t n_free = 0;
   std::vector<NodePlan> plan;   // one per node, topological order
 };
+int32_t check_evidence(const Net* net, const int8_t* evidence);  // sampling.cu: states < card, else BN_BOUNDS
 int32_t compile_program(const Net& net, const int8_t* evidence, bool treat_all_free, uint32_t state_stride,
                         SampleProgram* out);
 // specialize.cu: returns BN_OK and sets *used when the NVRTC-specialised kernel handled the launch

@@ -107,39 +107,37 @@ int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>&
   return BN_OK;
 }
 
-}  // namespace bn
 
-using namespace bn;
-
-extern "C" {
-
-const char* bn_last_error(void) { return bn::tl_error; }
-int32_t bn_version(void) { return 100; }
-
-int32_t bn_device_count(int32_t* out_n) {
-  BN_REQUIRE(out_n, BN_BAD_ARG, "out_n is NULL");
-  int n = 0;
-  BN_CUDA_TRY(cudaGetDeviceCount(&n));
-  *out_n = n;
-  return BN_OK;
+Net::~Net() {
+  spec_cache_clear(this);
+  loopy_plan_free(loopy);
+  for (Net* p : peers) {
+    cudaSetDevice(p->device);
+    delete p;
+  }
+  cudaSetDevice(device);
 }
 
-int32_t bn_set_stream(void* cuda_stream) {
-  bn::tl_stream = (cudaStream_t)cuda_stream;
-  return BN_OK;
+bn_net_t register_net(Net* net) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint64_t h = g_next++;
+  g_nets[h] = net;
+  return h;
 }
 
-uint64_t bn_launch_count(void) { return bn::g_launches.load(); }
-
-int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
-                      const int64_t* cpt_off, const double* cpt, int32_t device, bn_net_t* out_net) {
-  BN_REQUIRE(out_net && card && par_ptr && cpt_off && cpt, BN_BAD_ARG, "bn_net_create: NULL argument");
+// Validate a flat network and upload it to `device` (the body of bn_net_create; bn_net_create_comm calls it once per
+// local device of the communicator).
+int32_t make_net(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                 const int64_t* cpt_off, const double* cpt, int32_t device, Net** out) {
+  BN_REQUIRE(out && card && par_ptr && cpt_off && cpt, BN_BAD_ARG, "bn_net_create: NULL argument");
   BN_REQUIRE(n_nodes > 0, BN_BAD_ARG, "bn_net_create: n_nodes must be > 0");
   BN_REQUIRE(par_ptr[0] == 0 && cpt_off[0] == 0, BN_BAD_ARG, "bn_net_create: CSR offsets must start at 0");
   int32_t n_par = par_ptr[n_nodes];
   BN_REQUIRE(n_par == 0 || par_idx, BN_BAD_ARG, "bn_net_create: par_idx is NULL");
   for (int i = 0; i < n_nodes; ++i) {
-    BN_REQUIRE(card[i] >= 1 && card[i] <= 255, BN_BAD_ARG, "node %d: cardinality %d outside 1..255", i, card[i]);
+    // evidence and sampled states travel as int8 / uint8 with -1 / 0xFF reserved: 128 states per node is the ABI limit
+    BN_REQUIRE(card[i] >= 1 && card[i] <= BN_MAX_CARD, BN_BAD_ARG, "node %d: cardinality %d outside 1..%d", i, card[i],
+               BN_MAX_CARD);
     BN_REQUIRE(par_ptr[i + 1] >= par_ptr[i], BN_BAD_ARG, "par_ptr not monotone at node %d", i);
     int64_t q = 1;
     for (int k = par_ptr[i]; k < par_ptr[i + 1]; ++k) {
@@ -169,9 +167,10 @@ int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_p
   net->cpt_off.assign(cpt_off, cpt_off + n_nodes + 1);
   net->cpt.assign(cpt, cpt + cpt_off[n_nodes]);
   build_children(net);
-  cudaStream_t s = bn::tl_stream;
   // only what kernels read lives in HBM: the fp64 CPTs (Gibbs, Factor(bn, node)) and the cardinalities; graph
-  // structure is consumed by the host-side planners (sampling programs, code generators, elimination order)
+  // structure is consumed by the host-side planners (sampling programs, code generators, elimination order).
+  // The upload is complete on return (the stream must belong to `device`: comm.cu switches tl_stream per replica).
+  cudaStream_t s = tl_stream;
   cudaError_t e = cudaSuccess;
   auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
   chk(net->d_card.upload(net->card.data(), net->card.size(), s));
@@ -183,12 +182,75 @@ int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_p
     cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? BN_OOM : BN_CUDA_ERR;
   }
-  {
-    std::lock_guard<std::mutex> lk(bn::g_mu);
-    uint64_t h = bn::g_next++;
-    bn::g_nets[h] = net;
-    *out_net = h;
-  }
+  *out = net;
+  return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" {
+
+const char* bn_last_error(void) { return bn::tl_error; }
+int32_t bn_version(void) { return 100; }
+
+int32_t bn_device_count(int32_t* out_n) {
+  BN_REQUIRE(out_n, BN_BAD_ARG, "out_n is NULL");
+  int n = 0;
+  BN_CUDA_TRY(cudaGetDeviceCount(&n));
+  *out_n = n;
+  return BN_OK;
+}
+
+int32_t bn_set_stream(void* cuda_stream) {
+  bn::tl_stream = (cudaStream_t)cuda_stream;
+  return BN_OK;
+}
+
+uint64_t bn_launch_count(void) { return bn::g_launches.load(); }
+
+int32_t bn_synchronize(void) {
+  BN_CUDA_TRY(cudaStreamSynchronize(bn::tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_dev_alloc(int32_t device, uint64_t bytes, void** out_ptr) {
+  BN_REQUIRE(out_ptr, BN_BAD_ARG, "bn_dev_alloc: out_ptr is NULL");
+  BN_CUDA_TRY(cudaSetDevice(device));
+  bn::ensure_pool(device);
+  BN_CUDA_TRY(cudaMallocAsync(out_ptr, bytes ? bytes : 1, bn::tl_stream));
+  return BN_OK;
+}
+int32_t bn_dev_free(int32_t device, void* ptr) {
+  if (!ptr) return BN_OK;
+  BN_CUDA_TRY(cudaSetDevice(device));
+  BN_CUDA_TRY(cudaFreeAsync(ptr, bn::tl_stream));
+  return BN_OK;
+}
+int32_t bn_dev_memset(void* ptr, int32_t value, uint64_t bytes) {
+  BN_REQUIRE(ptr || !bytes, BN_BAD_ARG, "bn_dev_memset: NULL pointer");
+  BN_CUDA_TRY(cudaMemsetAsync(ptr, value, bytes, bn::tl_stream));
+  return BN_OK;
+}
+int32_t bn_dev_upload(void* dst_dev, const void* src, uint64_t bytes) {
+  BN_REQUIRE((dst_dev && src) || !bytes, BN_BAD_ARG, "bn_dev_upload: NULL pointer");
+  BN_CUDA_TRY(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, bn::tl_stream));
+  return BN_OK;
+}
+int32_t bn_dev_download(void* dst, const void* src_dev, uint64_t bytes) {
+  BN_REQUIRE((dst && src_dev) || !bytes, BN_BAD_ARG, "bn_dev_download: NULL pointer");
+  BN_CUDA_TRY(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, bn::tl_stream));
+  BN_CUDA_TRY(cudaStreamSynchronize(bn::tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                      const int64_t* cpt_off, const double* cpt, int32_t device, bn_net_t* out_net) {
+  BN_REQUIRE(out_net, BN_BAD_ARG, "bn_net_create: NULL argument");
+  Net* net = nullptr;
+  BN_TRY(bn::make_net(n_nodes, card, par_ptr, par_idx, cpt_off, cpt, device, &net));
+  *out_net = bn::register_net(net);
   return BN_OK;
 }
 

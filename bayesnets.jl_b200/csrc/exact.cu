@@ -115,44 +115,40 @@ extern "C" int32_t bn_exact_infer(bn_net_t hnet, const int8_t* evidence, const i
       BN_TRY(bn_factor_eliminate(with.data(), (int32_t)with.size(), &sd, 1, &res));
     } else {
       bn_factor_t acc = with[0];
-      bool own = false;
+      HandleBag tmp;  // the running product is owned here, so an error return cannot leak it
       for (size_t k = 1; k < with.size(); ++k) {
         bn_factor_t nxt = 0;
         BN_TRY(bn_factor_product(acc, with[k], &nxt));
-        if (own) bn_factor_free(acc);
-        acc = nxt; own = true;
+        if (!tmp.hs.empty()) tmp.drop(acc);
+        tmp.hs.push_back(nxt);
+        acc = nxt;
       }
-      int32_t rc = bn_factor_sum(acc, &sd, 1, &res);
-      if (own) bn_factor_free(acc);
-      BN_TRY(rc);
+      BN_TRY(bn_factor_sum(acc, &sd, 1, &res));
     }
     for (bn_factor_t h : with) bag.drop(h);
     bag.hs.push_back(res);  // push!(factors, ...) -- appended last, like the reference
   }
   // phi = normalize!(reduce(*, factors))   (:31)
   bn_factor_t acc = bag.hs[0];
-  bool own = false;
+  HandleBag tmp;  // owns the running product / the copy below on every exit path
   for (size_t k = 1; k < bag.hs.size(); ++k) {
     bn_factor_t nxt = 0;
-    int32_t rc = bn_factor_product(acc, bag.hs[k], &nxt);
-    if (own) bn_factor_free(acc);
-    BN_TRY(rc);
-    acc = nxt; own = true;
+    BN_TRY(bn_factor_product(acc, bag.hs[k], &nxt));
+    if (!tmp.hs.empty()) tmp.drop(acc);
+    tmp.hs.push_back(nxt);
+    acc = nxt;
   }
   if (!get_factor(acc)->data.owns) {  // a lone CPT view (single-factor network): normalise a copy, never the net
     bn_factor_t cp = 0;
     BN_TRY(bn_factor_slice(acc, nullptr, nullptr, 0, &cp));
-    acc = cp; own = true;
+    tmp.hs.push_back(cp);
+    acc = cp;
   }
-  int32_t rc = bn_factor_normalize(acc, 1);
+  BN_TRY(bn_factor_normalize(acc, 1));
   Factor* f = get_factor(acc);
-  if (rc == BN_OK) {
-    for (size_t i = 0; i < f->dims.size(); ++i) {
-      if (out_dims) out_dims[i] = f->dims[i];
-      if (out_card) out_card[i] = f->card[i];
-    }
-    rc = bn_factor_download(acc, out);
+  for (size_t i = 0; i < f->dims.size(); ++i) {
+    if (out_dims) out_dims[i] = f->dims[i];
+    if (out_card) out_card[i] = f->card[i];
   }
-  if (own) bn_factor_free(acc);
-  return rc;
+  return bn_factor_download(acc, out);
 }

@@ -362,16 +362,12 @@ using namespace bn;
 
 extern "C" {
 
-int32_t bn_gibbs_infer_dev(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
-                           uint64_t first_chain, uint64_t n_chains, int64_t nsamples, int64_t burn_in,
-                           int64_t thin, int32_t mode, uint64_t seed, double* out_dev);
-
-static int32_t gibbs_infer_impl(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
+// One GPU's share of a Gibbs inference job: chains [first_chain, first_chain + n_chains) on `net`'s device, enqueued
+// on the current stream (asynchronous: per-call staging is stream-ordered pool memory).
+static int32_t gibbs_infer_impl(Net* net, const int8_t* evidence, const int32_t* query, int32_t n_query,
                                 uint64_t first_chain, uint64_t n_chains, int64_t nsamples, int64_t burn_in,
                                 int64_t thin, int32_t mode, uint64_t seed, uint8_t* d_state, int32_t init_from_state,
                                 double* out_dev, double* d_chain_counts) {
-  Net* net = get_net(h);
-  BN_REQUIRE(net, BN_BAD_ARG, "bn_gibbs_infer: unknown net handle");
   // src/Inference/gibbs.jl:70-71
   BN_REQUIRE(burn_in < nsamples, BN_BAD_ARG, "Burn in (%lld) must be less than number of samples (%lld)",
              (long long)burn_in, (long long)nsamples);
@@ -388,6 +384,7 @@ static int32_t gibbs_infer_impl(bn_net_t h, const int8_t* evidence, const int32_
     ncell *= net->card[query[j]];
     BN_REQUIRE(ncell <= 4096, BN_UNSUPPORTED, "query table has more than 4096 cells");
   }
+  BN_TRY(check_evidence(net, evidence));
   BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)ncell * 8, tl_stream));
   if (n_chains == 0) return BN_OK;
   {  // network-specialised kernel first (specialize.cu); identical counts
@@ -396,15 +393,12 @@ static int32_t gibbs_infer_impl(bn_net_t h, const int8_t* evidence, const int32_
                                     mode == BN_GIBBS_FULL, first_chain, n_chains, burn_in, thin,
                                     (nsamples - burn_in + thin - 1) / thin, seed, out_dev, d_chain_counts, d_state,
                                     init_from_state, &used));
-    if (used) {
-      BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
-      return BN_OK;
-    }
+    if (used) return BN_OK;
   }
   const DevProps& dp = dev_props(net->device);
   const int T = gibbs_threads(dp, net->n, (size_t)ncell * 8, n_chains);
   BN_REQUIRE(T > 0, BN_UNSUPPORTED, "network too large for the Gibbs kernel (%d nodes)", net->n);
-  GibbsDevice dev;
+  GibbsDevice dev;  // stream-ordered pool staging: freed after the kernel, in stream order
   GibbsArgs a{};
   BN_TRY(stage_gibbs(net, evidence, (uint32_t)T, query, n_query, qstride, &dev, &a));
   a.first_chain = first_chain;
@@ -426,16 +420,34 @@ static int32_t gibbs_infer_impl(bn_net_t h, const int8_t* evidence, const int32_
   gibbs_infer_kernel<<<grid, T, smem, tl_stream>>>(a);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
-  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));  // staging buffers die with `dev`
   return BN_OK;
+}
+
+static int64_t query_cells(const Net* net, const int32_t* query, int32_t n_query) {
+  int64_t ncell = 1;
+  for (int j = 0; j < n_query; ++j)
+    if (query && query[j] >= 0 && query[j] < net->n) ncell *= net->card[query[j]];
+  return ncell;
 }
 
 int32_t bn_gibbs_infer_dev(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
                            uint64_t first_chain, uint64_t n_chains, int64_t nsamples, int64_t burn_in,
                            int64_t thin, int32_t mode, uint64_t seed, double* out_dev) {
+  Net* net = get_net(h);
+  BN_REQUIRE(net, BN_BAD_ARG, "bn_gibbs_infer: unknown net handle");
   BN_REQUIRE(out_dev, BN_BAD_ARG, "bn_gibbs_infer_dev: output is NULL");
-  return gibbs_infer_impl(h, evidence, query, n_query, first_chain, n_chains, nsamples, burn_in, thin, mode, seed,
-                          nullptr, 0, out_dev, nullptr);
+  if (!net->comm)
+    return gibbs_infer_impl(net, evidence, query, n_query, first_chain, n_chains, nsamples, burn_in, thin, mode, seed,
+                            nullptr, 0, out_dev, nullptr);
+  // multi-GPU net: chains are sharded by global chain index, integer counts all-reduced (exactly the 1-GPU counts)
+  BN_CUDA_TRY(cudaSetDevice(net->device));
+  const int64_t ncell = query_cells(net, query, n_query);
+  BN_REQUIRE(ncell <= 4096, BN_UNSUPPORTED, "query table has more than 4096 cells");
+  return comm_fanout(net, first_chain, n_chains, (size_t)ncell, out_dev,
+                     [&](Net* r, int, uint64_t lo, uint64_t cnt, double* out) {
+                       return gibbs_infer_impl(r, evidence, query, n_query, lo, cnt, nsamples, burn_in, thin, mode, seed,
+                                               nullptr, 0, out, nullptr);
+                     });
 }
 
 int32_t bn_gibbs_infer(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
@@ -447,32 +459,64 @@ int32_t bn_gibbs_infer(bn_net_t h, const int8_t* evidence, const int32_t* query,
   BN_REQUIRE(out_counts, BN_BAD_ARG, "bn_gibbs_infer: out_counts is NULL");
   BN_REQUIRE(!(init_from_state && !state_inout), BN_BAD_ARG, "init_from_state needs state_inout");
   BN_CUDA_TRY(cudaSetDevice(net->device));
-  int64_t ncell = 1;
-  for (int j = 0; j < n_query; ++j)
-    if (query && query[j] >= 0 && query[j] < net->n) ncell *= net->card[query[j]];
+  const int64_t ncell = query_cells(net, query, n_query);
   BN_REQUIRE(ncell <= 4096, BN_UNSUPPORTED, "query table has more than 4096 cells");
-  TmpBuf<double> d_out, d_cc;
-  TmpBuf<uint8_t> d_state;
+  const size_t nn = (size_t)net->n;
+  if (init_from_state)  // a resumed state indexes the CPTs on the device: it must be inside the cardinalities
+    for (uint64_t c = 0; c < n_chains; ++c)
+      for (size_t i = 0; i < nn; ++i)
+        BN_REQUIRE(state_inout[c * nn + i] < net->card[i], BN_BOUNDS, "chain %llu: state %d of node %d outside 0..%d",
+                   (unsigned long long)c, (int)state_inout[c * nn + i], (int)i, net->card[i] - 1);
+  int world = 1, first_rank = 0, nl = 1;
+  comm_describe(net, &world, &first_rank, &nl);
+  // per local GPU: the rows (chains) of state_inout / out_chain_counts that GPU runs
+  struct Shard { TmpBuf<uint8_t> st; TmpBuf<double> cc; uint64_t lo = 0, cnt = 0; cudaStream_t s = nullptr; int device = 0; };
+  std::vector<Shard> sh((size_t)nl);
+  auto launch = [&](Net* r, int d, uint64_t lo, uint64_t cnt, double* out) -> int32_t {
+    Shard& S = sh[(size_t)d];
+    S.lo = lo; S.cnt = cnt; S.s = tl_stream; S.device = r->device;
+    const size_t row0 = (size_t)(lo - first_chain);
+    if (state_inout) {
+      BN_CUDA_TRY(S.st.alloc((size_t)cnt * nn));
+      if (init_from_state && cnt)
+        BN_CUDA_TRY(cudaMemcpyAsync(S.st.p, state_inout + row0 * nn, (size_t)cnt * nn, cudaMemcpyHostToDevice, tl_stream));
+    }
+    if (out_chain_counts) {
+      BN_CUDA_TRY(S.cc.alloc((size_t)cnt * ncell));
+      BN_CUDA_TRY(cudaMemsetAsync(S.cc.p, 0, (size_t)cnt * ncell * 8, tl_stream));
+    }
+    return gibbs_infer_impl(r, evidence, query, n_query, lo, cnt, nsamples, burn_in, thin, mode, seed,
+                            state_inout ? S.st.p : nullptr, init_from_state, out, out_chain_counts ? S.cc.p : nullptr);
+  };
+  TmpBuf<double> d_out;
   BN_CUDA_TRY(d_out.alloc((size_t)ncell));
-  const size_t nst = (size_t)n_chains * net->n;
-  if (state_inout) {
-    BN_CUDA_TRY(d_state.alloc(nst));
-    if (init_from_state)
-      BN_CUDA_TRY(cudaMemcpyAsync(d_state.p, state_inout, nst, cudaMemcpyHostToDevice, tl_stream));
+  int32_t rc = net->comm ? comm_fanout(net, first_chain, n_chains, (size_t)ncell, d_out.p, launch)
+                         : launch(net, 0, first_chain, n_chains, d_out.p);
+  if (rc == BN_OK) {
+    BN_CUDA_TRY(cudaMemcpyAsync(out_counts, d_out.p, (size_t)ncell * 8, cudaMemcpyDeviceToHost, tl_stream));
+    for (Shard& S : sh) {
+      BN_CUDA_TRY(cudaSetDevice(S.device));
+      const size_t row0 = (size_t)(S.lo - first_chain);
+      if (state_inout && S.cnt)
+        BN_CUDA_TRY(cudaMemcpyAsync(state_inout + row0 * nn, S.st.p, (size_t)S.cnt * nn, cudaMemcpyDeviceToHost, S.s));
+      if (out_chain_counts && S.cnt)
+        BN_CUDA_TRY(cudaMemcpyAsync(out_chain_counts + row0 * ncell, S.cc.p, (size_t)S.cnt * ncell * 8,
+                                    cudaMemcpyDeviceToHost, S.s));
+    }
   }
-  if (out_chain_counts) {
-    BN_CUDA_TRY(d_cc.alloc((size_t)n_chains * ncell));
-    BN_CUDA_TRY(cudaMemsetAsync(d_cc.p, 0, (size_t)n_chains * ncell * 8, tl_stream));
+  for (Shard& S : sh) {  // wait for every local GPU, release its staging on its own device
+    if (cudaSetDevice(S.device) != cudaSuccess) continue;
+    cudaError_t e = cudaStreamSynchronize(S.s);
+    S.st.release();
+    S.cc.release();
+    if (e != cudaSuccess && rc == BN_OK) {
+      set_error("bn_gibbs_infer: %s", cudaGetErrorString(e));
+      rc = BN_CUDA_ERR;
+    }
   }
-  BN_TRY(gibbs_infer_impl(h, evidence, query, n_query, first_chain, n_chains, nsamples, burn_in, thin, mode, seed,
-                          state_inout ? d_state.p : nullptr, init_from_state, d_out.p,
-                          out_chain_counts ? d_cc.p : nullptr));
-  BN_CUDA_TRY(cudaMemcpyAsync(out_counts, d_out.p, (size_t)ncell * 8, cudaMemcpyDeviceToHost, tl_stream));
-  if (state_inout && nst) BN_CUDA_TRY(cudaMemcpyAsync(state_inout, d_state.p, nst, cudaMemcpyDeviceToHost, tl_stream));
-  if (out_chain_counts && n_chains)
-    BN_CUDA_TRY(cudaMemcpyAsync(out_chain_counts, d_cc.p, (size_t)n_chains * ncell * 8, cudaMemcpyDeviceToHost, tl_stream));
-  BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
-  return BN_OK;
+  cudaSetDevice(net->device);
+  if (rc == BN_OK) BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+  return rc;
 }
 
 int32_t bn_gibbs_sample(bn_net_t h, const int8_t* evidence, uint64_t first_chain, uint64_t n_chains,

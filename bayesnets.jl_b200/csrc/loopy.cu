@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(MINB > 0 ? 256 : 320, MINB) loopy_kernel(const
 }
 
 static int32_t loopy_plan(Net* net) {
+  std::lock_guard<std::mutex> lk(net->mu);  // built once per net; read-only afterwards
   if (net->loopy) return BN_OK;
   const int n = net->n;
   auto* P = new LoopyPlan();

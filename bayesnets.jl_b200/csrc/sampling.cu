@@ -336,12 +336,14 @@ static int32_t launch_particles(Net* net, const int8_t* evidence, bool all_free,
   SampleProgram prg;
   BN_TRY(compile_program(*net, evidence, all_free, (uint32_t)shp.threads, &prg));
 
-  // device scratch: [program words | query pairs | evidence]
+  // per-call device staging from the stream-ordered pool: [program words | query pairs | evidence]; freed (in stream
+  // order, after the kernel) when `stage` goes out of scope, so concurrent calls on one net never share it
   const size_t words_bytes = prg.words.size() * 4;
   const size_t q_off = (words_bytes + 15) / 16 * 16;
   const size_t ev_off = q_off + ((size_t)n_query * 8 + 15) / 16 * 16;
   const size_t total = ev_off + (size_t)net->n + 16;
-  if (net->scratch.n < total) BN_CUDA_TRY(net->scratch.alloc(total * 2));
+  TmpBuf<unsigned char> stage;
+  BN_CUDA_TRY(stage.alloc(total));
   std::vector<unsigned char> host(total, 0);
   memcpy(host.data(), prg.words.data(), words_bytes);
   uint32_t* hq = reinterpret_cast<uint32_t*>(host.data() + q_off);
@@ -351,22 +353,31 @@ static int32_t launch_particles(Net* net, const int8_t* evidence, bool all_free,
   }
   int8_t* hev = reinterpret_cast<int8_t*>(host.data() + ev_off);
   for (int i = 0; i < net->n; ++i) hev[i] = evidence ? evidence[i] : (int8_t)-1;
-  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, host.data(), total, cudaMemcpyHostToDevice, s));
+  BN_CUDA_TRY(cudaMemcpyAsync(stage.p, host.data(), total, cudaMemcpyHostToDevice, s));
 
-  a.words = reinterpret_cast<const uint32_t*>(net->scratch.p);
+  a.words = reinterpret_cast<const uint32_t*>(stage.p);
   a.prog_words = prg.prog_words;
   a.table_words = prg.table_words;
   a.n_nodes = (uint32_t)net->n;
   a.tables_in_smem = shp.tables_in_smem ? 1u : 0u;
-  a.query = reinterpret_cast<const uint32_t*>(net->scratch.p + q_off);
+  a.query = reinterpret_cast<const uint32_t*>(stage.p + q_off);
   a.n_query = n_query;
-  a.evidence = reinterpret_cast<const int8_t*>(net->scratch.p + ev_off);
+  a.evidence = reinterpret_cast<const int8_t*>(stage.p + ev_off);
 
   BN_CUDA_TRY(cudaFuncSetAttribute(particle_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)shp.smem));
   particle_kernel<MODE><<<shp.grid, shp.threads, shp.smem, s>>>(a);
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
+  return BN_OK;
+}
+
+// evidence states must index the node's CPT: a state >= card would read out of bounds on the device
+int32_t check_evidence(const Net* net, const int8_t* evidence) {
+  if (!evidence) return BN_OK;
+  for (int i = 0; i < net->n; ++i)
+    BN_REQUIRE(evidence[i] < net->card[i], BN_BOUNDS, "evidence state %d of node %d outside 0..%d", (int)evidence[i], i,
+               net->card[i] - 1);
   return BN_OK;
 }
 
@@ -395,15 +406,10 @@ using namespace bn;
 
 extern "C" {
 
-int32_t bn_lw_infer_dev(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
-                        uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_dev) {
-  Net* net = get_net(h);
-  BN_REQUIRE(net, BN_BAD_ARG, "bn_lw_infer: unknown net handle");
-  BN_REQUIRE(out_dev, BN_BAD_ARG, "bn_lw_infer: output is NULL");
-  BN_CUDA_TRY(cudaSetDevice(net->device));
-  std::vector<int64_t> qstride;
-  int64_t ncell = 1;
-  BN_TRY(check_query(net, evidence, query, n_query, &qstride, &ncell));
+// One GPU's share of a likelihood-weighting job: particles [first, first + n) on `net`'s device, current stream.
+static int32_t lw_infer_local(Net* net, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                              const std::vector<int64_t>& qstride, int64_t ncell, uint64_t first_particle,
+                              uint64_t n_particles, uint64_t seed, double* out_dev) {
   BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)(ncell + 2) * 8, tl_stream));
   if (n_particles == 0) return BN_OK;
   // network-specialised kernel first (specialize.cu); the generic interpreter covers everything else
@@ -421,6 +427,25 @@ int32_t bn_lw_infer_dev(bn_net_t h, const int8_t* evidence, const int32_t* query
   return launch_particles<MODE_INFER>(net, evidence, false, a, (uint32_t)n_query, query, qstride);
 }
 
+int32_t bn_lw_infer_dev(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
+                        uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_dev) {
+  Net* net = get_net(h);
+  BN_REQUIRE(net, BN_BAD_ARG, "bn_lw_infer: unknown net handle");
+  BN_REQUIRE(out_dev, BN_BAD_ARG, "bn_lw_infer: output is NULL");
+  BN_CUDA_TRY(cudaSetDevice(net->device));
+  BN_TRY(check_evidence(net, evidence));
+  std::vector<int64_t> qstride;
+  int64_t ncell = 1;
+  BN_TRY(check_query(net, evidence, query, n_query, &qstride, &ncell));
+  if (!net->comm)
+    return lw_infer_local(net, evidence, query, n_query, qstride, ncell, first_particle, n_particles, seed, out_dev);
+  // multi-GPU net: every GPU of the communicator takes its share of the global particle range, then one all-reduce
+  return comm_fanout(net, first_particle, n_particles, (size_t)ncell + 2, out_dev,
+                     [&](Net* r, int, uint64_t lo, uint64_t cnt, double* out) {
+                       return lw_infer_local(r, evidence, query, n_query, qstride, ncell, lo, cnt, seed, out);
+                     });
+}
+
 int32_t bn_lw_infer(bn_net_t h, const int8_t* evidence, const int32_t* query, int32_t n_query,
                     uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_counts,
                     double* out_stats) {
@@ -432,11 +457,13 @@ int32_t bn_lw_infer(bn_net_t h, const int8_t* evidence, const int32_t* query, in
   for (int j = 0; j < n_query; ++j)
     if (query && query[j] >= 0 && query[j] < net->n) ncell *= net->card[query[j]];
   BN_REQUIRE(ncell <= 16384, BN_UNSUPPORTED, "query table has more than 16384 cells");
-  if (net->result.n < (size_t)ncell + 2) BN_CUDA_TRY(net->result.alloc((size_t)ncell + 2));
-  BN_TRY(bn_lw_infer_dev(h, evidence, query, n_query, first_particle, n_particles, seed, net->result.p));
+  TmpBuf<double> result;  // per call: concurrent calls on one net never share a result buffer
+  BN_CUDA_TRY(result.alloc((size_t)ncell + 2));
+  BN_TRY(bn_lw_infer_dev(h, evidence, query, n_query, first_particle, n_particles, seed, result.p));
   std::vector<double> host((size_t)ncell + 2);
-  BN_CUDA_TRY(cudaMemcpyAsync(host.data(), net->result.p, host.size() * 8, cudaMemcpyDeviceToHost, tl_stream));
+  BN_CUDA_TRY(cudaMemcpyAsync(host.data(), result.p, host.size() * 8, cudaMemcpyDeviceToHost, tl_stream));
   BN_CUDA_TRY(cudaStreamSynchronize(tl_stream));
+  if (net->comm) BN_TRY(comm_sync_peers(net));
   memcpy(out_counts, host.data(), (size_t)ncell * 8);
   if (out_stats) { out_stats[0] = host[ncell]; out_stats[1] = host[ncell + 1]; }
   return BN_OK;

@@ -22,8 +22,15 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <condition_variable>
+#include <cstring>
+#include <functional>
 #include <memory>
 #include <sstream>
+#include <thread>
 
 namespace bn {
 
@@ -38,6 +45,7 @@ struct Nvrtc {
   nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
   nvrtcResult (*DestroyProgram)(nvrtcProgram*);
   const char* (*GetErrorString)(nvrtcResult);
+  nvrtcResult (*Version)(int*, int*) = nullptr;
   bool ok = false;
 };
 
@@ -62,6 +70,7 @@ static Nvrtc& nvrtc() {
     BN_SYM(GetProgramLog, "nvrtcGetProgramLog")
     BN_SYM(DestroyProgram, "nvrtcDestroyProgram")
     BN_SYM(GetErrorString, "nvrtcGetErrorString")
+    BN_SYM(Version, "nvrtcVersion")
 #undef BN_SYM
     n.ok = true;
   });
@@ -353,6 +362,151 @@ static int32_t nvrtc_compile(const std::string& src, std::vector<char>* cubin, s
   nv.DestroyProgram(&prog);
   return BN_OK;
 }
+static const char* kToolchainTag = "nvrtc sm_100a -lineinfo c++17 fmad=false v2";
+
+// ------------------------------------------------------------------------------------------ cubin cache
+// Generated source -> cubin, three levels:
+//   1. process-wide table keyed by the generated source (any net handle / device with the same structure, evidence
+//      mask and query reuses it);
+//   2. an on-disk cache (BN_CUBIN_CACHE, default $XDG_CACHE_HOME/bn_cuda or ~/.cache/bn_cuda; "off" disables): one file
+//      per source, named by a 128-bit hash of (toolchain tag, NVRTC version, source) and carrying the source itself, which
+//      is compared byte for byte on load -- a second process finds its kernels without paying NVRTC (~10 ms per node);
+//   3. NVRTC, either blocking (explicit "specialised" mode) or on a background host thread while the interpreter kernel
+//      keeps serving calls ("auto" mode): the first-ever call of a process never waits for a compile.
+struct CubinEntry {
+  enum State { COMPILING, READY, FAILED } state = COMPILING;
+  std::vector<char> cubin;
+  std::string log;
+  bool from_disk = false;
+};
+static std::mutex g_cubin_mu;
+static std::condition_variable g_cubin_cv;
+static std::unordered_map<std::string, std::shared_ptr<CubinEntry>> g_cubins;
+static std::atomic<uint64_t> g_spec_compiles{0}, g_disk_hits{0}, g_bg_compiles{0};
+
+struct BgThreads {  // background compiles are joined before the library is torn down
+  std::mutex mu;
+  std::vector<std::thread> th;
+  ~BgThreads() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& t : th) if (t.joinable()) t.join();
+  }
+};
+static BgThreads& bg_threads() { static BgThreads b; return b; }
+
+static uint64_t fnv1a(const std::string& s, uint64_t h) {
+  for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
+  return h;
+}
+
+static std::string cache_dir() {
+  const char* e = getenv("BN_CUBIN_CACHE");
+  if (e && (!strcmp(e, "off") || !strcmp(e, "0") || !*e)) return "";
+  std::string d;
+  if (e) d = e;
+  else if (const char* x = getenv("XDG_CACHE_HOME")) d = std::string(x) + "/bn_cuda";
+  else if (const char* h = getenv("HOME")) d = std::string(h) + "/.cache/bn_cuda";
+  else return "";
+  // mkdir -p (two levels are enough for the defaults)
+  for (size_t i = 1; i <= d.size(); ++i)
+    if (i == d.size() || d[i] == '/') ::mkdir(d.substr(0, i).c_str(), 0755);
+  return d;
+}
+
+static std::string cache_file(const std::string& src) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return "";
+  int major = 0, minor = 0;
+  if (nvrtc().Version) nvrtc().Version(&major, &minor);
+  const std::string tag = std::string(kToolchainTag) + " " + std::to_string(major) + "." + std::to_string(minor);
+  const uint64_t h1 = fnv1a(src, fnv1a(tag, 0xcbf29ce484222325ull)), h2 = fnv1a(src, fnv1a(tag, 0x84222325cbf29ce4ull));
+  char name[64];
+  snprintf(name, sizeof(name), "/%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
+  return dir + name;
+}
+
+static bool disk_load(const std::string& src, std::vector<char>* cubin) {
+  const std::string f = cache_file(src);
+  if (f.empty()) return false;
+  FILE* fp = fopen(f.c_str(), "rb");
+  if (!fp) return false;
+  bool ok = false;
+  uint64_t hdr[3];  // magic, source bytes, cubin bytes
+  if (fread(hdr, 8, 3, fp) == 3 && hdr[0] == 0x314e4942554342ull && hdr[1] == src.size() && hdr[2] < (1ull << 31)) {
+    std::string stored(hdr[1], '\0');
+    cubin->resize(hdr[2]);
+    ok = fread(&stored[0], 1, hdr[1], fp) == hdr[1] && fread(cubin->data(), 1, hdr[2], fp) == hdr[2] && stored == src;
+  }
+  fclose(fp);
+  return ok;
+}
+
+static void disk_store(const std::string& src, const std::vector<char>& cubin) {
+  const std::string f = cache_file(src);
+  if (f.empty()) return;
+  const std::string tmp = f + ".tmp" + std::to_string((long long)getpid()) + "_" + std::to_string((long long)(uintptr_t)&cubin);
+  FILE* fp = fopen(tmp.c_str(), "wb");
+  if (!fp) return;
+  const uint64_t hdr[3] = {0x314e4942554342ull, src.size(), cubin.size()};
+  const bool ok = fwrite(hdr, 8, 3, fp) == 3 && fwrite(src.data(), 1, src.size(), fp) == src.size() &&
+                  fwrite(cubin.data(), 1, cubin.size(), fp) == cubin.size();
+  fclose(fp);
+  if (ok) ::rename(tmp.c_str(), f.c_str());  // atomic: readers see the old file or the complete new one
+  else ::remove(tmp.c_str());
+}
+
+static void compile_into(const std::string& src, const std::shared_ptr<CubinEntry>& e) {
+  std::vector<char> cubin;
+  std::string log;
+  g_spec_compiles.fetch_add(1);
+  const int32_t rc = nvrtc_compile(src, &cubin, &log);
+  if (rc == BN_OK) disk_store(src, cubin);
+  std::lock_guard<std::mutex> lk(g_cubin_mu);
+  e->log = log;
+  if (rc == BN_OK) { e->cubin.swap(cubin); e->state = CubinEntry::READY; }
+  else e->state = CubinEntry::FAILED;
+  g_cubin_cv.notify_all();
+}
+
+// wait = true : returns a READY or FAILED entry (compiling in this thread if nobody else is).
+// wait = false: returns the entry in whatever state it is; starts a background compile when there is none.
+static std::shared_ptr<CubinEntry> get_cubin(const std::string& src, bool wait) {
+  std::shared_ptr<CubinEntry> e;
+  bool mine = false;
+  {
+    std::unique_lock<std::mutex> lk(g_cubin_mu);
+    auto it = g_cubins.find(src);
+    if (it != g_cubins.end()) {
+      e = it->second;
+      if (wait) g_cubin_cv.wait(lk, [&] { return e->state != CubinEntry::COMPILING; });
+      return e;
+    }
+    e = std::make_shared<CubinEntry>();
+    g_cubins[src] = e;
+    mine = true;
+  }
+  if (mine) {
+    std::vector<char> cubin;
+    if (disk_load(src, &cubin)) {
+      g_disk_hits.fetch_add(1);
+      std::lock_guard<std::mutex> lk(g_cubin_mu);
+      e->cubin.swap(cubin);
+      e->from_disk = true;
+      e->state = CubinEntry::READY;
+      g_cubin_cv.notify_all();
+      return e;
+    }
+    if (wait) {
+      compile_into(src, e);
+    } else {
+      g_bg_compiles.fetch_add(1);
+      BgThreads& b = bg_threads();
+      std::lock_guard<std::mutex> lk(b.mu);
+      b.th.emplace_back([src, e] { compile_into(src, e); });
+    }
+  }
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------ kernel cache
 struct SpecKernel {
@@ -363,12 +517,11 @@ struct SpecKernel {
   uint32_t table_words = 0, n_live = 0;
 };
 
-// Compiled kernels are owned by a process-wide table keyed by (device, generated source): re-uploading the same
-// network (a new bn_net_t) or another network with the same structure reuses the cubin instead of paying the
-// NVRTC compile (~1 s for 100 nodes) again.  Net::spec_cache is a non-owning per-handle shortcut.
+// Loaded kernels are owned by a process-wide table keyed by (device, generated source): re-uploading the same
+// network (a new bn_net_t), another network with the same structure, or the replicas of a multi-GPU net reuse the
+// cubin instead of paying NVRTC again.  Net::spec_cache is a non-owning per-handle shortcut (guarded by Net::mu).
 static std::mutex g_spec_mu;
 static std::unordered_map<std::string, std::unique_ptr<SpecKernel>> g_spec;
-static std::atomic<uint64_t> g_spec_compiles{0};
 
 void spec_cache_clear(Net* net) { net->spec_cache.clear(); }
 
@@ -382,15 +535,83 @@ static int32_t cu_fail(const char* what, CUresult r) {
 thread_local int tl_lw_mode = 0;   // 0 auto, 1 generic only, 2 specialised required
 thread_local int tl_lw_prune = 1;  // barren-node elimination in the specialised kernel
 
-// Tiered JIT for the "auto" modes.  NVRTC costs ~10 ms per node for the particle kernels and ~35 ms per node for Gibbs
-// (1 s / 7 s for the 100- / 200-node benchmark nets), which only pays off once enough work has been requested for
-// the same (structure, evidence mask, query): the interpreter serves calls until the cumulative demand for a key
-// crosses `threshold` (particles / rows, or node updates), then the specialised kernel is compiled and cached.
-// Explicit modes (bn_set_lw_mode / bn_set_gibbs_mode = 2) compile immediately.
-static bool jit_worthwhile(Net* net, const std::string& key, double work, double threshold) {
-  double& d = net->spec_demand[key];
-  d += work;
-  return d >= threshold;
+// The specialised kernel for `key` on net's device, or *out = nullptr when the interpreter kernel should serve this
+// call: the network does not qualify, the compile failed earlier, or ("auto" modes) the cubin is neither in the
+// process nor on disk yet -- then NVRTC is started on a background thread once the cumulative work requested for the key
+// reaches `threshold` (tiny calls never trigger a compile) and later calls switch over when it is ready.
+// must = true (explicit "specialised" mode) blocks until the kernel exists and reports failures.
+struct KernelRequest {
+  const char* entry;       // __global__ function name
+  int threads;
+  size_t smem;
+  uint32_t table_words, n_live;
+  bool want_occupancy;
+};
+static int32_t acquire_kernel(Net* net, const std::string& key, bool must, double work, double threshold,
+                              const std::function<std::string(KernelRequest*)>& gen, SpecKernel** out) {
+  *out = nullptr;
+  Driver& drv = driver();
+  std::lock_guard<std::mutex> nlk(net->mu);
+  auto it = net->spec_cache.find(key);
+  if (it != net->spec_cache.end()) {
+    *out = it->second;
+    BN_REQUIRE(*out || !must, BN_CUDA_ERR, "specialised kernel failed to compile earlier for this (net, evidence, query)");
+    return BN_OK;
+  }
+  if (!must) {
+    double& d = net->spec_demand[key];
+    d += work;
+    if (d < threshold) return BN_OK;
+  }
+  KernelRequest rq{};
+  const std::string src = gen(&rq);
+  std::shared_ptr<CubinEntry> ce = get_cubin(src, must);
+  if (ce->state == CubinEntry::COMPILING) return BN_OK;  // background compile in flight: interpreter for now
+  if (ce->state == CubinEntry::FAILED) {
+    net->spec_cache[key] = nullptr;  // do not retry a failing compile on every call
+    BN_REQUIRE(!must, BN_CUDA_ERR, "nvrtcCompileProgram failed: %.300s", ce->log.c_str());
+    return BN_OK;
+  }
+  const std::string gkey = std::to_string(net->device) + "|" + src;
+  std::lock_guard<std::mutex> lk(g_spec_mu);
+  auto git = g_spec.find(gkey);
+  SpecKernel* k = nullptr;
+  if (git != g_spec.end()) {
+    k = git->second.get();
+  } else {
+    std::unique_ptr<SpecKernel> nk(new SpecKernel());
+    CUresult r = drv.ModuleLoadData(&nk->mod, ce->cubin.data());
+    if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
+    r = drv.ModuleGetFunction(&nk->fn, nk->mod, rq.entry);
+    if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
+    nk->threads = rq.threads;
+    nk->smem = rq.smem;
+    nk->table_words = rq.table_words;
+    nk->n_live = rq.n_live;
+    r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)rq.smem);
+    if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
+    drv.FuncGetAttribute(&nk->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, nk->fn);
+    nk->blocks_per_sm = 1;
+    if (rq.want_occupancy) {
+      int occ = 0;
+      r = drv.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, nk->fn, nk->threads, rq.smem);
+      if (r != CUDA_SUCCESS) return cu_fail("cuOccupancyMaxActiveBlocksPerMultiprocessor", r);
+      nk->blocks_per_sm = occ > 0 ? occ : 1;
+    }
+    k = nk.get();
+    g_spec[gkey] = std::move(nk);
+  }
+  net->spec_cache[key] = k;
+  *out = k;
+  return BN_OK;
+}
+
+// "auto" mode thresholds: cumulative particles / rows (node updates for Gibbs) requested for one key before NVRTC is
+// started in the background.  The interpreter needs ~15 ms for 5e7 particles of a 100-node net; below that a compile
+// (~1 s of one host core) is not worth starting.
+static double auto_threshold(const char* env, double dflt) {
+  const char* e = getenv(env);
+  return e ? atof(e) : dflt;
 }
 
 struct SpecLaunch {
@@ -434,75 +655,42 @@ static int32_t launch_specialized(Net* net, const SpecLaunch& a, bool* used) {
   key += "|m" + std::to_string((int)a.mode) + (a.all_free ? "f" : "e") + (prune ? "p" : "a");
   for (uint32_t j = 0; j < a.n_query; ++j) key += "," + std::to_string(a.query[j]);
   SpecKernel* k = nullptr;
-  auto it = net->spec_cache.find(key);
-  if (it != net->spec_cache.end()) {
-    k = it->second;
-  } else if (!must && !jit_worthwhile(net, key, (double)a.n, 2e9)) {
-    return BN_OK;  // auto mode: the interpreter kernel serves this call (see jit_worthwhile)
-  } else {
+  static const double thr = auto_threshold("BN_SPEC_AUTO_THRESHOLD", 5e7);
+  BN_TRY(acquire_kernel(net, key, must, (double)a.n, thr, [&](KernelRequest* rq) {
     SpecShape shp;
     if (const char* e = getenv("BN_SPEC_THREADS")) shp.threads = atoi(e);
     if (const char* e = getenv("BN_SPEC_MINB")) shp.min_blocks = atoi(e);
     uint32_t n_live = 0;
     static const std::vector<int64_t> no_stride;
-    const std::string src = gen_source(a.mode, *net, prg, ev_mask, a.query, a.n_query, a.qstride ? *a.qstride : no_stride,
-                                       a.ncell, prune, shp, &n_live);
-    const std::string gkey = std::to_string(net->device) + "|" + src;
-    std::lock_guard<std::mutex> lk(g_spec_mu);
-    auto git = g_spec.find(gkey);
-    if (git != g_spec.end()) {
-      k = git->second.get();
-    } else {
-      std::vector<char> cubin;
-      std::string log;
-      g_spec_compiles.fetch_add(1);
-      int32_t rc = nvrtc_compile(src, &cubin, &log);
-      if (rc != BN_OK) {
-        if (must) return rc;
-        g_spec[gkey] = nullptr;  // do not retry a failing compile on every call
-      } else {
-        std::unique_ptr<SpecKernel> nk(new SpecKernel());
-        CUresult r = drv.ModuleLoadData(&nk->mod, cubin.data());
-        if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
-        r = drv.ModuleGetFunction(&nk->fn, nk->mod, "lw_spec");
-        if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
-        nk->threads = shp.threads;
-        nk->smem = smem;
-        nk->table_words = prg.table_words;
-        nk->n_live = n_live;
-        r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
-        if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
-        drv.FuncGetAttribute(&nk->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, nk->fn);
-        int occ = 0;
-        r = drv.OccupancyMaxActiveBlocksPerMultiprocessor(&occ, nk->fn, nk->threads, smem);
-        if (r != CUDA_SUCCESS) return cu_fail("cuOccupancyMaxActiveBlocksPerMultiprocessor", r);
-        nk->blocks_per_sm = occ > 0 ? occ : 1;
-        k = nk.get();
-        g_spec[gkey] = std::move(nk);
-      }
-    }
-    net->spec_cache[key] = k;
-  }
-  if (!k) {
-    BN_REQUIRE(!must, BN_CUDA_ERR, "specialised kernel failed to compile earlier for this (net, evidence, query)");
-    return BN_OK;
-  }
+    std::string src = gen_source(a.mode, *net, prg, ev_mask, a.query, a.n_query, a.qstride ? *a.qstride : no_stride,
+                                 a.ncell, prune, shp, &n_live);
+    rq->entry = "lw_spec";
+    rq->threads = shp.threads;
+    rq->smem = smem;
+    rq->table_words = prg.table_words;
+    rq->n_live = n_live;
+    rq->want_occupancy = true;
+    return src;
+  }, &k));
+  if (!k) return BN_OK;  // the interpreter kernel serves this call
   BN_REQUIRE(k->table_words == prg.table_words, BN_CUDA_ERR, "specialised kernel/table mismatch");
-  // tables (+ evidence values) -> device scratch: evidence VALUES live only here
+  // tables (+ evidence values) -> per-call device staging from the stream-ordered pool (freed in stream order after
+  // the kernel when `stage` goes out of scope): evidence VALUES live only here, and concurrent calls never share it
   cudaStream_t s = tl_stream;
   const size_t tbytes = (size_t)prg.table_words * 4;
   const size_t ev_off = (tbytes + 15) / 16 * 16;
   const size_t total = ev_off + (size_t)net->n + 16;
-  if (net->scratch.n < total) BN_CUDA_TRY(net->scratch.alloc(total * 2));
+  TmpBuf<unsigned char> stage;
+  BN_CUDA_TRY(stage.alloc(total));
   std::vector<unsigned char> host(total, 0);
   if (tbytes) memcpy(host.data(), prg.words.data() + prg.prog_words, tbytes);
   for (int i = 0; i < net->n; ++i) host[ev_off + i] = (unsigned char)(a.evidence ? a.evidence[i] : -1);
-  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, host.data(), total, cudaMemcpyHostToDevice, s));
+  BN_CUDA_TRY(cudaMemcpyAsync(stage.p, host.data(), total, cudaMemcpyHostToDevice, s));
   long want = (long)((a.n + k->threads - 1) / k->threads);
   long full = (long)dp.sm_count * k->blocks_per_sm;
   unsigned grid = (unsigned)(want < full ? (want > 0 ? want : 1) : full);
-  const uint32_t* tab_dev = reinterpret_cast<const uint32_t*>(net->scratch.p);
-  const signed char* ev_dev = reinterpret_cast<const signed char*>(net->scratch.p + ev_off);
+  const uint32_t* tab_dev = reinterpret_cast<const uint32_t*>(stage.p);
+  const signed char* ev_dev = reinterpret_cast<const signed char*>(stage.p + ev_off);
   uint64_t first = a.first, n = a.n;
   uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32), never = 0xFFFFFFFFu, max_att = a.max_attempts;
   double* out = a.out;
@@ -824,60 +1012,30 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
   key += std::string("|g") + (full ? "F" : "N") + std::to_string(T);
   for (uint32_t j = 0; j < n_query; ++j) key += "," + std::to_string(query[j]);
   SpecKernel* k = nullptr;
-  auto it = net->spec_cache.find(key);
-  if (it != net->spec_cache.end()) {
-    k = it->second;
-  } else if (!must && !jit_worthwhile(net, key, (double)n_chains * (double)(burn_in + total * thin) * (full ? net->n : 1), 2e11)) {
-    return BN_OK;
-  } else {
+  static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e9);
+  BN_TRY(acquire_kernel(net, key, must, (double)n_chains * (double)(burn_in + total * thin) * (full ? net->n : 1), thr,
+                        [&](KernelRequest* rq) {
     uint32_t n_free = 0;
     int minb = 512 / T;  // <= 128 registers per thread
     if (const char* e = getenv("BN_GIBBS_MINB")) minb = atoi(e);
-    const std::string src = gen_gibbs_source(*net, ev_mask, query, n_query, qstride, ncell, full, T, minb, &n_free);
-    const std::string gkey = std::to_string(net->device) + "|" + src;
-    std::lock_guard<std::mutex> lk(g_spec_mu);
-    auto git = g_spec.find(gkey);
-    if (git != g_spec.end()) {
-      k = git->second.get();
-    } else {
-      std::vector<char> cubin;
-      std::string log;
-      g_spec_compiles.fetch_add(1);
-      int32_t rc = nvrtc_compile(src, &cubin, &log);
-      if (rc != BN_OK) {
-        if (must) return rc;
-        g_spec[gkey] = nullptr;
-      } else {
-        std::unique_ptr<SpecKernel> nk(new SpecKernel());
-        CUresult r = drv.ModuleLoadData(&nk->mod, cubin.data());
-        if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
-        r = drv.ModuleGetFunction(&nk->fn, nk->mod, "gibbs_spec");
-        if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
-        nk->threads = T;
-        nk->smem = smem;
-        nk->n_live = n_free;
-        r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
-        if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
-        drv.FuncGetAttribute(&nk->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, nk->fn);
-        k = nk.get();
-        g_spec[gkey] = std::move(nk);
-      }
-    }
-    net->spec_cache[key] = k;
-  }
-  if (!k) {
-    BN_REQUIRE(!must, BN_CUDA_ERR, "specialised Gibbs kernel failed to compile earlier for this (net, evidence, query)");
-    return BN_OK;
-  }
-  // evidence values -> device scratch
+    std::string src = gen_gibbs_source(*net, ev_mask, query, n_query, qstride, ncell, full, T, minb, &n_free);
+    rq->entry = "gibbs_spec";
+    rq->threads = T;
+    rq->smem = smem;
+    rq->n_live = n_free;
+    return src;
+  }, &k));
+  if (!k) return BN_OK;  // the interpreter kernel serves this call
+  // evidence values -> per-call device staging (stream-ordered pool; freed in stream order after the kernel)
   cudaStream_t s = tl_stream;
   const size_t total_b = (size_t)net->n + 16;
-  if (net->scratch.n < total_b) BN_CUDA_TRY(net->scratch.alloc(total_b * 2));
+  TmpBuf<unsigned char> stage;
+  BN_CUDA_TRY(stage.alloc(total_b));
   std::vector<unsigned char> host(total_b, 0);
   for (int i = 0; i < net->n; ++i) host[i] = (unsigned char)(evidence ? evidence[i] : -1);
-  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, host.data(), total_b, cudaMemcpyHostToDevice, s));
+  BN_CUDA_TRY(cudaMemcpyAsync(stage.p, host.data(), total_b, cudaMemcpyHostToDevice, s));
   const double* cpt = net->d_cpt.p;
-  const signed char* ev_dev = reinterpret_cast<const signed char*>(net->scratch.p);
+  const signed char* ev_dev = reinterpret_cast<const signed char*>(stage.p);
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   long long bi = burn_in, th = thin, tot = total;
   void* args[] = {(void*)&cpt, (void*)&ev_dev, (void*)&first_chain, (void*)&n_chains, (void*)&k0, (void*)&k1, (void*)&bi,
@@ -917,43 +1075,17 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
   for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
   key += "|gsample" + std::to_string(T) + "s" + std::to_string(sync_every);
   SpecKernel* k = nullptr;
-  auto it = net->spec_cache.find(key);
-  if (it != net->spec_cache.end()) {
-    k = it->second;
-  } else if (!must && !jit_worthwhile(net, key, (double)n_chains * (double)(burn_in + nsamples * (thinning + 1)) * n_free, 2e11)) {
-    return BN_OK;
-  } else {
-    const std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 512 / T, sync_every, nullptr);
-    const std::string gkey = std::to_string(net->device) + "|" + src;
-    std::lock_guard<std::mutex> lk(g_spec_mu);
-    auto git = g_spec.find(gkey);
-    if (git != g_spec.end()) {
-      k = git->second.get();
-    } else {
-      std::vector<char> cubin;
-      std::string log;
-      g_spec_compiles.fetch_add(1);
-      int32_t rc = nvrtc_compile(src, &cubin, &log);
-      if (rc != BN_OK) {
-        g_spec[gkey] = nullptr;  // the interpreter serves this structure from now on
-      } else {
-        std::unique_ptr<SpecKernel> nk(new SpecKernel());
-        CUresult r = drv.ModuleLoadData(&nk->mod, cubin.data());
-        if (r != CUDA_SUCCESS) return cu_fail("cuModuleLoadData", r);
-        r = drv.ModuleGetFunction(&nk->fn, nk->mod, "gibbs_sample_spec");
-        if (r != CUDA_SUCCESS) return cu_fail("cuModuleGetFunction", r);
-        nk->threads = T;
-        nk->smem = smem;
-        nk->n_live = n_free;
-        r = drv.FuncSetAttribute(nk->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
-        if (r != CUDA_SUCCESS) return cu_fail("cuFuncSetAttribute", r);
-        k = nk.get();
-        g_spec[gkey] = std::move(nk);
-      }
-    }
-    net->spec_cache[key] = k;
-  }
-  if (!k) return BN_OK;
+  static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e9);
+  int32_t rc = acquire_kernel(net, key, must, (double)n_chains * (double)(burn_in + nsamples * (thinning + 1)) * n_free, thr,
+                              [&](KernelRequest* rq) {
+    std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 512 / T, sync_every, nullptr);
+    rq->entry = "gibbs_sample_spec";
+    rq->threads = T;
+    rq->smem = smem;
+    rq->n_live = n_free;
+    return src;
+  }, &k);
+  if (rc != BN_OK || !k) return BN_OK;  // the interpreter kernel serves this call (it covers every network)
   const double* cpt = net->d_cpt.p;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   long long bi = burn_in, ns = nsamples, th = thinning;
@@ -974,6 +1106,16 @@ using namespace bn;
 extern "C" {
 
 uint64_t bn_lw_spec_compile_count(void) { return bn::g_spec_compiles.load(); }
+
+int32_t bn_spec_cache_stats(uint64_t* out4) {
+  BN_REQUIRE(out4, BN_BAD_ARG, "bn_spec_cache_stats: NULL output");
+  out4[0] = bn::g_spec_compiles.load();
+  out4[1] = bn::g_bg_compiles.load();
+  out4[2] = bn::g_disk_hits.load();
+  std::lock_guard<std::mutex> lk(bn::g_spec_mu);
+  out4[3] = (uint64_t)bn::g_spec.size();
+  return BN_OK;
+}
 
 int32_t bn_set_gibbs_mode(int32_t mode) {
   BN_REQUIRE(mode >= 0 && mode <= 2, BN_BAD_ARG, "bn_set_gibbs_mode: mode %d outside 0..2", mode);
@@ -1007,19 +1149,20 @@ int32_t bn_gibbs_spec_source(int32_t n_nodes, const int32_t* card, const int32_t
   for (int j = 0; j < n_query; ++j) { qstride.push_back(cells); cells *= card[query[j]]; }
   std::vector<char> ev_mask((size_t)n_nodes, 0);
   for (int i = 0; i < n_nodes; ++i) ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0;
+  const int T = threads > 0 ? threads : 64;  // same launch bounds as launch_gibbs_specialized: <= 128 registers
   const std::string src = gen_gibbs_source(net, ev_mask, query, (uint32_t)n_query, qstride, (uint32_t)cells, full != 0,
-                                           threads > 0 ? threads : 64, 1, nullptr);
+                                           T, std::max(1, 512 / T), nullptr);
   *out_len = (int64_t)src.size();
   if (out_src && cap > 0) {
     const size_t m = src.size() < (size_t)(cap - 1) ? src.size() : (size_t)(cap - 1);
     memcpy(out_src, src.data(), m);
     out_src[m] = 0;
   }
-  if (cubin_size) {
-    std::vector<char> cubin;
-    std::string log;
-    BN_TRY(nvrtc_compile(src, &cubin, &log));
-    *cubin_size = (int64_t)cubin.size();
+  if (cubin_size) {  // through the process + disk cache, so the cubin can be inspected (cuobjdump -sass) afterwards
+    BN_REQUIRE(nvrtc().ok, BN_UNSUPPORTED, "libnvrtc.so.12 could not be loaded (set BN_NVRTC_PATH)");
+    std::shared_ptr<CubinEntry> ce = get_cubin(src, true);
+    BN_REQUIRE(ce->state == CubinEntry::READY, BN_CUDA_ERR, "nvrtcCompileProgram failed: %.300s", ce->log.c_str());
+    *cubin_size = (int64_t)ce->cubin.size();
   }
   return BN_OK;
 }
@@ -1059,11 +1202,11 @@ int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* p
     memcpy(out_src, src.data(), m);
     out_src[m] = 0;
   }
-  if (cubin_size) {
-    std::vector<char> cubin;
-    std::string log;
-    BN_TRY(nvrtc_compile(src, &cubin, &log));
-    *cubin_size = (int64_t)cubin.size();
+  if (cubin_size) {  // through the process + disk cache, so the cubin can be inspected (cuobjdump -sass) afterwards
+    BN_REQUIRE(nvrtc().ok, BN_UNSUPPORTED, "libnvrtc.so.12 could not be loaded (set BN_NVRTC_PATH)");
+    std::shared_ptr<CubinEntry> ce = get_cubin(src, true);
+    BN_REQUIRE(ce->state == CubinEntry::READY, BN_CUDA_ERR, "nvrtcCompileProgram failed: %.300s", ce->log.c_str());
+    *cubin_size = (int64_t)ce->cubin.size();
   }
   return BN_OK;
 }

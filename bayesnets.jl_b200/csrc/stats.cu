@@ -243,15 +243,16 @@ static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_r
   const int threads = (int)warps * 32;
   a.use_async = (pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(data_dev) % 16) == 0 && TR % 16 == 0) ? 1u : 0u;
   const size_t smem = fixed + 2 * (size_t)n * (TR + 16);
-  // program -> device scratch (reused across calls)
-  if (net->scratch.n < prog_b + 16) BN_CUDA_TRY(net->scratch.alloc((prog_b + 16) * 2));
-  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice, s));
-  BN_CUDA_TRY(cudaMemcpyAsync(net->scratch.p + prog.size() * 4, prog_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  BN_CUDA_TRY(cudaStreamSynchronize(s));  // pageable host vectors about to go out of scope
+  // program -> per-call device staging from the stream-ordered pool (freed in stream order after the kernel); a copy
+  // from pageable memory returns once the source has been staged, so the host vectors may go out of scope
+  TmpBuf<unsigned char> stage;
+  BN_CUDA_TRY(stage.alloc(prog_b + 16));
+  BN_CUDA_TRY(cudaMemcpyAsync(stage.p, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice, s));
+  BN_CUDA_TRY(cudaMemcpyAsync(stage.p + prog.size() * 4, prog_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
   a.data = data_dev;
   a.n_rows = n_rows;
   a.pitch = pitch;
-  a.prog = reinterpret_cast<const uint32_t*>(net->scratch.p);
+  a.prog = reinterpret_cast<const uint32_t*>(stage.p);
   a.prog_off = a.prog + prog.size();
   a.prog_words = (uint32_t)prog.size();
   a.n_nodes = (uint32_t)n;

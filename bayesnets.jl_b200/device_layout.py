@@ -81,16 +81,28 @@ def flatten(bn) -> DeviceLayout:
 
 
 class DeviceNet:
-    """A DiscreteBayesNet resident in HBM (opaque bn_net_t handle)."""
+    """A DiscreteBayesNet resident in HBM (opaque bn_net_t handle).  With a Communicator (distributed.py) the network
+    is replicated on every local GPU of the communicator (bn_net_create_comm) and the sampling entry points shard
+    their particles / chains over all of its GPUs inside the C call; `device` is then the first local GPU."""
 
-    def __init__(self, layout: DeviceLayout, device: int = 0):
+    def __init__(self, layout: DeviceLayout, device: int = 0, comm=None):
+        if int(layout.card.max(initial=1)) > _lib.BN_MAX_CARD:
+            raise ValueError(f"a node has {int(layout.card.max())} states; the device layout carries states as int8 / "
+                             f"uint8 with -1 / 0xFF reserved, i.e. at most {_lib.BN_MAX_CARD} states per node")
         self.layout = layout
-        self.device = device
+        self.comm = comm
+        self.device = device if comm is None else comm.devices[0]
         h = _lib.h64(0)
         par_idx = layout.par_idx if layout.par_idx.size else np.zeros(1, np.int32)
-        check(_lib.lib().bn_net_create(C.c_int32(layout.n), ptr(layout.card, _lib.i32p), ptr(layout.par_ptr, _lib.i32p),
-                                       ptr(par_idx, _lib.i32p), ptr(layout.cpt_off, _lib.i64p),
-                                       ptr(layout.cpt, _lib.f64p), C.c_int32(device), C.byref(h)))
+        if comm is None:
+            check(_lib.lib().bn_net_create(C.c_int32(layout.n), ptr(layout.card, _lib.i32p), ptr(layout.par_ptr, _lib.i32p),
+                                           ptr(par_idx, _lib.i32p), ptr(layout.cpt_off, _lib.i64p),
+                                           ptr(layout.cpt, _lib.f64p), C.c_int32(device), C.byref(h)))
+        else:
+            check(_lib.lib().bn_net_create_comm(C.c_int32(layout.n), ptr(layout.card, _lib.i32p),
+                                                ptr(layout.par_ptr, _lib.i32p), ptr(par_idx, _lib.i32p),
+                                                ptr(layout.cpt_off, _lib.i64p), ptr(layout.cpt, _lib.f64p),
+                                                _lib.h64(comm.handle), C.byref(h)))
         self.handle = h.value
         self._fin = weakref.finalize(self, DeviceNet._destroy, self.handle)
 
@@ -106,6 +118,7 @@ class DeviceNet:
 
 
 _default_device = 0
+_default_comm = None
 
 
 def set_default_device(device: int) -> None:
@@ -117,12 +130,45 @@ def default_device() -> int:
     return _default_device
 
 
-def device_net(bn, device: int | None = None) -> DeviceNet:
-    """Upload once per (network contents, device); re-flatten if the network was mutated."""
+def set_default_comm(comm) -> None:
+    """Make `comm` (a distributed.Communicator, or None) the default for device_net(): every infer() / raw_counts()
+    that does not name a device then runs on all GPUs of the communicator -- one call, whole machine."""
+    global _default_comm
+    _default_comm = comm
+
+
+def default_comm():
+    return _default_comm
+
+
+def _fingerprint(lay: DeviceLayout) -> bytes:
+    """Content hash of what the device holds: structure + CPT bytes.  Mutating a CPD in place (or replacing one)
+    changes it, so the stale device copy is never reused; ~10 us for a 100-node net."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for a in (lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt):
+        h.update(np.ascontiguousarray(a).tobytes())
+    h.update("\0".join(lay.names).encode())
+    return h.digest()
+
+
+def device_net(bn, device: int | None = None, comm=None) -> DeviceNet:
+    """The network's device copy: uploaded once per (network CONTENTS, device or communicator).  The network is
+    re-flattened on every call (host work, tens of microseconds) and the copy is keyed by a content fingerprint, so
+    in-place edits of a CPD's distributions are seen; a few copies (e.g. one per device) are kept per network."""
+    if comm is None and device is None:
+        comm = _default_comm
     device = _default_device if device is None else device
-    key = (tuple(id(c) for c in bn.cpds), device)
+    lay = flatten(bn)
+    key = (_fingerprint(lay), ("comm", id(comm)) if comm is not None else ("dev", device))
     cache = getattr(bn, "_device_cache", None)
-    if cache is None or cache[0] != key:
-        cache = (key, DeviceNet(flatten(bn), device))
+    if not isinstance(cache, dict):
+        cache = {}
         bn._device_cache = cache
-    return cache[1]
+    net = cache.get(key)
+    if net is None:
+        for k in [k for k in cache if k[0] != key[0]]:  # contents changed: drop the stale copies
+            cache.pop(k).close()
+        net = DeviceNet(lay, device, comm)
+        cache[key] = net
+    return net

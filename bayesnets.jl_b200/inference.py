@@ -6,6 +6,12 @@ network is uploaded once (device_layout.device_net) and the inner loop is one C-
 
 Extra fields the reference does not have: `seed` (counter-based Philox key; the reference uses Julia's
 global RNG), `n_chains` for Gibbs (1 = the reference's single chain) and `device`.
+
+Seeds.  The reference draws fresh random numbers on every call.  Here `seed=None` (the default) takes the next value of
+a process-wide counter per call; an explicit seed is used as given by the FIRST call made with it and advanced for
+every further call on the same method object (so repeated `infer` calls, and Gibbs chains resumed through `im.state`,
+never replay a stream); assigning `im.seed` again restarts from that value.  `last_seed` is what the last call used.
+With set_default_comm(comm) (distributed.py) the same calls run on every GPU of the communicator.
 """
 from __future__ import annotations
 
@@ -44,6 +50,30 @@ class InferenceState:
         return f"Query: {self.query}\nEvidence: {self.evidence}"
 
 
+_auto_seed = [0]
+_MASK64 = (1 << 64) - 1
+
+
+class _SeedStream:
+    """Per-call Philox key of a sampling InferenceMethod (module docstring, "Seeds")."""
+    _seed_owner = None
+    _seed_calls = 0
+    last_seed: Optional[int] = None
+
+    def _call_seed(self) -> int:
+        if self.seed is None:
+            _auto_seed[0] += 1
+            s = 0x5EED000000000000 + _auto_seed[0]
+        else:
+            if self._seed_owner != self.seed:
+                self._seed_owner, self._seed_calls = self.seed, 0
+            k = self._seed_calls
+            self._seed_calls += 1
+            s = (int(self.seed) + k * 0x9E3779B97F4A7C15) & _MASK64
+        self.last_seed = s
+        return s
+
+
 def _query_factor(inf: InferenceState, counts: np.ndarray, device) -> Factor:
     shape = [inf.pgm.ncategories(q) for q in inf.query]
     return Factor(inf.query, np.asarray(counts, np.float64).reshape(shape, order="F"), device=device)
@@ -51,10 +81,10 @@ def _query_factor(inf: InferenceState, counts: np.ndarray, device) -> Factor:
 
 # ---------------------------------------------------------------------------------------------
 @dataclass
-class LikelihoodWeightingInference(InferenceMethod):
+class LikelihoodWeightingInference(_SeedStream, InferenceMethod):
     """src/Inference/likelihood.jl:5-7 (+ seed/device).  `last_stats` = (sum w, sum w^2) of the last call."""
     nsamples: int = 500
-    seed: int = 0
+    seed: Optional[int] = None
     device: Optional[int] = None
     first_particle: int = 0
     last_stats: tuple = field(default=(0.0, 0.0), repr=False, compare=False)
@@ -70,7 +100,7 @@ class LikelihoodWeightingInference(InferenceMethod):
         stats = np.zeros(2, np.float64)
         qp = q if q.size else np.zeros(1, np.int32)
         check(_lib.lib().bn_lw_infer(_lib.h64(net.handle), ptr(ev, _lib.i8p), ptr(qp, _lib.i32p), C.c_int32(q.size),
-                                     C.c_uint64(self.first_particle), C.c_uint64(self.nsamples), C.c_uint64(self.seed),
+                                     C.c_uint64(self.first_particle), C.c_uint64(self.nsamples), C.c_uint64(self._call_seed()),
                                      ptr(counts, _lib.f64p), ptr(stats, _lib.f64p)))
         self.last_stats = (float(stats[0]), float(stats[1]))
         return counts
@@ -83,13 +113,13 @@ class LikelihoodWeightingInference(InferenceMethod):
 
 
 @dataclass
-class _GibbsBase(InferenceMethod):
+class _GibbsBase(_SeedStream, InferenceMethod):
     nsamples: int = 2000
     burn_in: int = 500
     thin: int = 3
     state: dict = field(default_factory=dict)  # carried across calls, like im.state (gibbs.jl:64,83-88)
     n_chains: int = 1
-    seed: int = 0
+    seed: Optional[int] = None
     device: Optional[int] = None
     first_chain: int = 0
     chain_states: Optional[np.ndarray] = field(default=None, repr=False, compare=False)
@@ -113,7 +143,12 @@ class _GibbsBase(InferenceMethod):
             init = 1
         elif self.state:
             # a user-supplied / previous single-chain state (1-based Assignment), replicated over chains
-            row = np.array([int(self.state[n]) - 1 for n in lay.names], np.uint8)
+            row = np.zeros(lay.n, np.uint8)
+            for i, n in enumerate(lay.names):
+                v = int(self.state[n])
+                if not 1 <= v <= int(lay.card[i]):  # the state indexes the CPTs on the device
+                    raise IndexError(f"BoundsError: state {v} of {n} outside 1:{int(lay.card[i])}")
+                row[i] = v - 1
             for k, v in inf.evidence.items():
                 if k in lay.index:
                     row[lay.index[k]] = int(v) - 1
@@ -126,7 +161,7 @@ class _GibbsBase(InferenceMethod):
         check(_lib.lib().bn_gibbs_infer(_lib.h64(net.handle), ptr(ev, _lib.i8p), ptr(qp, _lib.i32p), C.c_int32(q.size),
                                         C.c_uint64(self.first_chain), C.c_uint64(nch), C.c_int64(self.nsamples),
                                         C.c_int64(self.burn_in), C.c_int64(self.thin), C.c_int32(self._mode),
-                                        C.c_uint64(self.seed), ptr(st, _lib.u8p), C.c_int32(init),
+                                        C.c_uint64(self._call_seed()), ptr(st, _lib.u8p), C.c_int32(init),
                                         ptr(counts, _lib.f64p), ptr(cc, _lib.f64p)))
         self.chain_states = st
         self.state = {n: int(st[0, i]) + 1 for i, n in enumerate(lay.names)}

@@ -183,12 +183,13 @@ def statistics_device(bn_or_net, states_dev_ptr: int, n_rows: int, pitch: int | 
         check(_lib.lib().bn_statistics_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
                                            C.c_uint64(pitch), C.c_void_p(out_dev_ptr)))
         return lay, None
-    import torch  # plumbing only: a device buffer for the result
-    out = torch.empty(int(lay.cpt_off[-1]), dtype=torch.int64, device=f"cuda:{net.device}")
-    _lib.set_stream(torch.cuda.current_stream(net.device).cuda_stream)
+    n_bins = int(lay.cpt_off[-1])
+    out = _lib.DeviceBuffer(n_bins * 8, net.device)  # bn_dev_alloc: no array library on the product path
     check(_lib.lib().bn_statistics_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
-                                       C.c_uint64(pitch), C.c_void_p(out.data_ptr())))
-    return lay, out.cpu().numpy()
+                                       C.c_uint64(pitch), C.c_void_p(out.ptr)))
+    counts = out.download(np.int64, n_bins)
+    out.close()
+    return lay, counts
 
 
 # ------------------------------------------------------------------------------------------------ priors + score
@@ -339,12 +340,12 @@ def logpdf_device(bn_or_net, states_dev_ptr: int, n_rows: int, pitch: int | None
         check(_lib.lib().bn_logpdf_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
                                        C.c_uint64(pitch), C.c_void_p(out_dev_ptr)))
         return None
-    import torch  # plumbing only: a device buffer for the result
-    out = torch.empty(1, dtype=torch.float64, device=f"cuda:{net.device}")
-    _lib.set_stream(torch.cuda.current_stream(net.device).cuda_stream)
+    out = _lib.DeviceBuffer(8, net.device)  # bn_dev_alloc: no array library on the product path
     check(_lib.lib().bn_logpdf_dev(_lib.h64(net.handle), C.c_void_p(states_dev_ptr), C.c_uint64(n_rows),
-                                   C.c_uint64(pitch), C.c_void_p(out.data_ptr())))
-    return float(out.cpu()[0])
+                                   C.c_uint64(pitch), C.c_void_p(out.ptr)))
+    v = float(out.download(np.float64, 1)[0])
+    out.close()
+    return v
 
 
 # ------------------------------------------------------------------------------------------------ count / table

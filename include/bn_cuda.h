@@ -16,13 +16,19 @@
  *       CPT entry P(x_i = s | pa) = cpt[cpt_off[i] + s + card[i] * sum_k state(parent_k) * stride_k],
  *       stride_0 = 1, stride_k = prod_{j<k} card(parent_j)      (src/CPDs/categorical_cpd.jl:36-46,
  *       src/Factors/factors_main.jl:62-67: vcat(d.p for d in distributions))
- *   - evidence[n] is int8: -1 = free, otherwise the clamped 0-based state
+ *   - evidence[n] is int8: -1 = free, otherwise the clamped 0-based state; sampled tables are uint8 with 0xFF = "no
+ *     row" -- hence at most BN_MAX_CARD = 128 states per node (bn_net_create rejects more)
  *   - factors are column-major Float64 exactly as Factor.potential (src/Factors/factors_main.jl:20);
  *     variables are int32 ids (the Julia glue maps Symbol <-> id)
  *   - host pointers unless the name ends in _dev; the caller owns every host buffer, the library owns
  *     device memory behind opaque handles; no host pointer is retained after return
  *   - calls are synchronous unless they end in _dev (those enqueue on the stream set by
  *     bn_set_stream and return immediately)
+ *   - threading: any number of host threads / streams may use the same net or factor handles concurrently for
+ *     READ-style calls (infer, sample, statistics, products): per-call staging comes from the stream-ordered pool
+ *     and the per-net kernel cache is locked.  Calls that write a handle in place (bn_factor_normalize, _setindex,
+ *     _broadcast, _relabel) and the destroy / free calls need external ordering against other users of THAT handle.
+ *     A comm-bearing net (bn_net_create_comm) is driven by one host thread at a time (NCCL's rule for a communicator)
  *   - random streams: Philox4x32-10, key = seed, counter = (index_lo, index_hi, draw/4, stream id);
  *     particle / chain indices are GLOBAL (first_* + i), so sharding a job over ranks reproduces the
  *     single-GPU stream bit for bit
@@ -36,6 +42,7 @@
 extern "C" {
 #endif
 
+#define BN_MAX_CARD 128
 typedef uint64_t bn_net_t;    /* device-resident flattened DiscreteBayesNet */
 typedef uint64_t bn_factor_t; /* device-resident Factor (dims + column-major fp64 potential) */
 
@@ -48,7 +55,8 @@ typedef enum {
   BN_ZERO_WEIGHT = -5,    /* every particle had weight 0 / no initial Gibbs sample (src/gibbs.jl:332-334) */
   BN_OOM = -6,
   BN_UNSUPPORTED = -7,
-  BN_BOUNDS = -8          /* BoundsError (src/Factors/factors_access.jl:59-61) */
+  BN_BOUNDS = -8,         /* BoundsError (src/Factors/factors_access.jl:59-61) */
+  BN_NCCL_ERR = -9        /* libnccl.so.2 missing or a NCCL call failed (multi-GPU entry points only) */
 } bn_status;
 
 enum { BN_SAMPLE_ANCESTRAL = 0, BN_SAMPLE_REJECTION = 1, BN_SAMPLE_WEIGHTED = 2 };
@@ -63,9 +71,65 @@ int32_t bn_set_stream(void* cuda_stream);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t bn_launch_count(void);
 
+/* Wait for everything this host thread has enqueued on its current stream (the _dev entry points are asynchronous). */
+int32_t bn_synchronize(void);
+
+/* ---- plain device buffers for callers without a CUDA array library (the Julia glue, the Python mirror): the *_dev
+ *      entry points take their pointers.  Stream-ordered on the calling thread's current stream; bn_dev_download
+ *      synchronises that stream before returning, bn_dev_upload returns once `src` may be reused. ---------------- */
+int32_t bn_dev_alloc(int32_t device, uint64_t bytes, void** out_ptr);
+int32_t bn_dev_free(int32_t device, void* ptr);
+int32_t bn_dev_memset(void* ptr, int32_t value, uint64_t bytes);
+int32_t bn_dev_upload(void* dst_dev, const void* src, uint64_t bytes);
+int32_t bn_dev_download(void* dst, const void* src_dev, uint64_t bytes);
+
+/* ---- multi-GPU: infer(im, bn, query; evidence) is ONE call for the whole machine
+ *      (src/ProbabilisticGraphicalModels/inference.jl:48-49), so the fan-out over GPUs and the one collective the
+ *      sampling paths need live behind the C ABI.  NCCL (libnccl.so.2, dlopen'ed at first use; BN_NCCL_PATH overrides)
+ *      is called directly from C: no torch.distributed / CUDA.jl / MPI in the data path. ---------------------------
+ * A communicator spans `world` GPUs.  Two ways to make one:
+ *   bn_comm_init_all  : ONE process drives n_devices GPUs (ncclCommInitAll, one stream per device) -- what a Julia
+ *                       session needs; world = n_devices, all of them local.
+ *   bn_comm_init_rank : one process PER GPU (torchrun / MPI): rank 0 calls bn_comm_unique_id, ships the 128 bytes to
+ *                       the other ranks out of band (file, TCP store, MPI_Bcast), then every rank calls
+ *                       bn_comm_init_rank(id, rank, world, device) -- collective, returns when all ranks joined.
+ * bn_net_create_comm uploads the network to every LOCAL device of the communicator.  On such a net
+ *   bn_lw_infer[_dev], bn_gibbs_infer[_dev]: first_* / n_* describe the GLOBAL job; GPU g of `world` takes the
+ *       contiguous global index range bn_comm_shard(first, n, g, world) (Philox counters are global indices, so any
+ *       world size consumes the same streams), every local GPU is launched, and ONE ncclAllReduce(sum, fp64) of the
+ *       (cells + 2) doubles leaves the whole job's counts on every GPU before the call returns them.
+ *       _dev variants: out_dev lives on the FIRST local device and is enqueued on the caller's current stream.
+ *       bn_gibbs_infer: state_inout / out_chain_counts rows belong to chains; each process fills the rows of the chains
+ *       its local GPUs ran and leaves the others untouched.
+ *   every other entry point (factors, exact inference, statistics, tables ...) runs on the first local device.  */
+typedef uint64_t bn_comm_t;
+#define BN_COMM_ID_BYTES 128
+enum { BN_DTYPE_F64 = 0, BN_DTYPE_I64 = 1 };
+enum { BN_REDUCE_SUM = 0, BN_REDUCE_MAX = 1 };
+int32_t bn_comm_init_all(const int32_t* devices, int32_t n_devices, bn_comm_t* out_comm);
+int32_t bn_comm_unique_id(uint8_t* out_id /* BN_COMM_ID_BYTES */);
+int32_t bn_comm_init_rank(const uint8_t* id, int32_t rank, int32_t world, int32_t device, bn_comm_t* out_comm);
+/* world = GPUs in the communicator, first_rank = global rank of this process's first local GPU, n_local = local GPUs */
+int32_t bn_comm_info(bn_comm_t comm, int32_t* out_world, int32_t* out_first_rank, int32_t* out_n_local);
+int32_t bn_comm_destroy(bn_comm_t comm);
+/* The sharding rule, host-only (no GPU, no NCCL): rank g of `world` gets [first + n*g/world, first + n*(g+1)/world). */
+int32_t bn_comm_shard(uint64_t first, uint64_t n, int32_t rank, int32_t world, uint64_t* out_first, uint64_t* out_n);
+/* Element-wise reduction over the PROCESSES of the communicator of one host buffer per process (in place; a
+ * single-process communicator returns the buffer unchanged): timing maxima, user-side bookkeeping.  Synchronous. */
+int32_t bn_comm_allreduce(bn_comm_t comm, void* host_inout, int64_t count, int32_t dtype, int32_t op);
+/* The same on a device buffer of the first local GPU, enqueued on the caller's current stream (one local GPU per
+ * process only): e.g. the int64 sufficient statistics of a row-sharded table (bn_statistics_dev). */
+int32_t bn_comm_allreduce_dev(bn_comm_t comm, void* dev_inout, int64_t count, int32_t dtype, int32_t op);
+/* Every GPU of the communicator has finished what was enqueued before the call (an all-reduce of one double + sync). */
+int32_t bn_comm_barrier(bn_comm_t comm);
+
 /* ---- network: replaces nothing; it is the device_layout.jl upload (DiscreteBayesNet -> HBM) ---- */
 int32_t bn_net_create(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
                       const int64_t* cpt_off, const double* cpt, int32_t device, bn_net_t* out_net);
+/* The same network replicated on every local device of `comm` (see the multi-GPU section above).  The communicator
+ * must outlive the net. */
+int32_t bn_net_create_comm(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,
+                           const int64_t* cpt_off, const double* cpt, bn_comm_t comm, bn_net_t* out_net);
 int32_t bn_net_destroy(bn_net_t net);
 
 /* ---- likelihood weighting: infer(::LikelihoodWeightingInference, ::InferenceState)
@@ -84,10 +148,12 @@ int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* que
                         uint64_t first_particle, uint64_t n_particles, uint64_t seed, double* out_dev);
 
 /* LW kernel selection for subsequent calls from this host thread.
- * mode : 0 = auto: the generic interpreter kernel serves calls until the cumulative work requested for the same
- *            (structure, evidence mask, query) reaches 2e9 particles/rows (2e11 node updates for Gibbs), then the
- *            network-specialised kernel is NVRTC-compiled (~10 ms per node) and cached process-wide;
- *        1 = generic interpreter only, 2 = specialised required (compiled on first use; error if unavailable).
+ * mode : 0 = auto: the network-specialised kernel is used as soon as its cubin is at hand -- in the process, or in the
+ *            on-disk cache a previous process left; otherwise the generic interpreter kernel serves the call and, once
+ *            the cumulative work requested for the same (structure, evidence mask, query) reaches 5e7 particles/rows
+ *            (2e9 node updates for Gibbs), NVRTC compiles the kernel on a BACKGROUND host thread (~10 ms per node);
+ *            later calls switch over when it is ready.  No call ever waits for a compile;
+ *        1 = generic interpreter only, 2 = specialised required (compiled on first use, blocking; error if unavailable).
  * prune: != 0 lets the specialised kernel skip "barren" nodes (not an ancestor of a query or evidence node);
  *        draw indices are static, so the counts are bit-identical either way.  Default: mode 0, prune 1. */
 int32_t bn_set_lw_mode(int32_t mode, int32_t prune);
@@ -97,6 +163,9 @@ int32_t bn_set_lw_mode(int32_t mode, int32_t prune);
 int32_t bn_set_gibbs_mode(int32_t mode);
 /* Number of NVRTC compiles since load (kernels are cached process-wide by generated source). */
 uint64_t bn_lw_spec_compile_count(void);
+/* Kernel-cache counters since load: out4 = [NVRTC compiles, of which started on a background thread ("auto" modes),
+ * cubins found in the on-disk cache (BN_CUBIN_CACHE, default ~/.cache/bn_cuda; "off" disables), kernels loaded]. */
+int32_t bn_spec_cache_stats(uint64_t* out4);
 /* Host-only (no GPU): emit the CUDA source the specialised LW kernel would be built from for this flat network
  * and, when cubin_size != NULL, compile it with NVRTC for sm_100a.  out_src may be NULL to query *out_len. */
 int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, const int32_t* par_idx,

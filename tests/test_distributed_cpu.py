@@ -1,9 +1,11 @@
 """World-size-2 `gloo` test of the multi-GPU plumbing on CPU.
 
 The sharding contract is host logic: rank g runs particle ids [g*N//G, (g+1)*N//G) of ONE global Philox counter space
-and the ranks all-reduce the (cells + 2) doubles.  Here each rank's shard is computed by the oracle (the GPU kernels are
-bit-identical to it per tests/test_gpu_sampling.py), reduced with the product's own `allreduce_sum_` over gloo, and
-compared with the single-process result: integer (unweighted) counts must match exactly, weighted sums to 1e-12.
+and the ranks all-reduce the (cells + 2) doubles.  On the GPU box both halves live inside libbn_cuda.so (csrc/comm.cu:
+bn_comm_shard + ncclAllReduce).  Here the shard boundaries come from the library's own bn_comm_shard (host-only, no GPU
+needed), each rank's shard is computed by the oracle (the GPU kernels are bit-identical to it per
+tests/test_gpu_sampling.py), the reduction is gloo's, and the result is compared with the single-process one: integer
+(unweighted) counts must match exactly, weighted sums to 1e-12.
 """
 import os
 import socket
@@ -41,7 +43,13 @@ def _worker(rank, world, port, n_total, q):
         import torch
         import torch.distributed as dist
         import bayesnets_jl_b200 as bn
-        from bayesnets_jl_b200.distributed import allreduce_sum_, shard_range
+        from bayesnets_jl_b200.distributed import allreduce_sum_, comm_shard
+        from bayesnets_jl_b200.distributed import shard_range as py_shard_range
+
+        def shard_range(n, r, w):  # the C library's rule, checked against its Python restatement
+            lo, cnt = comm_shard(0, n, r, w)
+            assert (lo, cnt) == py_shard_range(n, r, w)
+            return lo, cnt
         from oracle import capi
         from oracle.factors_np import FlatNet
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -123,6 +131,20 @@ def test_two_rank_gloo_allreduce_equals_single_stream():
     for b, (qn, e) in enumerate(pairs):
         o = loopy_infer(on, qn, e, nsamples=8)
         assert np.array_equal(lb2[b, :len(o)], o) and not lb2[b, len(o):].any()
+
+
+def test_comm_api_on_cpu():
+    """Without a GPU the communicator entry points fail loudly (no fallback); the sharding rule is host-only."""
+    sys.path.insert(0, ROOT)
+    import bayesnets_jl_b200 as bn
+    from bayesnets_jl_b200.distributed import Communicator, comm_shard
+    assert comm_shard(5, 10, 1, 4) == (5 + 2, 3)  # [2, 5) of 10 -> 3 indices
+    assert sum(comm_shard(0, 10**11 + 7, g, 8)[1] for g in range(8)) == 10**11 + 7
+    with pytest.raises(ValueError):
+        comm_shard(0, 10, 4, 4)
+    if bn.device_count_or_zero() == 0:
+        with pytest.raises(bn.BNCudaError):
+            Communicator.init_all([0])
 
 
 # ------------------------------------------------------------------------------------------ split factors (8e)

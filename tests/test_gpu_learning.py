@@ -309,27 +309,32 @@ def test_sample_then_logpdf_on_device(bn):
 
 
 def test_sharded_table_statistics_single_rank(bn):
-    """distributed.ShardedTableStatistics at world size 1 (no process group: the all-reduce is the identity): sample ->
+    """distributed.ShardedTableStatistics at world size 1 (no communicator: the all-reduce is the identity): sample ->
     count -> logpdf on the device equals the oracle on the same table; a shard [first, first + count) of the global
-    row space holds exactly those rows of the whole table (what the 2-rank gloo test and tools/table_scaling.py rely on)."""
-    import torch
+    row space holds exactly those rows of the whole table (what the 2-rank tests and tools/multi_gpu_check.py rely on).
+    No torch anywhere: the device buffers are bn_dev_alloc allocations."""
+    from bayesnets_jl_b200 import DeviceBuffer
     from bayesnets_jl_b200.distributed import ShardedTableStatistics
     net = bn.rand_discrete_bn(40, 3, 4, seed=3)
     lay = bn.flatten(net)
     on = oracle_net_from_layout(lay)
     n_rows = 100_003
     sh = ShardedTableStatistics(net, n_rows, seed=21, device=0)
-    counts = sh.step().cpu().numpy()
+    sh.step()
+    counts = sh.counts_host()
     whole, _, _ = capi.sample(on, n_rows, seed=21)
-    assert np.array_equal(sh.table.cpu().numpy(), whole)
+    assert np.array_equal(sh.table.download(np.uint8, lay.n * n_rows).reshape(lay.n, n_rows), whole)
     assert np.array_equal(counts, capi.statistics(on, whole))
     assert sh.logpdf() == pytest.approx(capi.logpdf_table(on, whole), rel=1e-12)
     # a middle shard of the same global row space
     sh.first, sh.count = 33_334, 33_335
-    sh.table = torch.empty((lay.n, sh.count), dtype=torch.uint8, device="cuda:0")
+    sh.pitch = sh.count
+    sh.table = DeviceBuffer(lay.n * sh.count, 0)
     sh.sample()
-    assert np.array_equal(sh.table.cpu().numpy(), whole[:, 33_334:33_334 + 33_335])
-    assert np.array_equal(sh.launch().cpu().numpy(), capi.statistics(on, np.ascontiguousarray(whole[:, 33_334:33_334 + 33_335])))
+    part = sh.table.download(np.uint8, lay.n * sh.count).reshape(lay.n, sh.count)
+    assert np.array_equal(part, whole[:, 33_334:33_334 + 33_335])
+    sh.launch()
+    assert np.array_equal(sh.counts_host(), capi.statistics(on, np.ascontiguousarray(whole[:, 33_334:33_334 + 33_335])))
 
 
 def test_count_reference_values(bn, golden):

@@ -293,3 +293,37 @@ def test_mle_cpds_from_counts_match_reference_cpd_tests(bn, oracle):
     a, b = fit_counts([[], [0]], [3, 5], [[1, 2, 1, 2, 2], [1, 1, 2, 1, 2]], ["a", "b"])
     assert sum(len(d) for d in b.distributions) == 15
     assert b({"a": 3}).tolist() == [0.2] * 5
+
+
+def test_cubin_disk_cache_serves_a_second_process(bn, tmp_path):
+    """The specialised kernels' cubins persist in BN_CUBIN_CACHE keyed by a hash of the generated source (+ toolchain),
+    with the source stored beside the cubin and compared on load: a second PROCESS compiles nothing (the cold-start
+    path of bench.py's e2e_cached).  Host-only: NVRTC needs no device."""
+    import json
+    import subprocess
+    code = (
+        "import os, sys, json; sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tools'))\n"
+        "import bayesnets_jl_b200 as bn\n"
+        "from dump_lw_spec import spec_source\n"
+        "net = bn.rand_discrete_bn(25, 3, 4, seed=8); lay = bn.flatten(net)\n"
+        "src, cub, live = spec_source(lay, {'N4': 1}, ['N9'], prune=True)\n"
+        "src2, cub2, _ = spec_source(lay, {'N4': 1}, ['N9'], prune=True)\n"
+        "print(json.dumps({'cubin': cub, 'same': cub == cub2, 'stats': bn.spec_cache_stats()}))\n" % (ROOT, ROOT))
+    env = dict(os.environ, BN_CUBIN_CACHE=str(tmp_path / "cubins"))
+    runs = []
+    for _ in range(2):
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    first, second = runs
+    assert first["cubin"] > 0 and first["same"] and first["cubin"] == second["cubin"]
+    assert first["stats"]["nvrtc_compiles"] == 1 and first["stats"]["disk_hits"] == 0   # 2nd request: in-process table
+    assert second["stats"]["nvrtc_compiles"] == 0 and second["stats"]["disk_hits"] == 1  # fresh process: from disk
+    files = [f for f in os.listdir(tmp_path / "cubins") if f.endswith(".cubin")]
+    assert len(files) == 1
+    # a corrupted cache entry is ignored (source mismatch / short file), not trusted
+    p = tmp_path / "cubins" / files[0]
+    p.write_bytes(p.read_bytes()[:100])
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    third = json.loads(r.stdout.strip().splitlines()[-1])
+    assert third["stats"]["nvrtc_compiles"] == 1 and third["stats"]["disk_hits"] == 0 and third["cubin"] == first["cubin"]
