@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(HERE, "libbn_cuda.so")
 
 BN_OK, BN_BAD_ARG, BN_DIM_MISMATCH, BN_NOT_IN_FACTOR, BN_CUDA_ERR = 0, -1, -2, -3, -4
 BN_ZERO_WEIGHT, BN_OOM, BN_UNSUPPORTED, BN_BOUNDS, BN_NCCL_ERR = -5, -6, -7, -8, -9
-BN_MAX_CARD = 128
+BN_MAX_CARD = 255
+BN_MAX_EVIDENCE_STATE = 127
 BN_COMM_ID_BYTES = 128
 DTYPE_F64, DTYPE_I64 = 0, 1
 REDUCE_SUM, REDUCE_MAX = 0, 1

@@ -135,7 +135,7 @@ int32_t make_net(int32_t n_nodes, const int32_t* card, const int32_t* par_ptr, c
   int32_t n_par = par_ptr[n_nodes];
   BN_REQUIRE(n_par == 0 || par_idx, BN_BAD_ARG, "bn_net_create: par_idx is NULL");
   for (int i = 0; i < n_nodes; ++i) {
-    // evidence and sampled states travel as int8 / uint8 with -1 / 0xFF reserved: 128 states per node is the ABI limit
+    // sampled states travel as uint8 with 0xFF reserved
     BN_REQUIRE(card[i] >= 1 && card[i] <= BN_MAX_CARD, BN_BAD_ARG, "node %d: cardinality %d outside 1..%d", i, card[i],
                BN_MAX_CARD);
     BN_REQUIRE(par_ptr[i + 1] >= par_ptr[i], BN_BAD_ARG, "par_ptr not monotone at node %d", i);

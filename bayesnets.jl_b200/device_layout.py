@@ -50,6 +50,9 @@ class DeviceLayout:
                 raise TypeError(f"Invalid state for {k}: {v!r}")
             if not 1 <= int(v) <= int(self.card[i]):
                 raise IndexError(f"BoundsError: state {v} of {k} outside 1:{int(self.card[i])}")
+            if int(v) - 1 > _lib.BN_MAX_EVIDENCE_STATE:  # int8 on the ABI: never let it wrap to "free"
+                raise IndexError(f"BoundsError: evidence state {v} of {k}: only states 1:{_lib.BN_MAX_EVIDENCE_STATE + 1} "
+                                 "of a node can be clamped as evidence (int8 in include/bn_cuda.h)")
             ev[i] = int(v) - 1
         return ev
 
@@ -87,8 +90,8 @@ class DeviceNet:
 
     def __init__(self, layout: DeviceLayout, device: int = 0, comm=None):
         if int(layout.card.max(initial=1)) > _lib.BN_MAX_CARD:
-            raise ValueError(f"a node has {int(layout.card.max())} states; the device layout carries states as int8 / "
-                             f"uint8 with -1 / 0xFF reserved, i.e. at most {_lib.BN_MAX_CARD} states per node")
+            raise ValueError(f"a node has {int(layout.card.max())} states; the device layout carries states as uint8 "
+                             f"with 0xFF reserved, i.e. at most {_lib.BN_MAX_CARD} states per node")
         self.layout = layout
         self.comm = comm
         self.device = device if comm is None else comm.devices[0]

@@ -16,8 +16,10 @@
  *       CPT entry P(x_i = s | pa) = cpt[cpt_off[i] + s + card[i] * sum_k state(parent_k) * stride_k],
  *       stride_0 = 1, stride_k = prod_{j<k} card(parent_j)      (src/CPDs/categorical_cpd.jl:36-46,
  *       src/Factors/factors_main.jl:62-67: vcat(d.p for d in distributions))
- *   - evidence[n] is int8: -1 = free, otherwise the clamped 0-based state; sampled tables are uint8 with 0xFF = "no
- *     row" -- hence at most BN_MAX_CARD = 128 states per node (bn_net_create rejects more)
+ *   - evidence[n] is int8: negative = free, otherwise the clamped 0-based state; sampled tables are uint8 with a
+ *     leading 0xFF = "no row".  Hence at most BN_MAX_CARD = 255 states per node (bn_net_create rejects more), and only
+ *     states 0..BN_MAX_EVIDENCE_STATE = 127 of a node can be clamped as evidence (the host mirrors raise a BoundsError
+ *     for a larger evidence state instead of letting it wrap to "free")
  *   - factors are column-major Float64 exactly as Factor.potential (src/Factors/factors_main.jl:20);
  *     variables are int32 ids (the Julia glue maps Symbol <-> id)
  *   - host pointers unless the name ends in _dev; the caller owns every host buffer, the library owns
@@ -42,7 +44,8 @@
 extern "C" {
 #endif
 
-#define BN_MAX_CARD 128
+#define BN_MAX_CARD 255
+#define BN_MAX_EVIDENCE_STATE 127
 typedef uint64_t bn_net_t;    /* device-resident flattened DiscreteBayesNet */
 typedef uint64_t bn_factor_t; /* device-resident Factor (dims + column-major fp64 potential) */
 

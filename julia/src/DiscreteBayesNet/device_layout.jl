@@ -58,6 +58,7 @@ function evidence_vector(lay::DeviceLayout, bn::DiscreteBayesNet, evidence::Assi
         i = bn.name_to_index[k]
         v isa Integer || throw(TypeError(:evidence_vector, "state of $k", Integer, v))
         1 <= v <= lay.card[i] || throw(BoundsError(1:lay.card[i], v))
+        v - 1 <= 127 || throw(BoundsError(1:128, v))   # int8 on the ABI (BN_MAX_EVIDENCE_STATE): never wrap to "free"
         ev[i] = Int8(v - 1)
     end
     return ev
@@ -66,15 +67,17 @@ end
 query_indices(bn::DiscreteBayesNet, query::NodeNames) = Int32[bn.name_to_index[q] - 1 for q in query]
 
 """
-A DiscreteBayesNet resident in HBM (opaque `bn_net_t`).  One upload per (network, device);
-`bn_net_destroy` runs from the finalizer.
+A DiscreteBayesNet resident in HBM (opaque `bn_net_t`).  One upload per (network contents, device or communicator)
+-- see `device_net` in CUDABackend.jl; `bn_net_destroy` runs from the finalizer.  With a `Communicator` the network is
+replicated on every GPU of the communicator (`bn_net_create_comm`) and `device` is its first GPU.
 """
 mutable struct DeviceNet
     handle::UInt64
     layout::DeviceLayout
     device::Int32
-    function DeviceNet(bn::DiscreteBayesNet; device::Integer=0)
-        lay = DeviceLayout(bn)
+    comm::Any                      # Communicator or nothing (kept alive as long as the net)
+    function DeviceNet(lay::DeviceLayout; device::Integer=0)
+        maximum(lay.card) <= 255 || throw(ArgumentError("a node has more than 255 states (uint8 states on the device)"))
         h = Ref{UInt64}(0)
         par_idx = isempty(lay.par_idx) ? Int32[0] : lay.par_idx
         GC.@preserve lay par_idx begin
@@ -82,8 +85,22 @@ mutable struct DeviceNet
                             (Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Int32, Ref{UInt64}),
                             length(lay.names), lay.card, lay.par_ptr, par_idx, lay.cpt_off, lay.cpt, device, h))
         end
-        net = new(h[], lay, Int32(device))
+        net = new(h[], lay, Int32(device), nothing)
+        finalizer(x -> ccall((:bn_net_destroy, libbn_cuda), Int32, (UInt64,), x.handle), net)
+        return net
+    end
+    function DeviceNet(lay::DeviceLayout, comm)
+        maximum(lay.card) <= 255 || throw(ArgumentError("a node has more than 255 states (uint8 states on the device)"))
+        h = Ref{UInt64}(0)
+        par_idx = isempty(lay.par_idx) ? Int32[0] : lay.par_idx
+        GC.@preserve lay par_idx begin
+            _bn_check(ccall((:bn_net_create_comm, libbn_cuda), Int32,
+                            (Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, UInt64, Ref{UInt64}),
+                            length(lay.names), lay.card, lay.par_ptr, par_idx, lay.cpt_off, lay.cpt, comm.handle, h))
+        end
+        net = new(h[], lay, comm.devices[1], comm)
         finalizer(x -> ccall((:bn_net_destroy, libbn_cuda), Int32, (UInt64,), x.handle), net)
         return net
     end
 end
+DeviceNet(bn::DiscreteBayesNet; device::Integer=0) = DeviceNet(DeviceLayout(bn); device=device)

@@ -20,7 +20,9 @@ const BN_DIM_MISMATCH = Int32(-2)
 const BN_NOT_IN_FACTOR = Int32(-3)
 const BN_ZERO_WEIGHT = Int32(-5)
 const BN_OOM = Int32(-6)
+const BN_UNSUPPORTED = Int32(-7)
 const BN_BOUNDS = Int32(-8)
+const BN_NCCL_ERR = Int32(-9)
 
 _bn_msg() = unsafe_string(ccall((:bn_last_error, libbn_cuda), Cstring, ()))
 
@@ -32,6 +34,7 @@ function _bn_check(rc::Int32)
     (rc == BN_BAD_ARG || rc == BN_NOT_IN_FACTOR) && throw(ArgumentError(msg))  # inference.jl:10-11, errors.jl:12
     rc == BN_BOUNDS && throw(BoundsError(msg))                         # factors_access.jl:59-61
     rc == BN_OOM && throw(OutOfMemoryError())
+    rc == BN_NCCL_ERR && error("NCCL: $msg")
     error("libbn_cuda status $rc: $msg")
 end
 
@@ -39,10 +42,11 @@ end
     set_lw_mode(mode::Symbol=:auto; prune::Bool=true)
     set_gibbs_mode(mode::Symbol=:auto)
 
-Kernel selection for this thread (include/bn_cuda.h): `:auto` lets the generic interpreter kernels serve calls until
-enough work has been requested for one (structure, evidence mask, query) to amortise the NVRTC compile of the
-network-specialised kernel; `:generic` / `:specialized` force one or the other. `prune` lets the specialised LW
-kernel skip barren nodes (never changes a count bit).
+Kernel selection for this thread (include/bn_cuda.h): `:auto` uses the network-specialised kernel as soon as its cubin
+is at hand (in the process or in the on-disk cache); until then the generic interpreter kernels serve the calls while
+NVRTC compiles on a background thread -- no call waits for a compile.  `:generic` / `:specialized` force one or the
+other (`:specialized` blocks on the first compile). `prune` lets the specialised LW kernel skip barren nodes (never
+changes a count bit).
 """
 const _KERNEL_MODES = Dict(:auto => Int32(0), :generic => Int32(1), :specialized => Int32(2))
 set_lw_mode(mode::Symbol=:auto; prune::Bool=true) =
@@ -50,21 +54,98 @@ set_lw_mode(mode::Symbol=:auto; prune::Bool=true) =
 set_gibbs_mode(mode::Symbol=:auto) =
     _bn_check(ccall((:bn_set_gibbs_mode, libbn_cuda), Int32, (Int32,), _KERNEL_MODES[mode]))
 
-# one resident copy of the network per BayesNet object (WeakKeyDict so it dies with the net)
-const _device_nets = WeakKeyDict{Any,DeviceNet}()
-device_net(bn::DiscreteBayesNet; device::Integer=0) = get!(() -> DeviceNet(bn; device=device), _device_nets, bn)
+# Seeds: the reference draws fresh random numbers on every call (Julia's global RNG).  `seed = nothing` (the default
+# everywhere below) takes the next value of a process-wide counter; an explicit seed reproduces a call bit for bit.
+const _seed_counter = Ref{UInt64}(0)
+_next_seed(seed::Nothing) = (_seed_counter[] += 1; UInt64(0x5EED000000000000) + _seed_counter[])
+_next_seed(seed::Integer) = UInt64(seed)
+
+# ------------------------------------------------------------------------------------------------
+# Multi-GPU: one `infer` call for the whole machine (src/ProbabilisticGraphicalModels/inference.jl:48-49).
+# A Julia session is ONE process, so it uses bn_comm_init_all: libbn_cuda.so creates one NCCL communicator and one
+# stream per listed device, bn_net_create_comm replicates the network on all of them, and bn_lw_infer / bn_gibbs_infer
+# on such a net shard the global particle / chain range over the GPUs and issue the one ncclAllReduce themselves.
+# (Process-per-GPU launches -- MPI.jl, Distributed -- call bn_comm_unique_id on rank 0, broadcast the 128 bytes and
+# call bn_comm_init_rank on every rank; the rest is identical.)
+mutable struct Communicator
+    handle::UInt64
+    devices::Vector{Int32}
+    function Communicator(handle::UInt64, devices::Vector{Int32})
+        c = new(handle, devices)
+        finalizer(x -> ccall((:bn_comm_destroy, libbn_cuda), Int32, (UInt64,), x.handle), c)
+        return c
+    end
+end
+
+"One process drives all of `devices` (ncclCommInitAll): what a Julia session uses."
+function Communicator(devices::AbstractVector{<:Integer})
+    devs = Int32[d for d in devices]
+    h = Ref{UInt64}(0)
+    GC.@preserve devs begin
+        _bn_check(ccall((:bn_comm_init_all, libbn_cuda), Int32, (Ptr{Int32}, Int32, Ref{UInt64}), devs, length(devs), h))
+    end
+    return Communicator(h[], devs)
+end
+
+"Communicator of one process-per-GPU rank (`id` = rank 0's `comm_unique_id()`, shipped by the launcher)."
+function Communicator(id::Vector{UInt8}, rank::Integer, world::Integer, device::Integer)
+    length(id) == 128 || throw(ArgumentError("NCCL id must be 128 bytes"))
+    h = Ref{UInt64}(0)
+    GC.@preserve id begin
+        _bn_check(ccall((:bn_comm_init_rank, libbn_cuda), Int32, (Ptr{UInt8}, Int32, Int32, Int32, Ref{UInt64}),
+                        id, rank, world, device, h))
+    end
+    return Communicator(h[], Int32[device])
+end
+
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    _bn_check(ccall((:bn_comm_unique_id, libbn_cuda), Int32, (Ptr{UInt8},), id))
+    return id
+end
+
+"(world, first_rank, n_local) of a communicator."
+function comm_info(c::Communicator)
+    w = Ref{Int32}(0); f = Ref{Int32}(0); n = Ref{Int32}(0)
+    _bn_check(ccall((:bn_comm_info, libbn_cuda), Int32, (UInt64, Ref{Int32}, Ref{Int32}, Ref{Int32}), c.handle, w, f, n))
+    return Int(w[]), Int(f[]), Int(n[])
+end
+comm_barrier(c::Communicator) = _bn_check(ccall((:bn_comm_barrier, libbn_cuda), Int32, (UInt64,), c.handle))
+
+# one communicator per device list, made on first use
+const _communicators = Dict{Vector{Int32},Communicator}()
+_communicator(devices) = get!(() -> Communicator(devices), _communicators, Int32[d for d in devices])
+
+# Resident copies of a network: one per (network CONTENTS, device or device list).  Keyed weakly by the BayesNet object
+# and, inside, by a hash of the flattened layout, so a CPD edited in place is re-uploaded instead of served stale.
+const _device_nets = WeakKeyDict{Any,Dict{Any,DeviceNet}}()
+function device_net(bn::DiscreteBayesNet; device::Integer=0, devices=nothing)
+    lay = DeviceLayout(bn)
+    fp = hash((lay.card, lay.par_ptr, lay.par_idx, lay.cpt_off, lay.cpt, lay.names))
+    where_ = devices === nothing ? Int32(device) : Int32[d for d in devices]
+    cache = get!(() -> Dict{Any,DeviceNet}(), _device_nets, bn)
+    for k in collect(keys(cache))                  # contents changed: drop the stale copies
+        k[1] == fp || delete!(cache, k)
+    end
+    return get!(cache, (fp, where_)) do
+        devices === nothing ? DeviceNet(lay; device=device) : DeviceNet(lay, _communicator(devices))
+    end
+end
 
 # ------------------------------------------------------------------------------------------------
 # Likelihood weighting                                     replaces src/Inference/likelihood.jl:16-58
+# `devices = 0:7` runs the ONE call on all eight GPUs (particles sharded by global index + one all-reduce inside the
+# library); `devices = nothing` uses the single GPU `device`.
 @with_kw struct CUDALikelihoodWeighting <: InferenceMethod
     nsamples::Int = 500
-    seed::UInt64 = 0
+    seed::Union{UInt64,Nothing} = nothing
     device::Int = 0
+    devices::Union{Nothing,AbstractVector{<:Integer}} = nothing
 end
 
 function infer(im::CUDALikelihoodWeighting, inf::InferenceState{BN}) where {BN<:DiscreteBayesNet}
     bn = inf.pgm
-    net = device_net(bn; device=im.device)
+    net = device_net(bn; device=im.device, devices=im.devices)
     ev = evidence_vector(net.layout, bn, inf.evidence)
     q = query_indices(bn, inf.query)
     ϕ = Factor(inf.query, map(n -> ncategories(bn, n), inf.query))     # likelihood.jl:22
@@ -72,7 +153,7 @@ function infer(im::CUDALikelihoodWeighting, inf::InferenceState{BN}) where {BN<:
     GC.@preserve ev q ϕ stats begin
         _bn_check(ccall((:bn_lw_infer, libbn_cuda), Int32,
                         (UInt64, Ptr{Int8}, Ptr{Int32}, Int32, UInt64, UInt64, UInt64, Ptr{Float64}, Ptr{Float64}),
-                        net.handle, ev, q, length(q), 0, im.nsamples, im.seed, ϕ.potential, stats))
+                        net.handle, ev, q, length(q), 0, im.nsamples, _next_seed(im.seed), ϕ.potential, stats))
     end
     normalize!(ϕ)                                                       # likelihood.jl:56 (0/0 -> NaN as before)
     return ϕ
@@ -86,8 +167,9 @@ end
     thin::Int = 3
     state::Assignment = Assignment()
     n_chains::Int = 1          # 1 = the reference's single chain; >1 = independent chains, counts summed
-    seed::UInt64 = 0
+    seed::Union{UInt64,Nothing} = nothing
     device::Int = 0
+    devices::Union{Nothing,AbstractVector{<:Integer}} = nothing   # e.g. 0:7: chains sharded over the GPUs
 end
 @with_kw mutable struct CUDAGibbsFull <: InferenceMethod
     nsamples::Int = 2000
@@ -95,8 +177,9 @@ end
     thin::Int = 3
     state::Assignment = Assignment()
     n_chains::Int = 1
-    seed::UInt64 = 0
+    seed::Union{UInt64,Nothing} = nothing
     device::Int = 0
+    devices::Union{Nothing,AbstractVector{<:Integer}} = nothing
 end
 _gibbs_mode(::CUDAGibbsNodewise) = Int32(0)
 _gibbs_mode(::CUDAGibbsFull) = Int32(1)
@@ -105,7 +188,7 @@ function infer(im::Union{CUDAGibbsNodewise,CUDAGibbsFull}, inf::InferenceState{B
     im.burn_in < im.nsamples || throw(ArgumentError("Burn in ($(im.burn_in)) " *
                 "must be less than number of samples ($(im.nsamples))"))    # gibbs.jl:70-71
     bn = inf.pgm
-    net = device_net(bn; device=im.device)
+    net = device_net(bn; device=im.device, devices=im.devices)
     lay = net.layout
     ev = evidence_vector(lay, bn, inf.evidence)
     q = query_indices(bn, inf.query)
@@ -115,7 +198,9 @@ function infer(im::Union{CUDAGibbsNodewise,CUDAGibbsFull}, inf::InferenceState{B
     init = Int32(0)
     if !isempty(im.state)                        # resume from im.state (gibbs.jl:83-88)
         for c in 1:im.n_chains, (i, nm) in enumerate(lay.names)
-            st[i, c] = UInt8(get(inf.evidence, nm, im.state[nm]) - 1)
+            x = get(inf.evidence, nm, im.state[nm])
+            1 <= x <= lay.card[i] || throw(BoundsError(1:lay.card[i], x))   # the state indexes the CPTs on the device
+            st[i, c] = UInt8(x - 1)
         end
         init = Int32(1)
     end
@@ -124,7 +209,7 @@ function infer(im::Union{CUDAGibbsNodewise,CUDAGibbsFull}, inf::InferenceState{B
                         (UInt64, Ptr{Int8}, Ptr{Int32}, Int32, UInt64, UInt64, Int64, Int64, Int64, Int32, UInt64,
                          Ptr{UInt8}, Int32, Ptr{Float64}, Ptr{Float64}),
                         net.handle, ev, q, length(q), 0, im.n_chains, im.nsamples, im.burn_in, im.thin,
-                        _gibbs_mode(im), im.seed, st, init, ϕ.potential, C_NULL))
+                        _gibbs_mode(im), _next_seed(im.seed), st, init, ϕ.potential, C_NULL))
     end
     for (i, nm) in enumerate(lay.names)          # im.state = x (gibbs.jl:141)
         im.state[nm] = Int(st[i, 1]) + 1
@@ -205,17 +290,20 @@ end
 # ------------------------------------------------------------------------------------------------
 # Table samplers                                      replaces src/sampling.jl:24-41,52-57,72-93,153-174
 struct CUDADirectSampler <: BayesNetSampler
-    seed::UInt64
+    seed::Union{UInt64,Nothing}
 end
+CUDADirectSampler() = CUDADirectSampler(nothing)
 struct CUDARejectionSampler <: BayesNetSampler
     evidence::Assignment
     max_nsamples::Int
-    seed::UInt64
+    seed::Union{UInt64,Nothing}
 end
+CUDARejectionSampler(evidence::Assignment; max_nsamples::Int=100) = CUDARejectionSampler(evidence, max_nsamples, nothing)
 struct CUDALikelihoodWeightedSampler <: BayesNetSampler
     evidence::Assignment
-    seed::UInt64
+    seed::Union{UInt64,Nothing}
 end
+CUDALikelihoodWeightedSampler(evidence::Assignment) = CUDALikelihoodWeightedSampler(evidence, nothing)
 
 function _sample_table(bn::DiscreteBayesNet, ev::Vector{Int8}, kind::Integer, attempts::Integer, n::Integer, seed)
     net = device_net(bn)
@@ -225,7 +313,7 @@ function _sample_table(bn::DiscreteBayesNet, ev::Vector{Int8}, kind::Integer, at
     GC.@preserve ev states w ok begin
         _bn_check(ccall((:bn_sample, libbn_cuda), Int32,
                         (UInt64, Ptr{Int8}, Int32, Int32, UInt64, UInt64, UInt64, Ptr{UInt8}, Ptr{Float64}, Ptr{UInt8}),
-                        net.handle, ev, kind, attempts, 0, n, seed, states, w, ok))
+                        net.handle, ev, kind, attempts, 0, n, _next_seed(seed), states, w, ok))
     end
     return states, w, ok
 end
@@ -250,37 +338,126 @@ function Random.rand(bn::DiscreteBayesNet, s::CUDALikelihoodWeightedSampler, nsa
     return df
 end
 
+"""
+    cuda_get_weighted_sample(bn, evidence) -> (Assignment, weight)
+
+get_weighted_sample (src/sampling.jl:102-121): one likelihood-weighted particle, evidence clamped.
+"""
+function cuda_get_weighted_sample(bn::DiscreteBayesNet, evidence::Assignment; seed=nothing)
+    lay = device_net(bn).layout
+    ev = evidence_vector(lay, bn, evidence)
+    states, w, _ = _sample_table(bn, ev, 2, 1, 1, seed)
+    a = Assignment()
+    for (i, nm) in enumerate(lay.names)
+        a[nm] = Int(states[1, i]) + 1
+    end
+    return (a, w[1])
+end
+cuda_get_weighted_sample(bn::DiscreteBayesNet, pair::Pair{NodeName}...; seed=nothing) =
+    cuda_get_weighted_sample(bn, Assignment(pair); seed=seed)
+
 # gibbs_sample(bn, nsamples, burn_in; ...) on the device    replaces src/gibbs.jl:289-374 (discrete nets)
+# Same keyword surface, validation order and messages as the reference (:289-324).  `time_limit` is validated but never
+# triggers (the device loop has no wall clock; the reference only uses it to cut a slow CPU loop short, :218-220) and
+# `max_cache_size` is accepted and unused (the string-keyed conditional cache, :43-71, is a CPU optimisation).
+# Extras: `seed`, `n_chains` (1 = the reference's single chain; more = independent chains, nsamples rows each).
 function cuda_gibbs_sample(bn::DiscreteBayesNet, nsamples::Integer, burn_in::Integer;
-        thinning::Integer=0, consistent_with::Assignment=Assignment(),
+        thinning::Integer=0,
+        consistent_with::Assignment=Assignment(),
         variable_order::Union{Vector{Symbol},Nothing}=nothing,
-        initial_sample::Union{Assignment,Nothing}=nothing, seed::Integer=0, n_chains::Integer=1)
+        time_limit::Union{Int,Nothing}=nothing,
+        error_if_time_out::Bool=true,
+        initial_sample::Union{Assignment,Nothing}=nothing,
+        max_cache_size::Union{Int,Nothing}=nothing,
+        seed=nothing, n_chains::Integer=1)
     nsamples > 0 || throw(ArgumentError("nsamples parameter less than 1"))       # gibbs.jl:299-301
     burn_in >= 0 || throw(ArgumentError("Negative burn_in parameter"))
-    thinning >= 0 || throw(ArgumentError("Negative sample_skip parameter"))
+    thinning >= 0 || throw(ArgumentError("Negative thinning parameter"))
+    bn_names = names(bn)
+    if variable_order !== nothing                                                  # gibbs.jl:302-311
+        for name in bn_names
+            name in variable_order || throw(ArgumentError("Gibbs sample variable_order must contain all variables in the Bayes Net"))
+        end
+        for name in variable_order
+            name in bn_names || throw(ArgumentError("Gibbs sample variable_order contains a variable not in the Bayes Net"))
+        end
+    end
+    if time_limit !== nothing                                                      # gibbs.jl:312-314
+        time_limit > 0 || throw(ArgumentError(join(["Invalid time_limit specified (", time_limit, ")"])))
+    end
+    if initial_sample !== nothing                                                  # gibbs.jl:315-324
+        for name in bn_names
+            haskey(initial_sample, name) || throw(ArgumentError("Gibbs sample initial_sample must be an assignment with all variables in the Bayes Net"))
+        end
+        for name in keys(consistent_with)
+            initial_sample[name] == consistent_with[name] || throw(ArgumentError("Gibbs sample initial_sample was inconsistent with consistent_with"))
+        end
+        pdf(bn, initial_sample) > 0 || throw(ArgumentError("Gibbs sample initial_sample has a pdf value of zero"))
+    end
     net = device_net(bn)
     lay = net.layout
     ev = evidence_vector(lay, bn, consistent_with)
     free = [nm for (i, nm) in enumerate(lay.names) if ev[i] < 0]
     order = C_NULL
-    if variable_order !== nothing                                                  # gibbs.jl:302-313
-        sort(variable_order) == sort(free) ||
-            throw(ArgumentError("variable_order must contain exactly the non-evidence variables"))
-        order = Int32[findfirst(==(v), free) - 1 for v in variable_order]
+    if variable_order !== nothing       # evidence variables are never resampled (gibbs.jl:210): keep the free ones, in order
+        order = Int32[findfirst(==(v), free) - 1 for v in variable_order if v in free]
     end
     init = C_NULL
-    if initial_sample !== nothing                                                  # gibbs.jl:315-324
-        all(haskey(initial_sample, nm) for nm in lay.names) ||
-            throw(ArgumentError("Gibbs sample initial_sample must be an assignment with all variables in the Bayes Net"))
+    if initial_sample !== nothing
         init = repeat(UInt8[initial_sample[nm] - 1 for nm in lay.names], 1, n_chains)
     end
     out = Matrix{UInt8}(undef, n_chains * nsamples, length(lay.names))
     GC.@preserve ev order init out begin
         _bn_check(ccall((:bn_gibbs_sample, libbn_cuda), Int32,
                         (UInt64, Ptr{Int8}, UInt64, UInt64, Int64, Int64, Int64, Ptr{Int32}, UInt64, Ptr{UInt8}, Ptr{UInt8}),
-                        net.handle, ev, 0, n_chains, nsamples, burn_in, thinning, order, seed, init, out))
+                        net.handle, ev, 0, n_chains, nsamples, burn_in, thinning, order, _next_seed(seed), init, out))
     end
-    return DataFrame([nm => Int.(out[:, i]) .+ 1 for (i, nm) in enumerate(lay.names)])
+    samples = DataFrame([nm => Int.(out[:, i]) .+ 1 for (i, nm) in enumerate(lay.names) if ev[i] < 0])
+    # columns for the variables that were conditioned on, Float64 like the reference (gibbs.jl:368-373)
+    evidence = Dict{Symbol,Array{Float64,1}}()
+    for varname in keys(consistent_with)
+        evidence[varname] = ones(size(samples)[1]) * consistent_with[varname]
+    end
+    return hcat(samples, DataFrame(evidence))
+end
+
+"""
+GibbsSampler on the device (src/gibbs.jl:410-451): same fields and defaults as the reference's `GibbsSampler`.
+"""
+mutable struct CUDAGibbsSampler <: BayesNetSampler
+    evidence::Assignment
+    burn_in::Int
+    thinning::Int
+    variable_order::Union{Vector{Symbol},Nothing}
+    time_limit::Union{Int,Nothing}
+    error_if_time_out::Bool
+    initial_sample::Union{Assignment,Nothing}
+    max_cache_size::Union{Int,Nothing}
+
+    function CUDAGibbsSampler(evidence::Assignment=Assignment();
+        burn_in::Int=100,
+        thinning::Int=0,
+        variable_order::Union{Vector{Symbol},Nothing}=nothing,
+        time_limit::Union{Int,Nothing}=nothing,
+        error_if_time_out::Bool=true,
+        initial_sample::Union{Assignment,Nothing}=nothing,
+        max_cache_size::Union{Int,Nothing}=nothing)
+        new(evidence, burn_in, thinning, variable_order, time_limit, error_if_time_out, initial_sample, max_cache_size)
+    end
+end
+
+Random.rand(bn::DiscreteBayesNet, sampler::CUDAGibbsSampler, nsamples::Integer) =
+    cuda_gibbs_sample(bn, nsamples, sampler.burn_in; thinning=sampler.thinning,
+        consistent_with=sampler.evidence, variable_order=sampler.variable_order,
+        time_limit=sampler.time_limit, error_if_time_out=sampler.error_if_time_out,
+        initial_sample=sampler.initial_sample, max_cache_size=sampler.max_cache_size)
+
+function Random.rand!(a::Assignment, bn::DiscreteBayesNet, sampler::CUDAGibbsSampler)   # gibbs.jl:454-460
+    df = rand(bn, sampler, 1)
+    for name in names(bn)
+        a[name] = df[1, name]
+    end
+    return a
 end
 
 # ------------------------------------------------------------------------------------------------

@@ -113,3 +113,52 @@ def test_factor_from_bn_matches_cpd_layout(bn, golden):
         sl = bn.Factor.from_bn(net, name, ev)
         assert sl.dimensions == [name] + cpd.parents[1:]
         assert np.array_equal(sl.potential, np.take(phi.potential, 0, axis=1))
+
+
+def test_exact_c5_at_its_stated_size(bn):
+    """BASELINE configs[4] at full size: ExactInference on a 30-node binary net whose hub has 23 parents (a 2^24-entry
+    CPT, 128 MiB) -- src/Inference/exact.jl:6-33.  The numpy oracle materialises every product (minutes at this size),
+    so here: fused == the reference's pairwise product-then-sum to 1e-12, the posterior is a distribution, evidence
+    on a root changes it the way Bayes' rule says (P(q) = sum_e P(q | e) P(e)); the oracle itself is compared on the
+    same construction with 19 parents (2^20 entries)."""
+    import ctypes as C
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import path_bench
+    from bayesnets_jl_b200 import _lib
+    from bayesnets_jl_b200.device_layout import DeviceNet
+
+    def run(lay, dn, ev, q, fused):
+        o, od, oc = np.zeros(2), np.zeros(1, np.int32), np.zeros(1, np.int32)
+        _lib.check(_lib.lib().bn_exact_infer(_lib.h64(dn.handle), _lib.ptr(ev, _lib.i8p), _lib.ptr(q, _lib.i32p), C.c_int32(1),
+                                             C.c_int32(fused), _lib.ptr(od, _lib.i32p), _lib.ptr(oc, _lib.i32p),
+                                             _lib.ptr(o, _lib.f64p)))
+        assert int(od[0]) == int(q[0]) and int(oc[0]) == 2
+        return o
+
+    lay = path_bench.c5_layout(bn, k=23)
+    assert lay.n == 30 and int(lay.cpt_off[-1] - lay.cpt_off[-2]) == 1 << 24
+    dn = DeviceNet(lay, 0)
+    q = np.array([lay.n - 1], np.int32)
+    ev = np.full(lay.n, -1, np.int8)
+    ev[3] = 1
+    pf, pu = run(lay, dn, ev, q, 1), run(lay, dn, ev, q, 0)
+    np.testing.assert_allclose(pf, pu, rtol=RTOL)
+    assert abs(pf.sum() - 1.0) < 1e-12 and (pf > 0).all()
+    # total probability over the evidence node: P(hub) = sum_s P(hub | B4 = s) P(B4 = s)
+    none = np.full(lay.n, -1, np.int8)
+    prior_q = run(lay, dn, none, q, 1)
+    prior_e = run(lay, dn, none, np.array([3], np.int32), 1)
+    ev0 = none.copy()
+    ev0[3] = 0
+    mix = prior_e[0] * run(lay, dn, ev0, q, 1) + prior_e[1] * pf
+    np.testing.assert_allclose(mix, prior_q, rtol=1e-11)
+    dn.close()
+    # the oracle on the 2^20 sub-case
+    lay_s = path_bench.c5_layout(bn, k=19)
+    dn_s = DeviceNet(lay_s, 0)
+    got = run(lay_s, dn_s, ev, np.array([lay_s.n - 1], np.int32), 1)
+    ref = exact_infer(oracle_net_from_layout(lay_s), [lay_s.names[-1]], {lay_s.names[3]: 1}).permuted_to([lay_s.names[-1]])
+    np.testing.assert_allclose(got, ref, rtol=RTOL)
+    dn_s.close()

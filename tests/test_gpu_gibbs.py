@@ -199,3 +199,31 @@ def test_gibbs_wide_query_and_cards_up_to_8(bn, gibbs_mode, mode):
         oc, _ = capi.gibbs_infer(on, lay.evidence_vector({"d": 1}), lay.query_indices(["a", "b"]), 200, 300, 60, 2,
                                  full=full, seed=7)
         assert np.array_equal(c, oc.ravel(order="F"))
+
+
+def test_gibbs_c4_at_its_stated_size(bn, gibbs_mode):
+    """BASELINE configs[3] at full size on one GPU: GibbsSamplingNodewise(2000, 1000, 5), 200-node net, 20 evidence,
+    65 536 chains in ONE launch (src/Inference/gibbs.jl:66-145).  The oracle runs the first 256 chains: their
+    integer counts, per-chain counts and final states must be identical; every chain must have kept exactly
+    ceil((nsamples - burn_in) / thin) samples (:74)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gibbs_bench
+    gibbs_mode("specialized")
+    net, lay, query, evidence = gibbs_bench.build_case(bn)
+    assert lay.n == 200 and len(evidence) == 20
+    n_chains, nsamples, burn_in, thin = 65536, 2000, 1000, 5
+    im = bn.GibbsSamplingNodewise(nsamples=nsamples, burn_in=burn_in, thin=thin, n_chains=n_chains, seed=0,
+                                  keep_chain_counts=True)
+    counts = im.raw_counts(bn.InferenceState(net, query, evidence))
+    kept = -(-(nsamples - burn_in) // thin)
+    assert np.array_equal(im.last_chain_counts.sum(axis=1), np.full(n_chains, float(kept)))
+    assert counts.sum() == n_chains * kept and np.array_equal(counts, im.last_chain_counts.sum(axis=0))
+    on = oracle_net_from_layout(lay)
+    evv, qi = lay.evidence_vector(evidence), lay.query_indices(query)
+    oc, ost, opc = capi.gibbs_infer(on, evv, qi, 256, nsamples, burn_in, thin, seed=0, per_chain=True)
+    assert np.array_equal(im.last_chain_counts[:256], opc)
+    assert np.array_equal(im.chain_states[:256], ost)
+    for i, e in enumerate(evv):  # evidence stays clamped in every chain
+        if e >= 0:
+            assert (im.chain_states[:, i] == e).all()

@@ -269,3 +269,32 @@ def test_edge_cardinalities_and_deterministic_tables(bn, lw_mode, mode):
     _, st, w, ok = _sample(net, 5000, {"leaf": 1}, 2, 1, 9, None)
     ost, ow, _ = capi.sample(on, 5000, evidence=lay.evidence_vector({"leaf": 1}), kind=2, seed=9)
     assert np.array_equal(st, ost) and np.array_equal(w, ow)
+
+
+def test_lw_mc_bound_at_benchmark_scale(bn, lw_mode):
+    """north_star: "posteriors inside the stated MC bound" at the benchmark's size, not at a toy size: the C2 case of
+    bench.py (100 nodes, 10 evidence, 2 query, every node sampled), 4 calls x 1e9 particles with distinct seeds pooled
+    into one 4e9-particle estimate; every cell within 4 sigma (sigma^2 = p(1-p)/N_eff) of ExactInference on the device.
+    31-bit thresholds bias a probability by <= 2^-32, far below 4 sigma ~ 3e-5 here."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    def check(net, lay, query, evidence):
+        im = bn.LikelihoodWeightingInference(nsamples=4096, seed=1)
+        im.raw_counts(bn.InferenceState(net, query, evidence))
+        return im.last_stats[0] > 0
+
+    net, lay, query, evidence = bench.build_case(bn, check=check)
+    lw_mode("specialized", False)
+    c, sw, sw2 = 0.0, 0.0, 0.0
+    for seed in range(4):
+        counts, (a, b) = lw_raw(bn, net, query, evidence, 1_000_000_000, seed=seed)
+        c, sw, sw2 = c + counts, sw + a, sw2 + b
+    p = c / c.sum()
+    exact = bench.exact_posterior(bn, net, query, evidence, 0)
+    n_eff = sw * sw / sw2
+    assert n_eff > 1e8
+    z = bench.z_scores(p, exact, n_eff)
+    assert np.abs(z).max() < 4.0, z

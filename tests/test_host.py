@@ -327,3 +327,64 @@ def test_cubin_disk_cache_serves_a_second_process(bn, tmp_path):
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     third = json.loads(r.stdout.strip().splitlines()[-1])
     assert third["stats"]["nvrtc_compiles"] == 1 and third["stats"]["disk_hits"] == 0 and third["cubin"] == first["cubin"]
+
+
+def test_evidence_state_beyond_int8_is_an_error_not_free(bn):
+    """Evidence travels as int8 (-1 = free): a state above 128 of a wide node must raise, never wrap to 'free'."""
+    rng = np.random.default_rng(0)
+    net = bn.BayesNet()
+    net.push(bn.CategoricalCPD("wide", [], [], [rng.dirichlet(np.ones(200))]))
+    net.push(bn.CategoricalCPD("leaf", ["wide"], [200], [rng.dirichlet(np.ones(2)) for _ in range(200)]))
+    lay = bn.flatten(net)
+    assert lay.evidence_vector({"wide": 128})[0] == 127
+    with pytest.raises(IndexError):
+        lay.evidence_vector({"wide": 129})
+    with pytest.raises(IndexError):
+        lay.evidence_vector({"wide": 201})
+
+
+def test_julia_ccalls_match_the_header():
+    """julia/src/**: every `ccall((:bn_*, libbn_cuda), Ret, (Types...), args...)` must bind a prototype of
+    include/bn_cuda.h with the same arity and C types, and so must the ctypes table (tools/abi_table.py).  Julia cannot
+    run in this image; this is what keeps the glue a maintainer would add from drifting away from the ABI."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import abi_table
+    protos, calls, errs = abi_table.check()
+    assert not errs, "\n".join(errs)
+    assert len(calls) >= 40 and len({c["name"] for c in calls}) >= 37
+    # the entry points the hot path needs are all bound from Julia
+    bound = {c["name"] for c in calls}
+    for need in ("bn_net_create", "bn_net_create_comm", "bn_comm_init_all", "bn_comm_init_rank", "bn_lw_infer", "bn_gibbs_infer",
+                 "bn_gibbs_sample", "bn_sample", "bn_exact_infer", "bn_factor_product", "bn_factor_sum", "bn_factor_normalize",
+                 "bn_factor_eliminate", "bn_loopy_infer", "bn_statistics", "bn_logpdf"):
+        assert need in bound, need
+    # INTEGRATION.md carries the table generated from this parse
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert abi_table.markdown(protos, calls) in doc, "regenerate: python tools/abi_table.py (INTEGRATION.md section 2)"
+
+
+def test_julia_and_python_hosts_expose_the_same_surface(bn):
+    """The two host mirrors must not drift: the reference's keyword surface of gibbs_sample / GibbsSampler
+    (src/gibbs.jl:289-297,410-433), its validation messages (:299-323) and the samplers are in both."""
+    import inspect
+    jl = open(os.path.join(ROOT, "julia", "src", "Inference", "CUDABackend", "CUDABackend.jl")).read()
+    py = inspect.signature(bn.gibbs_sample).parameters
+    for kw in ("thinning", "consistent_with", "variable_order", "time_limit", "error_if_time_out", "initial_sample",
+               "max_cache_size"):
+        assert kw in py and re.search(rf"\b{kw}::", jl), kw
+    for msg in ("nsamples parameter less than 1", "Negative burn_in parameter", "Negative thinning parameter",
+                "Gibbs sample variable_order must contain all variables in the Bayes Net",
+                "Gibbs sample variable_order contains a variable not in the Bayes Net",
+                "Gibbs sample initial_sample must be an assignment with all variables in the Bayes Net",
+                "Gibbs sample initial_sample was inconsistent with consistent_with",
+                "Gibbs sample initial_sample has a pdf value of zero"):
+        assert msg in jl and msg in inspect.getsource(bn.gibbs_sample), msg
+    for name in ("cuda_get_weighted_sample", "CUDAGibbsSampler", "CUDALikelihoodWeightedSampler", "CUDARejectionSampler",
+                 "CUDADirectSampler", "CUDALikelihoodWeighting", "CUDAGibbsNodewise", "CUDAGibbsFull", "CUDAExact",
+                 "CUDALoopyBelief", "Communicator"):
+        assert name in jl, name
+    for name in ("get_weighted_sample", "GibbsSampler", "LikelihoodWeightedSampler", "RejectionSampler", "DirectSampler",
+                 "LikelihoodWeightingInference", "GibbsSamplingNodewise", "GibbsSamplingFull", "ExactInference", "LoopyBelief",
+                 "Communicator"):
+        assert hasattr(bn, name), name
+    assert "Float64" in jl[jl.index("function cuda_gibbs_sample"):jl.index("mutable struct CUDAGibbsSampler")]  # evidence columns
