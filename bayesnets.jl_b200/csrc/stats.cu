@@ -29,6 +29,12 @@
 // bytes per row, read once.  Count tables too large for shared memory fall back to global atomics.
 #include "common.cuh"
 
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <type_traits>
+
 namespace bn {
 
 constexpr int STATS_REG_PARENTS = 3;  // parents held in registers; further ones are read from the program
@@ -187,17 +193,14 @@ __global__ void __launch_bounds__(1024, 1) statistics_kernel(const StatsArgs a) 
     }
 }
 
-static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch,
-                                 unsigned long long* out_dev) {
+// The node-lane kernel above behind its launch logic: the fallback for families with more than 256 bins (a bin index
+// must fit one byte for the row-lane kernel below) and for networks too wide for its tiles.  out_dev is already zeroed.
+static int32_t statistics_launch_nodelanes(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch,
+                                           unsigned long long* out_dev) {
   const DevProps& dp = dev_props(net->device);
   cudaStream_t s = tl_stream;
   const int n = net->n;
   const int64_t n_bins = net->cpt_off[n];
-  BN_REQUIRE(n_bins < (int64_t)0x7fffffff, BN_UNSUPPORTED, "count table too large (%lld entries)", (long long)n_bins);
-  BN_REQUIRE(pitch >= n_rows, BN_BAD_ARG, "pitch (%llu) smaller than n_rows (%llu)", (unsigned long long)pitch,
-             (unsigned long long)n_rows);
-  BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)n_bins * sizeof(unsigned long long), s));
-  if (n_rows == 0 || n == 0) return BN_OK;
   // per-node program: [table offset, n_par, (parent, stride) x n_par], stride includes the node's own cardinality
   std::vector<uint32_t> prog, prog_off((size_t)n);
   prog.reserve((size_t)n * 8);
@@ -273,6 +276,458 @@ static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_r
   count_launch();
   BN_CUDA_TRY(cudaGetLastError());
   return BN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ row-lane kernel
+// The kernel that serves every network whose families have <= 256 bins (all of BASELINE's: cards <= 4, <= 3 parents).
+//
+// What bounded the node-lane kernel above was shared memory: with 32 different NODES in a warp every histogram
+// read-modify-write lands in 32 unrelated banks (52% of its wavefronts were conflict replays, profiles/r1f_stats_*)
+// and every parent-state load is a gather.  This kernel turns the tile around: the 32 lanes of a warp are 32 ROW
+// groups (8 consecutive rows each: one 64-bit load per column carries their states), a warp owns whole NODES, and
+//   * a tile (256 rows x all nodes) arrives by ONE 2-D TMA copy (cp.async.bulk.tensor over a tensor map of the
+//     node-major table; rows past the end are zero-filled by the hardware) issued by a producer warp into a two-stage
+//     ring of full / empty mbarriers: consumer warps never meet at a CTA barrier, they only wait for data;
+//   * state loads are consecutive 64-bit words: conflict free, one request per (node | parent) column per 256 rows;
+//   * the bin index of 4 rows is computed at once on packed bytes: idx = s_i + sum_k m_k * s_parent_k as ONE IMAD per
+//     parent on a 32-bit word holding 4 rows (no byte ever exceeds 255 because the family has <= 256 bins);
+//   * every lane has PRIVATE counters in its own bank: 8-bit counters, 4 bins per 32-bit word, word (bin >> 2) of lane l
+//     at hist[(row0_i + (bin >> 2)) * 32 + l] -- the bank is the lane, so the read-modify-writes are conflict free by
+//     construction and need no atomics (a node belongs to one warp).  8 bits suffice because a lane adds at most 8 per
+//     tile: every 31 tiles the warp folds its counters into 32-bit per-CTA totals (a skewed, conflict-free transpose
+//     read, SIMD byte sums), which go to the 64-bit global table once at the end;
+//   * a warp walks its nodes two at a time with their read-modify-write chains interleaved (the 8 updates of one node
+//     must stay in order -- two rows may hit the same counter -- but two nodes never share one);
+//   * nodes are dealt to the warps of the CTA by the host (longest processing time first), tiles to the CTAs round-robin.
+// Rows past the table end and 0xFF-marked rows (rejection sampler gave up) take a per-tile slow path that zeroes their
+// states and gives them an increment of 0; states >= cardinality (the _dev entry trusts the table) are masked to the
+// node's power-of-two counter span, so they are miscounted but never written outside the counter area + its guard.
+// Tables whose base or pitch is not 16-byte aligned cannot be described by a tensor map: plain loads, one buffer.
+constexpr uint32_t ROWS_TR = 256;        // rows per tile = 8 per lane
+constexpr uint32_t ROWS_REC = 12;        // words per node record
+constexpr uint32_t ROWS_FLUSH = 31;      // tiles between folds: 31 * 8 = 248 <= 255
+constexpr uint32_t ROWS_GUARD = 32;      // counter word-rows behind the last node: where masked out-of-range bins may land
+constexpr uint32_t ROWS_MAX_WARPS = 24;  // consumer warps (+ 1 producer warp): 800 threads, <= 80 registers
+
+struct RowArgs {
+  const uint8_t* data;
+  uint64_t n_rows, pitch;
+  const uint32_t* prog;      // [3 * n_warps header | node records (ROWS_REC words, + 2 per extra parent)] -> smem
+  const uint32_t* row_out;   // per counter word-row: global bin of its first bin | (valid bins - 1) << 30
+  uint32_t prog_words, n_nodes, n_warps, n_wrows;
+  uint32_t box_nodes, n_boxes;   // TMA: n_boxes copies of box_nodes columns x 256 rows per tile
+  unsigned long long* out;
+};
+
+__device__ __forceinline__ uint32_t has_ff_byte(uint32_t v) {  // != 0 iff some byte of v is 0xFF
+  const uint32_t x = ~v;
+  return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+template <bool MORE, bool TMA>
+__global__ void __launch_bounds__((ROWS_MAX_WARPS + 1) * 32, 1)
+statistics_rows_kernel(const RowArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* prog = reinterpret_cast<uint32_t*>(smem_raw);
+  const uint32_t prog_pad = (a.prog_words + 31u) & ~31u;
+  uint32_t* hist = prog + prog_pad;                       // [n_wrows + guard][32] packed 8-bit counters, column = lane
+  uint32_t* tot = hist + (a.n_wrows + ROWS_GUARD) * 32u;  // [n_wrows * 4] 32-bit totals of this CTA
+  const uint32_t cols_pad = TMA ? a.box_nodes * a.n_boxes : a.n_nodes;
+  const uint32_t tile_bytes = cols_pad * ROWS_TR;         // dense [column][256 rows]
+  unsigned char* tiles = reinterpret_cast<unsigned char*>(tot + ((a.n_wrows * 4u + 31u) & ~31u));
+  __shared__ __align__(8) uint64_t bars[4];               // full[0..1], empty[0..1]
+  const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5;
+  for (uint32_t w = tid; w < a.prog_words; w += T) prog[w] = a.prog[w];
+  for (uint32_t w = tid; w < (a.n_wrows + ROWS_GUARD) * 32u + a.n_wrows * 4u; w += T) hist[w] = 0u;  // counters, guard, totals
+  const uint32_t full0 = s_addr(&bars[0]), empty0 = s_addr(&bars[2]);
+  if (TMA && tid == 0) {
+    for (uint32_t st = 0; st < 2u; ++st) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8u * st));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * st), "r"(a.n_warps));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t n_tiles = (a.n_rows + ROWS_TR - 1) / ROWS_TR;
+
+  if (TMA && warp == a.n_warps) {
+    // ---- producer warp: one lane keeps the two-stage ring full
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t st = it & 1u;
+        if (it >= 2u) mbar_wait(empty0 + 8u * st, ((it >> 1) - 1u) & 1u);  // every consumer warp released tile it - 2
+        const uint32_t bar = full0 + 8u * st;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+        for (uint32_t bx = 0; bx < a.n_boxes; ++bx) {
+          const uint32_t dst = s_addr(tiles + st * tile_bytes + bx * a.box_nodes * ROWS_TR);
+          const uint32_t c0 = (uint32_t)(t * ROWS_TR), c1 = bx * a.box_nodes;
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+              "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(bar)
+              : "memory");
+        }
+      }
+    }
+    return;
+  }
+  if (warp >= a.n_warps) return;  // (never: the launch has exactly n_warps consumer warps + the producer)
+
+  const uint32_t rec0 = prog[3 * warp], n_my = prog[3 * warp + 1], my_row0 = prog[3 * warp + 2] & 0xffffu,
+                 my_rows = prog[3 * warp + 2] >> 16;
+  // fold this warp's 8-bit lane-private counters into the CTA's 32-bit totals and clear them.  Lane l takes word-row
+  // r0 + l and walks its 32 lane columns starting at column l (skewed): every step touches 32 different banks.
+  auto fold = [&]() {
+    for (uint32_t base = 0; base < my_rows; base += 32u) {
+      const uint32_t r = base + lane;
+      if (r < my_rows) {
+        uint32_t* row = hist + (my_row0 + r) * 32u;
+        uint32_t lo = 0u, hi = 0u;  // 16-bit fields: bins 0, 2 | bins 1, 3 (32 * 255 < 65536)
+#pragma unroll 8
+        for (uint32_t c = 0; c < 32u; ++c) {
+          const uint32_t col = (c + lane) & 31u;
+          const uint32_t x = row[col];
+          row[col] = 0u;
+          lo += x & 0x00FF00FFu;
+          hi += (x >> 8) & 0x00FF00FFu;
+        }
+        uint32_t* t4 = tot + (my_row0 + r) * 4u;
+        t4[0] += lo & 0xFFFFu; t4[1] += hi & 0xFFFFu; t4[2] += lo >> 16; t4[3] += hi >> 16;
+      }
+    }
+    __syncwarp();
+  };
+
+  // one tile: my 8 rows of every column start at `tile`; SLOW = some row of the tile does not count
+  auto process = [&](const unsigned char* tile, auto slow_tag, uint32_t ok_lo, uint32_t ok_hi) {
+    constexpr bool SLOW = decltype(slow_tag)::value;
+    const uint32_t keep_lo = ok_lo * 0xFFu, keep_hi = ok_hi * 0xFFu;  // 0x01 -> 0xFF per counting row
+    auto ld = [&](uint32_t col_off) {
+      uint2 v = *reinterpret_cast<const uint2*>(tile + col_off);
+      if (SLOW) { v.x &= keep_lo; v.y &= keep_hi; }  // a 0xFF state would carry into its neighbours' bytes below
+      return v;
+    };
+    const uint32_t* rec = prog + rec0;
+    for (uint32_t k = 0; k < n_my; k += 2u) {
+      // records: [col offset, first counter word-row, byte mask of the node's power-of-two bin span, n_par, (parent col
+      // offset, multiplier) x 3, ...]; uniform across the warp (broadcast loads).  Two nodes per trip.
+      const uint4 A0 = *reinterpret_cast<const uint4*>(rec), A1 = *reinterpret_cast<const uint4*>(rec + 4),
+                  A2 = *reinterpret_cast<const uint4*>(rec + 8);
+      const uint32_t a_words = MORE ? ((ROWS_REC + (A0.w > 3u ? 2u * (A0.w - 3u) : 0u) + 3u) & ~3u) : ROWS_REC;
+      const uint32_t* recb = rec + a_words;
+      const uint4 B0 = *reinterpret_cast<const uint4*>(recb), B1 = *reinterpret_cast<const uint4*>(recb + 4),
+                  B2 = *reinterpret_cast<const uint4*>(recb + 8);
+      const uint32_t b_words = MORE ? ((ROWS_REC + (B0.w > 3u ? 2u * (B0.w - 3u) : 0u) + 3u) & ~3u) : ROWS_REC;
+      uint2 ia = ld(A0.x), ib = ld(B0.x);
+      {
+        const uint2 pa = ld(A1.x), pb = ld(B1.x);  // absent parents: multiplier 0 (column 0 is always readable)
+        ia.x += A1.y * pa.x; ia.y += A1.y * pa.y;
+        ib.x += B1.y * pb.x; ib.y += B1.y * pb.y;
+      }
+      if ((A0.w | B0.w) > 1u) {
+        const uint2 pa1 = ld(A1.z), pa2 = ld(A2.x), pb1 = ld(B1.z), pb2 = ld(B2.x);
+        ia.x += A1.w * pa1.x + A2.y * pa2.x; ia.y += A1.w * pa1.y + A2.y * pa2.y;
+        ib.x += B1.w * pb1.x + B2.y * pb2.x; ib.y += B1.w * pb1.y + B2.y * pb2.y;
+      }
+      if (MORE) {
+        for (uint32_t e = 3; e < A0.w; ++e) {
+          const uint2 pp = ld(rec[ROWS_REC + 2 * (e - 3)]);
+          const uint32_t m = rec[ROWS_REC + 2 * (e - 3) + 1];
+          ia.x += m * pp.x; ia.y += m * pp.y;
+        }
+        for (uint32_t e = 3; e < B0.w; ++e) {
+          const uint2 pp = ld(recb[ROWS_REC + 2 * (e - 3)]);
+          const uint32_t m = recb[ROWS_REC + 2 * (e - 3) + 1];
+          ib.x += m * pp.x; ib.y += m * pp.y;
+        }
+      }
+      // byte offset of every row's counter inside my lane column: (bin >> 2) * 128 + (bin & 3), two rows per 32-bit word
+      // (16-bit fields); bins are first masked to the node's power-of-two span
+      const uint32_t al = ia.x & A0.z, ah = ia.y & A0.z, bl = ib.x & B0.z, bh = ib.y & B0.z;
+#define BN_F_EVEN(x) ((((x) & 0x00FC00FCu) << 5) | ((x) & 0x00030003u))
+#define BN_F_ODD(x) ((((x) >> 3) & 0x1F801F80u) | (((x) >> 8) & 0x00030003u))
+      const uint32_t a02 = BN_F_EVEN(al), a13 = BN_F_ODD(al), a46 = BN_F_EVEN(ah), a57 = BN_F_ODD(ah);
+      const uint32_t b02 = BN_F_EVEN(bl), b13 = BN_F_ODD(bl), b46 = BN_F_EVEN(bh), b57 = BN_F_ODD(bh);
+#undef BN_F_EVEN
+#undef BN_F_ODD
+      unsigned char* ha = reinterpret_cast<unsigned char*>(hist) + A0.y * 128u + 4u * lane;
+      unsigned char* hb = reinterpret_cast<unsigned char*>(hist) + B0.y * 128u + 4u * lane;
+      // lane-private bank: conflict free, no atomics.  The updates of one node stay in program order (two rows may hit
+      // the same counter); the two nodes' chains are interleaved (they never share a counter).
+#define BN_ROW2(FA, FB, HALF, J)                                                              \
+      {                                                                                       \
+        unsigned char* ca = ha + ((HALF) ? ((FA) >> 16) : ((FA) & 0xFFFFu));                  \
+        unsigned char* cb = hb + ((HALF) ? ((FB) >> 16) : ((FB) & 0xFFFFu));                  \
+        const uint32_t inc = SLOW ? ((((J) < 4 ? ok_lo : ok_hi) >> (8u * ((J) & 3u))) & 1u) : 1u; \
+        const uint32_t va = *ca, vb = *cb;                                                    \
+        *ca = (unsigned char)(va + inc);                                                      \
+        *cb = (unsigned char)(vb + inc);                                                      \
+      }
+      BN_ROW2(a02, b02, 0, 0) BN_ROW2(a13, b13, 0, 1) BN_ROW2(a02, b02, 1, 2) BN_ROW2(a13, b13, 1, 3)
+      BN_ROW2(a46, b46, 0, 4) BN_ROW2(a57, b57, 0, 5) BN_ROW2(a46, b46, 1, 6) BN_ROW2(a57, b57, 1, 7)
+#undef BN_ROW2
+      rec = recb + b_words;
+    }
+  };
+  // rows of this tile that count: all (fast path) unless the tile is ragged or carries 0xFF marks in node 0's column
+  auto run_tile = [&](const unsigned char* tile, uint32_t rows) {
+    const uint2 w0 = *reinterpret_cast<const uint2*>(tile);
+    const bool slow = __any_sync(0xffffffffu, (has_ff_byte(w0.x) | has_ff_byte(w0.y)) != 0u) || rows < ROWS_TR;
+    if (!slow) {
+      process(tile, std::false_type{}, 0x01010101u, 0x01010101u);
+    } else {
+      uint32_t ok_lo = 0u, ok_hi = 0u;
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) {
+        const uint32_t st0 = ((j < 4u ? w0.x : w0.y) >> (8u * (j & 3u))) & 0xffu;
+        const uint32_t ok = (8u * lane + j < rows && st0 != 0xFFu) ? 1u : 0u;
+        if (j < 4u) ok_lo |= ok << (8u * j); else ok_hi |= ok << (8u * (j - 4u));
+      }
+      process(tile, std::true_type{}, ok_lo, ok_hi);
+    }
+  };
+
+  uint32_t it = 0, since_fold = 0;
+  for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const uint64_t r0 = t * ROWS_TR;
+    const uint32_t rows = (uint32_t)(a.n_rows - r0 < ROWS_TR ? a.n_rows - r0 : ROWS_TR);
+    if (TMA) {
+      const uint32_t st = it & 1u;
+      mbar_wait(full0 + 8u * st, (it >> 1) & 1u);  // the tile has landed
+      run_tile(tiles + st * tile_bytes + 8u * lane, rows);
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8u * st) : "memory");
+    } else {
+      __syncthreads();  // everybody is done with the (single) buffer
+      for (uint32_t i = 0; i < a.n_nodes; ++i)
+        for (uint32_t r = tid; r < ROWS_TR; r += T)
+          tiles[i * ROWS_TR + r] = r < rows ? a.data[(uint64_t)i * a.pitch + r0 + r] : (unsigned char)0;
+      __syncthreads();
+      run_tile(tiles + 8u * lane, rows);
+    }
+    if (++since_fold == ROWS_FLUSH) {
+      fold();
+      since_fold = 0;
+    }
+  }
+  fold();
+  // totals -> global table: each warp flushes the counter word-rows it owns
+  for (uint32_t r = my_row0 + lane; r < my_row0 + my_rows; r += 32u) {
+    const uint32_t ro = a.row_out[r], g = ro & 0x3FFFFFFFu, nv = (ro >> 30) + 1u;
+    for (uint32_t f = 0; f < nv; ++f) {
+      const uint32_t c = tot[r * 4u + f];
+      if (c) atomicAdd(&a.out[g + f], (unsigned long long)c);
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Plan + launch of the row-lane kernel, one launch per group of consecutive nodes whose counters fit shared memory
+// together; returns BN_OK with *handled = false when the network does not qualify (the node-lane kernel takes over).
+static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch,
+                                      unsigned long long* out_dev, bool* handled) {
+  *handled = false;
+  const DevProps& dp = dev_props(net->device);
+  cudaStream_t s = tl_stream;
+  const int n = net->n;
+  const size_t budget = (size_t)dp.max_smem_optin - 1024;
+  if (net->cpt_off[n] >= (int64_t)(1u << 30) || n > 4096) return BN_OK;
+  for (int i = 0; i < n; ++i)
+    if (net->cpt_off[i + 1] - net->cpt_off[i] > 256) return BN_OK;  // a bin index must fit one byte
+  if (getenv("BN_STATS_NODELANES")) return BN_OK;
+  bool more = false;
+  for (int i = 0; i < n; ++i) more = more || (net->par_ptr[i + 1] - net->par_ptr[i] > 3);
+  // TMA needs a 16-byte aligned table and pitch, and 32-bit coordinates
+  const bool tma = pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(data_dev) % 16) == 0 && n_rows < (1ull << 32) &&
+                   pitch < (1ull << 40) && encode_tiled() != nullptr && !getenv("BN_STATS_NO_TMA");
+  const uint32_t n_boxes = (uint32_t)((n + 255) / 256), box_nodes = (uint32_t)((n + n_boxes - 1) / n_boxes);
+  const size_t tile_b = (size_t)(tma ? box_nodes * n_boxes : (uint32_t)n) * ROWS_TR;
+  const size_t tiles_b = tile_b * (tma ? 2 : 1);
+  auto wrows_of = [&](int i) { return (uint32_t)((net->cpt_off[i + 1] - net->cpt_off[i] + 3) / 4); };
+  auto rec_words_of = [&](int i) {
+    const uint32_t np = (uint32_t)(net->par_ptr[i + 1] - net->par_ptr[i]);
+    const uint32_t w = ROWS_REC + (np > 3 ? 2 * (np - 3) : 0);
+    return more ? ((w + 3u) & ~3u) : ROWS_REC;
+  };
+  const uint64_t n_tiles = (n_rows + ROWS_TR - 1) / ROWS_TR;
+  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)dp.sm_count);
+  BN_REQUIRE(n_rows / (uint64_t)grid < (1ull << 31), BN_UNSUPPORTED, "too many rows per CTA for the 32-bit CTA totals");
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (tma) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_rows, (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {ROWS_TR, box_nodes};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(data_dev), gdim, gstride, box,
+                                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BN_REQUIRE(r == CUDA_SUCCESS, BN_CUDA_ERR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+  int first = 0;
+  while (first < n) {
+    size_t used = tiles_b + (ROWS_MAX_WARPS * 3 + 4) * 4 + 512 + ROWS_GUARD * 128 + 2 * ROWS_REC * 4;
+    uint32_t wrows = 0;
+    int last = first;
+    while (last < n) {
+      const size_t need = (size_t)wrows_of(last) * 144 + (size_t)rec_words_of(last) * 4 + 2 * ROWS_REC * 4;
+      if (used + need > budget || wrows + wrows_of(last) + ROWS_GUARD > 65535u) break;
+      used += need;
+      wrows += wrows_of(last);
+      ++last;
+    }
+    if (last == first) return first == 0 ? BN_OK : BN_UNSUPPORTED;  // a single node does not fit beside the tiles
+    // deal the group's nodes to warps, longest processing time first.  Warps cost issue slots per tile whether or not
+    // they are busy, and every warp waits for the slowest one sooner or later: pick the warp count that minimises
+    // (warps x longest warp), preferring enough warps to hide the counter read-modify-write latency.
+    const int m = last - first;
+    std::vector<int> order(m);
+    for (int j = 0; j < m; ++j) order[j] = first + j;
+    auto cost = [&](int i) { return 34 + 4 * std::min(3, net->par_ptr[i + 1] - net->par_ptr[i] > 1 ? 3 : 1); };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost(x) > cost(y); });
+    static const int warps_env = getenv("BN_STATS_WARPS") ? atoi(getenv("BN_STATS_WARPS")) : 0;
+    auto deal = [&](int W, std::vector<std::vector<int>>* out) {  // -> longest warp (nodes are walked in pairs)
+      std::vector<int> load(W, 0);
+      std::vector<std::vector<int>> mine(W);
+      for (int i : order) {
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[w] += cost(i);
+        mine[w].push_back(i);
+      }
+      int longest = 0;
+      for (int w = 0; w < W; ++w) {
+        int l = 40;  // per-tile overhead of a warp
+        for (size_t j = 0; j < mine[w].size(); j += 2) l += 2 * cost(mine[w][j]);  // an odd node drags a dummy partner
+        longest = std::max(longest, l);
+      }
+      if (out) out->swap(mine);
+      return longest;
+    };
+    int best_w = 1;
+    double best_t = 1e300;
+    for (int W = std::min<int>(ROWS_MAX_WARPS, m); W >= 1; --W) {
+      if (warps_env && W != std::min(warps_env, std::min<int>(ROWS_MAX_WARPS, m))) continue;
+      double tm = (double)W * deal(W, nullptr);
+      if (W < 16) tm *= 16.0 / W;  // too few warps leave the schedulers idle
+      if (tm < best_t) { best_t = tm; best_w = W; }
+    }
+    const int W = best_w;
+    std::vector<std::vector<int>> mine;
+    deal(W, &mine);
+    uint32_t total_rows = 0;
+    for (int i = first; i < last; ++i) total_rows += wrows_of(i);
+    std::vector<uint32_t> prog((3 * (size_t)W + 3) / 4 * 4, 0), row_out;  // header, padded: records are read as 128-bit words
+    uint32_t row = 0;
+    for (int w = 0; w < W; ++w) {
+      prog[3 * w] = (uint32_t)prog.size();
+      const uint32_t row_begin = row;
+      // pair nodes with the same shape (<= 1 parent | more): a pair takes the longer path together
+      std::stable_sort(mine[w].begin(), mine[w].end(), [&](int x, int y) {
+        return (net->par_ptr[x + 1] - net->par_ptr[x] > 1) > (net->par_ptr[y + 1] - net->par_ptr[y] > 1);
+      });
+      for (int i : mine[w]) {
+        const uint32_t np = (uint32_t)(net->par_ptr[i + 1] - net->par_ptr[i]);
+        const size_t at = prog.size();
+        prog.resize(at + rec_words_of(i), 0);
+        prog[at + 0] = (uint32_t)i * ROWS_TR;
+        prog[at + 1] = row;
+        {
+          uint32_t span = 4;  // power of two >= the node's counter bytes (4 per word-row)
+          while (span < 4 * wrows_of(i)) span <<= 1;
+          prog[at + 2] = (span - 1) * 0x01010101u;
+        }
+        prog[at + 3] = np;
+        int64_t stride = net->card[i];
+        for (uint32_t e = 0; e < np; ++e) {
+          const uint32_t col = (uint32_t)net->par_idx[net->par_ptr[i] + e] * ROWS_TR;
+          const size_t slot = e < 3 ? at + 4 + 2 * e : at + ROWS_REC + 2 * (e - 3);
+          prog[slot] = col;
+          prog[slot + 1] = (uint32_t)stride;  // < 256: the family has <= 256 bins
+          stride *= net->card[net->par_idx[net->par_ptr[i] + e]];
+        }
+        const uint32_t B = (uint32_t)(net->cpt_off[i + 1] - net->cpt_off[i]);
+        for (uint32_t r = 0; r < wrows_of(i); ++r)
+          row_out.push_back((uint32_t)(net->cpt_off[i] + 4 * r) | ((std::min(4u, B - 4 * r) - 1u) << 30));
+        row += wrows_of(i);
+      }
+      uint32_t n_rec = (uint32_t)mine[w].size();
+      if (n_rec % 2) {  // odd: a dummy partner that counts into the guard rows (column 0, mask 0, no parents)
+        const size_t at = prog.size();
+        prog.resize(at + ROWS_REC, 0);
+        prog[at + 1] = total_rows;
+        ++n_rec;
+      }
+      prog[3 * w + 1] = n_rec;
+      prog[3 * w + 2] = row_begin | ((row - row_begin) << 16);
+    }
+    while (prog.size() % 4) prog.push_back(0);
+    RowArgs a{};
+    a.data = data_dev;
+    a.n_rows = n_rows;
+    a.pitch = pitch;
+    a.prog_words = (uint32_t)prog.size();
+    a.n_nodes = (uint32_t)n;
+    a.n_warps = (uint32_t)W;
+    a.n_wrows = row;
+    a.box_nodes = box_nodes;
+    a.n_boxes = n_boxes;
+    a.out = out_dev;
+    TmpBuf<uint32_t> stage;  // per call, freed in stream order after the kernel
+    BN_CUDA_TRY(stage.alloc(prog.size() + row_out.size()));
+    BN_CUDA_TRY(cudaMemcpyAsync(stage.p, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice, s));
+    BN_CUDA_TRY(cudaMemcpyAsync(stage.p + prog.size(), row_out.data(), row_out.size() * 4, cudaMemcpyHostToDevice, s));
+    a.prog = stage.p;
+    a.row_out = stage.p + prog.size();
+    const size_t smem = (((size_t)a.prog_words + 31) & ~(size_t)31) * 4 + ((size_t)row + ROWS_GUARD) * 128 +
+                        (((size_t)row * 4 + 31) & ~(size_t)31) * 4 + tiles_b;
+    void (*kern)(const RowArgs, const CUtensorMap) =
+        tma ? (more ? statistics_rows_kernel<true, true> : statistics_rows_kernel<false, true>)
+            : (more ? statistics_rows_kernel<true, false> : statistics_rows_kernel<false, false>);
+    BN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin - 1024));
+    BN_REQUIRE(smem <= budget, BN_CUDA_ERR, "statistics plan exceeds shared memory (%zu bytes)", smem);
+    kern<<<grid, (W + (tma ? 1 : 0)) * 32, smem, s>>>(a, tmap);
+    count_launch();
+    BN_CUDA_TRY(cudaGetLastError());
+    first = last;
+  }
+  *handled = true;
+  return BN_OK;
+}
+
+static int32_t statistics_launch(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch,
+                                 unsigned long long* out_dev) {
+  const int n = net->n;
+  const int64_t n_bins = net->cpt_off[n];
+  BN_REQUIRE(n_bins < (int64_t)0x7fffffff, BN_UNSUPPORTED, "count table too large (%lld entries)", (long long)n_bins);
+  BN_REQUIRE(pitch >= n_rows, BN_BAD_ARG, "pitch (%llu) smaller than n_rows (%llu)", (unsigned long long)pitch,
+             (unsigned long long)n_rows);
+  BN_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)n_bins * sizeof(unsigned long long), tl_stream));
+  if (n_rows == 0 || n == 0) return BN_OK;
+  bool handled = false;
+  BN_TRY(statistics_launch_rows(net, data_dev, n_rows, pitch, out_dev, &handled));
+  if (handled) return BN_OK;
+  return statistics_launch_nodelanes(net, data_dev, n_rows, pitch, out_dev);
 }
 
 
