@@ -199,6 +199,10 @@ int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>&
 // Internal to variable elimination, whose kernels only read their operands; never handed to callers, never normalised
 // in place.  The view must not outlive the net.
 int32_t factor_view_of_cpd(Net* net, int32_t node, bn_factor_t* out);
+// factor_stream.cu: one-shot streaming kernels; *handled = false -> nothing launched, use the contraction kernel
+int32_t sum_segmented(const double* in, const std::vector<int32_t>& card, const std::vector<char>& summed, double* out,
+                      bool* handled);
+int32_t push_duplicate(const double* in, long long n_in, int32_t length, double* out, bool* handled);
 // permute.cu: tiled transpose behind bn_factor_permutedims; *handled = false -> nothing launched, use the contraction
 int32_t permute_tiled(int device, const double* in, const std::vector<int32_t>& card, const int32_t* perm, double* out,
                       bool* handled);

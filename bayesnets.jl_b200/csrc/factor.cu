@@ -723,6 +723,15 @@ static int32_t eliminate_impl(const std::vector<Factor*>& fs, const int32_t* sum
   }
   Factor* o = nullptr;
   BN_TRY(new_factor(od, oc, device, &o));
+  if (fs.size() == 1 && !sd.empty()) {  // sum(phi, dims) of one factor: the one-shot streaming kernel (factor_stream.cu)
+    std::vector<char> flag(d.size(), 0);
+    for (size_t i = 0; i < d.size(); ++i)
+      for (int j = 0; j < n_sum; ++j) flag[i] = flag[i] || (sum_dims[j] == d[i]);
+    bool handled = false;
+    int32_t rc = sum_segmented(fs[0]->data.p, c, flag, o->data.p, &handled);
+    if (rc != BN_OK) { delete o; return rc; }
+    if (handled) { *out = o; return BN_OK; }
+  }
   // operand order: largest first so the leading (register-offset, vectorised) operand is the big one;
   // the product value itself is order independent only up to commutativity, so keep the fold order
   // for the multiplication and merely choose which operand drives the vector mode.
@@ -1029,7 +1038,9 @@ int32_t bn_factor_push(bn_factor_t h, int32_t dim, int32_t length, bn_factor_t* 
   BN_CUDA_TRY(cudaSetDevice(f->device));
   Factor* o = nullptr;
   BN_TRY(new_factor(od, oc, f->device, &o));
-  int32_t rc = contract(f->device, {Operand{f->data.p, f->dims, f->card}}, od, oc, {}, {}, o->data.p);
+  bool handled = false;  // the table repeated `length` times: one load, `length` stores (factor_stream.cu)
+  int32_t rc = push_duplicate(f->data.p, f->len, length, o->data.p, &handled);
+  if (rc == BN_OK && !handled) rc = contract(f->device, {Operand{f->data.p, f->dims, f->card}}, od, oc, {}, {}, o->data.p);
   if (rc != BN_OK) { delete o; return rc; }
   *out = register_factor(o);
   return BN_OK;

@@ -363,6 +363,55 @@ def test_large_streaming_shapes_bit_exact(bn, seed):
         assert np.array_equal(got.potential, ref.potential), h
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_sum_streaming_kernel_shapes_bit_exact(bn, seed, monkeypatch):
+    """csrc/factor_stream.cu: sum(phi, dims) of one factor (factors_dims.jl:60-85,100).  Mixed-radix shapes that hit
+    both modes (innermost dim kept -> 128-bit columns; innermost dim summed -> output pairs), 1..4 summed dims up to 16
+    joint states, odd segments that must fall back, sizes that leave a ragged last CTA.  Equal to the oracle bit for
+    bit, and to the contraction kernel (BN_FACTOR_NO_STREAM)."""
+    rng = np.random.default_rng(4200 + seed)
+    nd = int(rng.integers(3, 12))
+    cards = [int(rng.choice([2, 2, 2, 3, 4, 5, 6])) for _ in range(nd)]
+    while np.prod(cards) > (1 << 21):
+        cards[int(rng.integers(0, nd))] = 2 if np.prod(cards) < (1 << 24) else 1
+    if seed % 2 == 0:
+        cards[0] = int(rng.choice([2, 4, 6]))  # even innermost dim: vector columns or pairs
+    names = [f"ss{seed}_{i}" for i in range(nd)]
+    A = rng.random(cards)
+    fa, na = F(bn, names, A), NpFactor(list(range(nd)), A)
+    picks = [[0], [nd - 1], [nd // 2], [0, 1], [0, nd - 1], [1, nd - 2]]
+    for _ in range(4):
+        picks.append(sorted(int(x) for x in rng.choice(nd, size=int(rng.integers(1, min(5, nd))), replace=False)))
+    for sd in picks:
+        sd = sorted(set(sd))
+        if len(sd) == nd:
+            continue
+        ref = na.sum(sd)
+        n0 = bn.launch_count()
+        got = fa.sum([names[i] for i in sd])
+        assert bn.launch_count() > n0
+        assert got.dimensions == [names[i] for i in ref.dimensions]
+        assert np.array_equal(got.potential, ref.potential), (cards, sd)
+        monkeypatch.setenv("BN_FACTOR_NO_STREAM", "1")
+        gen = fa.sum([names[i] for i in sd])
+        monkeypatch.delenv("BN_FACTOR_NO_STREAM")
+        assert np.array_equal(gen.potential, got.potential), (cards, sd)
+
+
+def test_push_streaming_kernel_vs_oracle(bn, monkeypatch):
+    """push!(phi, dim, length) (factors_main.jl:148-158) through the duplicate kernel: even and odd table lengths (odd
+    falls back to the contraction), lengths 1..5, a ragged last CTA."""
+    rng = np.random.default_rng(77)
+    for i, cards in enumerate([[2] * 15, [3, 5, 7, 11], [4, 3, 1001], [2, 3, 5, 7, 9, 4], [6]]):
+        for length in (1, 2, 5):
+            names = [f"pu{i}_{length}_{j}" for j in range(len(cards))]
+            A = rng.random(cards)
+            f, o = F(bn, names, A), NpFactor(names, np.asfortranarray(A.copy()))
+            f.push_("new", length)
+            o2 = o.push("new", length)
+            assert f.dimensions == o2.dimensions and np.array_equal(f.potential, o2.potential)
+
+
 # ------------------------------------------------------------------- the rest of the Factor algebra (csrc/factor_ops.cu)
 def test_broadcast_reference_suite(bn):
     """test/test_factors.jl:87-105, same assertions."""
