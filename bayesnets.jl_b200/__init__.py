@@ -10,7 +10,7 @@ image; julia/ holds the equivalent `ccall` glue a BayesNets.jl maintainer would 
 There is NO CPU fallback: importing works anywhere, but any compute call raises unless libbn_cuda.so is
 built and a B200 is visible.
 """
-from ._lib import (BNCudaError, DeviceBuffer, DimensionMismatch, EXPORTS, LIB_PATH, device_count, device_count_or_zero, launch_count,  # noqa: F401
+from ._lib import (BNCudaError, DeviceBuffer, DimensionMismatch, EXPORTS, LIB_PATH, device_count, device_count_or_zero, launch_count, pool_trim,  # noqa: F401
                    set_gibbs_mode, set_lw_mode, set_stream, spec_cache_stats, synchronize)
 from .bayes_net import (Assignment, BayesNet, CategoricalCPD, DiscreteBayesNet, DiscreteCPD, consistent,  # noqa: F401
                         get_asia_bn, get_sat_fail_bn, get_sprinkler_bn, rand_bn_inference, rand_cpd,

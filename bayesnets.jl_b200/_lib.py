@@ -38,6 +38,7 @@ _SIGS = {
     "bn_device_count": (C.c_int32, [i32p]),
     "bn_set_stream": (C.c_int32, [C.c_void_p]),
     "bn_launch_count": (C.c_uint64, []),
+    "bn_pool_trim": (C.c_int32, [C.POINTER(C.c_uint64)]),
     "bn_synchronize": (C.c_int32, []),
     "bn_dev_alloc": (C.c_int32, [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bn_dev_free": (C.c_int32, [C.c_int32, C.c_void_p]),
@@ -178,6 +179,13 @@ def set_gibbs_mode(mode: str = "auto") -> None:
 
 def launch_count() -> int:
     return int(lib().bn_launch_count())
+
+
+def pool_trim() -> int:
+    """Give the device memory parked by freed factors / temporaries back to the driver; returns the bytes released."""
+    n = C.c_uint64(0)
+    check(lib().bn_pool_trim(C.byref(n)))
+    return int(n.value)
 
 
 class DeviceBuffer:

@@ -90,6 +90,14 @@ struct DevBuf {
 // frees 2^20..2^27-entry intermediates back to back; the default mempool keeps them cached (release
 // threshold = max), so after warm-up an allocation is a pointer bump and frees never synchronise the device.
 void ensure_pool(int device);
+// Block cache in front of cudaMallocAsync / cudaFreeAsync (core.cu).  A block released on stream s is parked under
+// (device, s, bytes) and handed to the next allocation of exactly that size on that stream without any driver call:
+// stream order makes the reuse safe, and back-to-back factor ops lose no time to the stream-ordered free
+// (measured: 1.7 us per op on 35 us kernels, tools/probe/alloc_gap.cu).  Bounded by BN_POOL_CACHE_MB (default 16384);
+// beyond it, and when the driver reports out-of-memory, blocks go back to the driver pool.
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t s, int* device_out);
+void pool_free(void* p, size_t bytes, cudaStream_t s, int device);
+size_t pool_trim();  // returns the bytes that were parked
 template <typename T>
 struct PoolBuf {
   T* p = nullptr;
@@ -97,12 +105,14 @@ struct PoolBuf {
   bool owns = true;  // false: a read-only view of memory owned elsewhere (borrow)
   cudaStream_t s = nullptr;  // the stream the allocation was made on; the free is ordered on the same stream, so a
                              // finalizer running after bn_set_stream() switched streams cannot free under a kernel
+  int device = 0;
+  size_t bytes = 0;
   PoolBuf() = default;
   PoolBuf(const PoolBuf&) = delete;
   PoolBuf& operator=(const PoolBuf&) = delete;
   ~PoolBuf() { release(); }
   void release() {
-    if (p && owns) cudaFreeAsync(p, s);
+    if (p && owns) pool_free(p, bytes, s, device);
     p = nullptr; n = 0; owns = true;
   }
   void borrow(T* ptr, size_t count) {
@@ -113,7 +123,8 @@ struct PoolBuf {
     release();
     n = count;
     s = tl_stream;
-    return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), s);
+    bytes = (count ? count : 1) * sizeof(T);
+    return pool_alloc((void**)&p, bytes, s, &device);
   }
   cudaError_t upload(const T* host, size_t count, cudaStream_t st) {
     cudaError_t e = alloc(count);

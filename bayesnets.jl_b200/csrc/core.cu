@@ -44,6 +44,77 @@ void ensure_pool(int device) {
   done[device] = true;
 }
 
+namespace {
+struct BlockKey {
+  int device;
+  cudaStream_t s;
+  size_t bytes;
+  bool operator==(const BlockKey& o) const { return device == o.device && s == o.s && bytes == o.bytes; }
+};
+struct BlockKeyHash {
+  size_t operator()(const BlockKey& k) const {
+    return std::hash<size_t>()(k.bytes) ^ (std::hash<const void*>()((const void*)k.s) * 31u) ^ ((size_t)k.device << 56);
+  }
+};
+std::mutex g_cache_mu;
+std::unordered_map<BlockKey, std::vector<void*>, BlockKeyHash> g_cache;
+size_t g_cache_bytes = 0;
+size_t cache_cap() {
+  static const size_t cap = (getenv("BN_POOL_CACHE_MB") ? (size_t)atoll(getenv("BN_POOL_CACHE_MB")) : (size_t)16384) << 20;
+  return cap;
+}
+}  // namespace
+
+size_t pool_trim() {
+  std::unordered_map<BlockKey, std::vector<void*>, BlockKeyHash> take;
+  size_t parked = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    take.swap(g_cache);
+    parked = g_cache_bytes;
+    g_cache_bytes = 0;
+  }
+  for (auto& kv : take)  // cudaFree (synchronising) rather than cudaFreeAsync: the stream a block was parked under may be gone
+    for (void* q : kv.second) cudaFree(q);
+  return parked;
+}
+
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t s, int* device_out) {
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess) return e;
+  *device_out = device;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache.find(BlockKey{device, s, bytes});
+    if (it != g_cache.end() && !it->second.empty()) {
+      *p = it->second.back();
+      it->second.pop_back();
+      g_cache_bytes -= bytes;
+      return cudaSuccess;
+    }
+  }
+  e = cudaMallocAsync(p, bytes, s);
+  if (e == cudaErrorMemoryAllocation) {  // give the parked blocks back to the driver pool and retry once
+    cudaGetLastError();
+    pool_trim();
+    e = cudaMallocAsync(p, bytes, s);
+  }
+  return e;
+}
+
+void pool_free(void* p, size_t bytes, cudaStream_t s, int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache_bytes + bytes <= cache_cap()) {
+      g_cache[BlockKey{device, s, bytes}].push_back(p);
+      g_cache_bytes += bytes;
+      return;
+    }
+  }
+  cudaFreeAsync(p, s);
+}
+
 Net* get_net(bn_net_t h) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_nets.find(h);
@@ -212,6 +283,12 @@ uint64_t bn_launch_count(void) { return bn::g_launches.load(); }
 
 int32_t bn_synchronize(void) {
   BN_CUDA_TRY(cudaStreamSynchronize(bn::tl_stream));
+  return BN_OK;
+}
+
+int32_t bn_pool_trim(uint64_t* out_bytes) {
+  const size_t parked = bn::pool_trim();
+  if (out_bytes) *out_bytes = (uint64_t)parked;
   return BN_OK;
 }
 

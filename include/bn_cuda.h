@@ -76,6 +76,11 @@ uint64_t bn_launch_count(void);
 
 /* Wait for everything this host thread has enqueued on its current stream (the _dev entry points are asynchronous). */
 int32_t bn_synchronize(void);
+/* Device memory of freed factors / per-call temporaries is parked inside the library, keyed by (device, stream, size),
+ * and handed to the next allocation of that size on that stream without a driver call (at most BN_POOL_CACHE_MB MiB,
+ * default 16384; given back automatically when the driver reports out-of-memory).  bn_pool_trim returns all parked
+ * blocks to the driver now (synchronises the device); out_bytes (may be NULL) receives how many bytes were parked. */
+int32_t bn_pool_trim(uint64_t* out_bytes);
 
 /* ---- plain device buffers for callers without a CUDA array library (the Julia glue, the Python mirror): the *_dev
  *      entry points take their pointers.  Stream-ordered on the calling thread's current stream; bn_dev_download

@@ -54,6 +54,18 @@ set_lw_mode(mode::Symbol=:auto; prune::Bool=true) =
 set_gibbs_mode(mode::Symbol=:auto) =
     _bn_check(ccall((:bn_set_gibbs_mode, libbn_cuda), Int32, (Int32,), _KERNEL_MODES[mode]))
 
+"""
+    cuda_pool_trim() -> bytes
+
+Return the device memory that freed factors / per-call temporaries left parked inside the library to the CUDA driver
+(for callers that share the GPU with another allocator).
+"""
+function cuda_pool_trim()
+    n = Ref{UInt64}(0)
+    _bn_check(ccall((:bn_pool_trim, libbn_cuda), Int32, (Ref{UInt64},), n))
+    return Int(n[])
+end
+
 # Seeds: the reference draws fresh random numbers on every call (Julia's global RNG).  `seed = nothing` (the default
 # everywhere below) takes the next value of a process-wide counter; an explicit seed reproduces a call bit for bit.
 const _seed_counter = Ref{UInt64}(0)

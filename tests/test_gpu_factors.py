@@ -398,6 +398,81 @@ def test_sum_streaming_kernel_shapes_bit_exact(bn, seed, monkeypatch):
         assert np.array_equal(gen.potential, got.potential), (cards, sd)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_eliminate_big_times_small_bit_exact(bn, seed):
+    """The variable-elimination step sum(A * small..., dims) (src/Inference/exact.jl:27) where A spans every dim and the
+    small operands are contiguous stretches of A's dims plus the summed dims, in any operand order: innermost dim summed
+    / kept, 1-2 summed dims, mixed radix.  Equal to the oracle's left fold + sum bit for bit."""
+    rng = np.random.default_rng(7300 + seed)
+    nd = int(rng.integers(9, 15))
+    cards = [int(rng.choice([2, 4])) for _ in range(2)] + [int(rng.choice([2, 2, 2, 2, 3, 4])) for _ in range(nd - 2)]
+    while np.prod(cards) < (1 << 17):
+        i = int(rng.integers(2, nd))
+        cards[i] = 4
+        if all(x == 4 for x in cards[2:]):
+            break
+    while np.prod(cards) > (1 << 21):
+        cards[2 + int(np.argmax(cards[2:]))] = 2
+    assert (1 << 16) <= np.prod(cards) <= (1 << 21)
+    names = [f"se{seed}_{i}" for i in range(nd)]
+    ids = list(range(nd))
+    A = rng.random(cards)
+    fa, na = F(bn, names, A), NpFactor(ids, A)
+    for trial in range(4):
+        h = [0] if trial % 2 == 0 else [int(rng.integers(2, nd))]
+        if trial == 3 and nd > 6:
+            h = sorted({h[0], int(rng.integers(2, nd))})
+        smalls = []
+        for _ in range(int(rng.integers(1, 3))):
+            lo = int(rng.integers(1, nd - 2))
+            hi = int(rng.integers(lo + 1, min(nd, lo + 6) + 1))
+            run = [i for i in range(lo, hi) if i not in h]
+            if np.prod([cards[i] for i in run] + [1]) * np.prod([cards[i] for i in h]) > (1 << 16):
+                run = run[:3]
+            sd = h if rng.random() < 0.8 else h[:1]
+            dims = (sd + run) if rng.random() < 0.6 else (run + sd)
+            if not dims:
+                dims = list(h)
+            smalls.append((dims, rng.random([cards[i] for i in dims])))
+        order = [("A", None)] + [("S", i) for i in range(len(smalls))]
+        if rng.random() < 0.5:
+            order = order[1:2] + order[0:1] + order[2:]
+        fs, ref = [], None
+        for kind, i in order:
+            f, n = (fa, na) if kind == "A" else (F(bn, [names[j] for j in smalls[i][0]], smalls[i][1]),
+                                                 NpFactor(smalls[i][0], smalls[i][1]))
+            fs.append(f)
+            ref = n if ref is None else ref * n
+        ref = ref.sum(h)
+        got = bn.eliminate(fs, [names[i] for i in h])
+        assert got.dimensions == [names[i] for i in ref.dimensions]
+        assert np.array_equal(got.potential, ref.potential), (cards, h, [s[0] for s in smalls], order)
+
+
+def test_block_cache_reuse_and_trim(bn):
+    """Freed factor tables are parked inside the library and reused by the next allocation of the same size on the same
+    stream (csrc/core.cu pool_alloc / pool_free); bn_pool_trim hands them back to the driver.  Results are unaffected by
+    reuse: a chain of sums over recycled blocks equals the oracle's."""
+    import gc
+    rng = np.random.default_rng(5)
+    k = 18
+    names = [f"bc{i}" for i in range(k)]
+    A = rng.random((2,) * k)
+    fa, na = F(bn, names, A), NpFactor(list(range(k)), A)
+    bn.pool_trim()
+    for rep in range(3):  # same sizes every round: rounds 2 and 3 run entirely on recycled blocks
+        f, n = fa, na
+        for d in (0, 5, 9, 3):
+            f, n = f.sum([names[d]]), n.sum(d)
+            assert np.array_equal(f.potential, n.potential)
+        del f
+        gc.collect()
+    parked = bn.pool_trim()
+    assert parked >= 8 * (1 << (k - 1))  # at least the largest intermediate was parked
+    assert bn.pool_trim() == 0
+    assert np.array_equal(fa.sum([names[0]]).potential, na.sum(0).potential)
+
+
 def test_push_streaming_kernel_vs_oracle(bn, monkeypatch):
     """push!(phi, dim, length) (factors_main.jl:148-158) through the duplicate kernel: even and odd table lengths (odd
     falls back to the contraction), lengths 1..5, a ragged last CTA."""

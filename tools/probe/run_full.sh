@@ -1,0 +1,10 @@
+# full round-2 verification on one GPU: all GPU tests, smoke, bench (+ ncu launch list after the plain run)
+set -x
+mkdir -p gpurun_out
+TAG=${1:-r2f}
+(time timeout 1500 python -m pytest tests -m gpu -x -q) > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${TAG}_tests.log
+tail -5 gpurun_out/${TAG}_tests.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
+tail -2 gpurun_out/${TAG}_smoke.log
+(time timeout 900 python bench.py) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+tail -c 2500 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
