@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbn_cuda.so")
-SOURCES = ["core.cu", "sampling.cu", "specialize.cu", "gibbs.cu", "factor.cu", "exact.cu", "stats.cu", "loopy.cu", "factor_ops.cu", "permute.cu", "comm.cu", "factor_stream.cu"]
+SOURCES = ["core.cu", "sampling.cu", "specialize.cu", "gibbs.cu", "factor.cu", "exact.cu", "stats.cu", "loopy.cu", "factor_ops.cu", "permute.cu", "comm.cu", "factor_stream.cu", "gibbs_tables.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

@@ -147,13 +147,29 @@ void loopy_plan_free(LoopyPlan* p);
 
 struct Comm;  // comm.cu: NCCL communicator(s) + one stream per local device
 
+// gibbs_tables.cu: Markov-blanket conditionals as integer threshold tables (nodes with small blankets)
+struct GibbsTables {
+  uint32_t row_limit = 0;
+  std::vector<int64_t> tab_off;                 // per node: word offset of its table, -1 = keeps the fp64 conditional
+  std::vector<std::vector<int>> members;        // blanket members (ascending node index) ...
+  std::vector<std::vector<uint32_t>> strides;   // ... and their row strides
+  uint64_t words = 0;
+  DevBuf<uint32_t> tab;
+  bool has_never = false;  // some tabled row needs the unrepresentable threshold 2^32: the caller keeps the fp64 kernel
+};
+void gibbs_tables_free(GibbsTables* t);
+void gibbs_tables_layout(const Net& net, uint32_t row_limit, GibbsTables* g);
+int32_t gibbs_tables_get(Net* net, uint32_t row_limit, const GibbsTables** out);
+
 // Threading contract (include/bn_cuda.h): any number of host threads / streams may use one net concurrently.  Per-call
 // staging (programs, tables, evidence bytes, results) is allocated from the stream-ordered pool per call, never shared;
 // the only mutable per-net state is the kernel cache below, guarded by `mu`.
 struct Net {
   ~Net();
   LoopyPlan* loopy = nullptr;
-  std::mutex mu;  // guards spec_cache, spec_demand, loopy
+  GibbsTables* gtab = nullptr;
+  mutable std::atomic<int> gibbs_row_limit{-1};  // specialize.cu: blanket-table row limit, decided at first use
+  std::mutex mu;  // guards spec_cache, spec_demand, loopy, gtab
   std::unordered_map<std::string, SpecKernel*> spec_cache;
   std::unordered_map<std::string, double> spec_demand;  // work requested per key before its kernel was compiled
   // multi-GPU (comm.cu): a net created with bn_net_create_comm is the replica on the communicator's first local

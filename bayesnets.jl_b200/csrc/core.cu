@@ -182,6 +182,7 @@ int32_t new_factor(const std::vector<int32_t>& dims, const std::vector<int32_t>&
 Net::~Net() {
   spec_cache_clear(this);
   loopy_plan_free(loopy);
+  if (gtab) gibbs_tables_free(gtab);
   for (Net* p : peers) {
     cudaSetDevice(p->device);
     delete p;

@@ -751,13 +751,61 @@ __device__ __noinline__ void refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1, u32
                     r = (d & 2u) ? ((d & 1u) ? b3 : b2) : ((d & 1u) ? b1 : b0); ++d; }
 )BNSRC";
 
+// Rows a node's blanket may have to get a table.  The tables share L1 with the fp64 CPTs (what is left of the SM's 256 KB
+// after two CTAs' state columns, ~124 KB): measured on the C4 net (CPT 64 KB), 256 rows (61 KB of tables) is 8% faster
+// than no tables, 1024 rows (126 KB) 7% slower.  So: the largest power of two whose tables + CPTs stay within 128 KB.
+// BN_GIBBS_TABLE_ROWS overrides (0 = no tables).
+static uint32_t gibbs_table_row_limit(const Net& net) {
+  if (const char* e = getenv("BN_GIBBS_TABLE_ROWS")) return (uint32_t)atoi(e);
+  if (net.gibbs_row_limit >= 0) return (uint32_t)net.gibbs_row_limit;  // decided once per net (structure only)
+  const uint64_t budget = 128u << 10, cpt_bytes = (uint64_t)net.cpt_off[net.n] * 8;
+  uint32_t best = 0;
+  for (uint32_t lim = 16; lim <= 4096; lim *= 2) {
+    GibbsTables g;
+    gibbs_tables_layout(net, lim, &g);
+    if (cpt_bytes + g.words * 4 <= budget) best = lim; else break;
+  }
+  net.gibbs_row_limit = (int)best;
+  return best;
+}
+
+// Update of a node whose Markov-blanket conditional is tabulated (gibbs_tables.cu): row index from the blanket's states,
+// one vector load of the K-1 integer thresholds, pick = #{v : r >= R_v} -- the same decision as the fp64 scan for every r.
+static void emit_table_update(std::ostringstream& o, const Net& net, const GibbsTables& gt, int i, const char* ind) {
+  const int K = net.card[i];
+  const std::vector<int>& mb = gt.members[i];
+  o << ind << "const u32* tp = tab + (" << (uint32_t)gt.tab_off[i] << "u";
+  const uint32_t W = K <= 2 ? 1u : (K == 3 ? 2u : (K == 4 ? 4u : 8u));
+  for (size_t j = 0; j < mb.size(); ++j) o << " + (u32)st[" << mb[j] << " * NT] * " << gt.strides[i][j] * W << "u";
+  o << ");\n";
+  if (K == 2) {
+    o << ind << "const u32 pick = (u32)(r >= __ldg(tp));\n";
+  } else if (K == 3) {
+    o << ind << "const uint2 t = __ldg(reinterpret_cast<const uint2*>(tp));\n";
+    o << ind << "const u32 pick = (u32)(r >= t.x) + (u32)(r >= t.y);\n";
+  } else {
+    o << ind << "const uint4 t = __ldg(reinterpret_cast<const uint4*>(tp));\n";
+    o << ind << "u32 pick = (u32)(r >= t.x) + (u32)(r >= t.y) + (u32)(r >= t.z);\n";
+    if (K >= 5) {
+      o << ind << "pick += (u32)(r >= t.w);\n";
+      if (K >= 6) {
+        o << ind << "{ const uint4 t2 = __ldg(reinterpret_cast<const uint4*>(tp) + 1); pick += (u32)(r >= t2.x)";
+        if (K >= 7) o << " + (u32)(r >= t2.y)";
+        if (K >= 8) o << " + (u32)(r >= t2.z)";
+        o << "; }\n";
+      }
+    }
+  }
+}
+
 static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_mask, const int32_t* query,
                                     uint32_t n_query, const std::vector<int64_t>& qstride, uint32_t ncell, bool full,
-                                    int threads, int min_blocks, uint32_t* n_free_out) {
+                                    int threads, int min_blocks, uint32_t* n_free_out, const GibbsTables* gt = nullptr) {
   const int n = net.n;
   std::ostringstream o;
   uint32_t n_free = 0;
   for (int i = 0; i < n; ++i) n_free += ev_mask[i] ? 0 : 1;
+
   o << "// generated by libbn_cuda (specialize.cu): Gibbs " << (full ? "Full" : "Nodewise") << ", " << n << " nodes, "
     << n_free << " free, query cells " << ncell << "\n";
   o << kPrelude << kGibbsPrelude;
@@ -784,7 +832,7 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   o << "extern \"C\" __global__ void __launch_bounds__(NT, " << min_blocks << ") gibbs_spec(const double* __restrict__ cpt, "
        "const signed char* __restrict__ ev, u64 first_chain, u64 n_chains, u32 k0, u32 k1, long long burn_in, long long thin, "
        "long long total, double* __restrict__ out, double* __restrict__ cc, unsigned char* __restrict__ state_io, "
-       "int init_from_state) {\n";
+       "int init_from_state, const u32* __restrict__ tab) {\n";
   o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
   o << "  unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem_raw);\n";
   o << "  const u32 tid = threadIdx.x;\n";
@@ -832,6 +880,16 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   for (int i = 0; i < n; ++i) {
     if (ev_mask[i]) continue;
     const int K = net.card[i];
+    if (gt && gt->tab_off[i] >= 0) {
+      o << "      {  // node " << i << ": card " << K << ", tabulated conditional over " << gt->members[i].size() << " blanket nodes\n";
+      o << "        u32 r; NEXT_R(r);\n";
+      emit_table_update(o, net, *gt, i, "        ");
+      o << "        st[" << i << " * NT] = (unsigned char)pick;\n";
+      if (!full) o << "        TICK\n";
+      o << "      }\n";
+      if (++emitted % sync_every == 0) o << "      __syncthreads();  // keep the CTA's warps on the same code window\n";
+      continue;
+    }
     o << "      {  // node " << i << ": card " << K << ", " << (net.child_ptr[i + 1] - net.child_ptr[i]) << " children\n";
     o << "        u32 r; NEXT_R(r);\n";
     o << "        const double uu = ((double)r + 0.5) * (1.0 / 4294967296.0);\n";
@@ -1011,6 +1069,16 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
   for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
   key += std::string("|g") + (full ? "F" : "N") + std::to_string(T);
   for (uint32_t j = 0; j < n_query; ++j) key += "," + std::to_string(query[j]);
+  // tabulated conditionals for nodes with small Markov blankets (gibbs_tables.cu); BN_GIBBS_TABLE_ROWS=0 turns them off
+  const GibbsTables* gt = nullptr;
+  {
+    const uint32_t row_limit = gibbs_table_row_limit(*net);
+    if (row_limit > 0) {
+      BN_TRY(gibbs_tables_get(net, row_limit, &gt));
+      if (gt && (gt->words == 0 || gt->has_never)) gt = nullptr;
+      if (gt) key += "|t" + std::to_string(row_limit);
+    }
+  }
   SpecKernel* k = nullptr;
   static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e9);
   BN_TRY(acquire_kernel(net, key, must, (double)n_chains * (double)(burn_in + total * thin) * (full ? net->n : 1), thr,
@@ -1018,7 +1086,7 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
     uint32_t n_free = 0;
     int minb = 512 / T;  // <= 128 registers per thread
     if (const char* e = getenv("BN_GIBBS_MINB")) minb = atoi(e);
-    std::string src = gen_gibbs_source(*net, ev_mask, query, n_query, qstride, ncell, full, T, minb, &n_free);
+    std::string src = gen_gibbs_source(*net, ev_mask, query, n_query, qstride, ncell, full, T, minb, &n_free, gt);
     rq->entry = "gibbs_spec";
     rq->threads = T;
     rq->smem = smem;
@@ -1038,9 +1106,10 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
   const signed char* ev_dev = reinterpret_cast<const signed char*>(stage.p);
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   long long bi = burn_in, th = thin, tot = total;
+  const uint32_t* tab_dev = gt ? gt->tab.p : nullptr;
   void* args[] = {(void*)&cpt, (void*)&ev_dev, (void*)&first_chain, (void*)&n_chains, (void*)&k0, (void*)&k1, (void*)&bi,
                   (void*)&th, (void*)&tot, (void*)&out_dev, (void*)&chain_counts_dev, (void*)&state_dev,
-                  (void*)&init_from_state};
+                  (void*)&init_from_state, (void*)&tab_dev};
   const unsigned grid = (unsigned)((n_chains + k->threads - 1) / k->threads);
   CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)s, args, nullptr);
   if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(gibbs_spec)", r);
@@ -1150,8 +1219,11 @@ int32_t bn_gibbs_spec_source(int32_t n_nodes, const int32_t* card, const int32_t
   std::vector<char> ev_mask((size_t)n_nodes, 0);
   for (int i = 0; i < n_nodes; ++i) ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0;
   const int T = threads > 0 ? threads : 64;  // same launch bounds as launch_gibbs_specialized: <= 128 registers
+  GibbsTables gt;  // layout only (host): the source launch_gibbs_specialized generates when no tabled row needs 2^32
+  const uint32_t row_limit = gibbs_table_row_limit(net);
+  if (row_limit > 0) gibbs_tables_layout(net, row_limit, &gt);
   const std::string src = gen_gibbs_source(net, ev_mask, query, (uint32_t)n_query, qstride, (uint32_t)cells, full != 0,
-                                           T, std::max(1, 512 / T), nullptr);
+                                           T, std::max(1, 512 / T), nullptr, (row_limit > 0 && gt.words > 0) ? &gt : nullptr);
   *out_len = (int64_t)src.size();
   if (out_src && cap > 0) {
     const size_t m = src.size() < (size_t)(cap - 1) ? src.size() : (size_t)(cap - 1);

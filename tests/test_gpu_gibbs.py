@@ -61,6 +61,47 @@ def test_gibbs_state_resume_equals_oracle(bn, gibbs_mode, mode):
     assert im.state == {n: int(ost2[0, i]) + 1 for i, n in enumerate(lay.names)}
 
 
+@pytest.mark.parametrize("rows", ["0", "16", "4096"])
+@pytest.mark.parametrize("full", [False, True])
+def test_gibbs_tabulated_conditionals_equal_oracle(bn, gibbs_mode, monkeypatch, rows, full):
+    """csrc/gibbs_tables.cu: nodes with small Markov blankets draw from integer threshold tables (R_v = the smallest
+    32-bit draw for which the fp64 cumulative scan of src/Inference/gibbs.jl:36-50,110-112 passes state v).  Every row
+    limit -- no tables, a few nodes, every node of the 30-node net -- must walk the oracle's chains exactly."""
+    monkeypatch.setenv("BN_GIBBS_TABLE_ROWS", rows)
+    gibbs_mode("specialized")
+    net, lay, on, query, evidence = random_case(bn, 30, 11, 3)
+    cls = bn.GibbsSamplingFull if full else bn.GibbsSamplingNodewise
+    nsamples, burn, thin = (40, 10, 3) if full else (1200, 300, 7)
+    im = cls(nsamples=nsamples, burn_in=burn, thin=thin, n_chains=200, seed=21, keep_chain_counts=True)
+    counts = im.raw_counts(bn.InferenceState(net, query, evidence))
+    oc, ost, opc = capi.gibbs_infer(on, lay.evidence_vector(evidence), lay.query_indices(query), 200, nsamples, burn,
+                                    thin, full=full, seed=21, per_chain=True)
+    assert np.array_equal(counts, oc.ravel(order="F"))
+    assert np.array_equal(im.chain_states, ost)
+    assert np.array_equal(im.last_chain_counts, opc)
+
+
+def test_gibbs_tables_with_deterministic_cpds_fall_back(bn, gibbs_mode, monkeypatch):
+    """CPDs with exact zeros put the threshold 2^32 ("never") into some table rows; it does not fit 32 bits, so the
+    library keeps the fp64 kernel for such a net -- and still equals the oracle.  Cards 2..5 cover every row width."""
+    monkeypatch.setenv("BN_GIBBS_TABLE_ROWS", "4096")
+    gibbs_mode("specialized")
+    rng = np.random.default_rng(3)
+    nodes = [["a", [], [[0.2, 0.8]]],
+             ["b", ["a"], [[1.0, 0.0, 0.0], [0.0, 0.5, 0.5]]],
+             ["c", ["a", "b"], [list(x) for x in rng.dirichlet(np.ones(4), 6)]],
+             ["d", ["c"], [[0.0, 1.0, 0.0, 0.0, 0.0], [0.1, 0.2, 0.3, 0.2, 0.2], [0.0, 0.0, 0.0, 0.0, 1.0], [0.2] * 5]],
+             ["e", ["b", "d"], [list(x) for x in rng.dirichlet(np.ones(2), 15)]]]
+    net = make_mirror_net(bn, nodes)
+    lay = bn.flatten(net)
+    on = oracle_net_from_layout(lay)
+    query, evidence = ["c", "d"], {"e": 1}
+    im = bn.GibbsSamplingNodewise(nsamples=900, burn_in=100, thin=3, n_chains=128, seed=5)
+    counts = im.raw_counts(bn.InferenceState(net, query, evidence))
+    oc, ost = capi.gibbs_infer(on, lay.evidence_vector(evidence), lay.query_indices(query), 128, 900, 100, 3, seed=5)
+    assert np.array_equal(counts, oc.ravel(order="F")) and np.array_equal(im.chain_states, ost)
+
+
 def test_gibbs_large_cardinality_path(bn):
     """Nodes with more than 8 states take the chunked conditional path."""
     rng = np.random.default_rng(0)
