@@ -744,10 +744,12 @@ constexpr int GIBBS_SPEC_MAX_CARD = 8;
 // is not per-node arithmetic stays out of line or out of the loop: the Philox refill every 4th update is a call, the
 // thinned record step counts in registers (<= 16 query cells) or through one MATCH.ANY-grouped atomic per cell.
 static const char* kGibbsPrelude = R"BNSRC(
-__device__ __noinline__ void refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1, u32& b0, u32& b1, u32& b2, u32& b3) {
-  px(c0, c1, blk, 2u, k0, k1, b0, b1, b2, b3);
+__device__ __noinline__ uint4 refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1) {  // by value: the block stays in registers
+  uint4 b;
+  px(c0, c1, blk, 2u, k0, k1, b.x, b.y, b.z, b.w);
+  return b;
 }
-#define NEXT_R(r) { if ((d & 3u) == 0u) refill(c0, c1, d >> 2, k0, k1, b0, b1, b2, b3); \
+#define NEXT_R(r) { if ((d & 3u) == 0u) { const uint4 nb = refill(c0, c1, d >> 2, k0, k1); b0 = nb.x; b1 = nb.y; b2 = nb.z; b3 = nb.w; } \
                     r = (d & 2u) ? ((d & 1u) ? b3 : b2) : ((d & 1u) ? b1 : b0); ++d; }
 )BNSRC";
 
@@ -810,16 +812,19 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
     << n_free << " free, query cells " << ncell << "\n";
   o << kPrelude << kGibbsPrelude;
   o << "#define NT " << threads << "\n#define NN " << n << "u\n#define NCELL " << ncell << "u\n";
-  // record step: <= 16 query cells count in per-thread registers (no atomics until the end); larger tables group the
-  // warp's lanes by cell (MATCH.ANY) and the group leader adds the group size to the CTA's shared-memory bins
+  // record step, out of line (it runs once per `thin` updates, but inline it was ~35 instructions in EVERY node's
+  // block): <= 16 query cells count in per-thread shared-memory counters cnt[cell][thread] (no atomics until the end);
+  // larger tables group the warp's lanes by cell (MATCH.ANY) and the group leader adds the group size to the CTA's bins
   const bool reg_bins = ncell <= (uint32_t)SPEC_MAX_REG_CELLS;
   o << "#define CELL (0u";
   for (uint32_t j = 0; j < n_query; ++j) o << " + (u32)st[" << query[j] << " * NT] * " << (uint32_t)qstride[j] << "u";
   o << ")\n";
   if (reg_bins) {
-    o << "#define RECORD { const u32 cell = CELL;";
-    for (uint32_t c = 0; c < ncell; ++c) o << " n" << c << " += (u32)(cell == " << c << "u);";
-    o << " if (cc && live) cc[ci * NCELL + cell] += 1.0; }\n";
+    o << "__device__ __noinline__ void record(const unsigned char* st, u32* cnt, double* cc, u64 ci, bool live) {\n";
+    o << "  const u32 cell = CELL;\n";
+    o << "  cnt[cell * NT] += 1u;\n";
+    o << "  if (cc && live) cc[ci * NCELL + cell] += 1.0;\n}\n";
+    o << "#define RECORD record(st, cnt, cc, ci, live);\n";
   } else {
     o << "__device__ __noinline__ void record(const unsigned char* st, unsigned long long* bins, double* cc, u64 ci, bool live) {\n";
     o << "  const u32 cell = live ? CELL : 0xFFFFFFFFu;\n";
@@ -828,7 +833,8 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
     o << "              if (cc) cc[ci * NCELL + cell] += 1.0; }\n}\n";
     o << "#define RECORD record(st, bins, cc, ci, live);\n";
   }
-  o << "#define TICK { if (--until == 0) { until = thin; RECORD; if (++smp >= total) goto finished; } }\n";
+  // 32-bit countdowns (the launcher sends burn-in + thin >= 2^31 or more than 2^26 kept samples to the interpreter)
+  o << "#define TICK { if (--until == 0u) { until = (u32)thin; RECORD; if (++smp >= (u32)total) goto finished; } }\n";
   o << "extern \"C\" __global__ void __launch_bounds__(NT, " << min_blocks << ") gibbs_spec(const double* __restrict__ cpt, "
        "const signed char* __restrict__ ev, u64 first_chain, u64 n_chains, u32 k0, u32 k1, long long burn_in, long long thin, "
        "long long total, double* __restrict__ out, double* __restrict__ cc, unsigned char* __restrict__ state_io, "
@@ -836,13 +842,17 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
   o << "  unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem_raw);\n";
   o << "  const u32 tid = threadIdx.x;\n";
-  o << "  unsigned char* st = smem_raw + NCELL * 8u + tid;\n";
+  if (reg_bins) {
+    o << "  u32* cnt = reinterpret_cast<u32*>(smem_raw + NCELL * 8u) + tid;\n";
+    o << "  for (u32 c = 0; c < NCELL; ++c) cnt[c * NT] = 0u;\n";
+    o << "  unsigned char* st = smem_raw + NCELL * 8u + NCELL * NT * 4u + tid;\n";
+  } else {
+    o << "  unsigned char* st = smem_raw + NCELL * 8u + tid;\n";
+  }
   o << "  for (u32 c = tid; c < NCELL; c += NT) bins[c] = 0ull;\n";
   o << "  __syncthreads();\n";
   o << "  const u64 ci = (u64)blockIdx.x * NT + tid;\n";
   o << "  const bool live = ci < n_chains;  // surplus threads of the last CTA run a dummy chain (barriers need them)\n";
-  if (reg_bins)
-    for (uint32_t c = 0; c < ncell; ++c) o << "  u32 n" << c << " = 0u;\n";
   o << "  {\n";
   o << "    const u64 chain = first_chain + ci;\n";
   o << "    const u32 c0 = (u32)chain, c1 = (u32)(chain >> 32);\n";
@@ -867,7 +877,7 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   }
   o << "    }\n";
   o << "    u32 d = 0u, b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;\n";
-  o << "    long long until = burn_in + thin, smp = 0;\n";
+  o << "    u32 until = (u32)(burn_in + thin), smp = 0u;\n";
   if (n_free == 0 && !full) {
     o << "    goto finished;\n";
   }
@@ -937,7 +947,7 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   o << "  }\n";
   if (reg_bins) {
     for (uint32_t c = 0; c < ncell; ++c) {
-      o << "  { u32 v = live ? n" << c << " : 0u;\n";
+      o << "  { u32 v = live ? cnt[" << c << "u * NT] : 0u;\n";
       o << "#pragma unroll\n    for (int of = 16; of > 0; of >>= 1) v += __shfl_xor_sync(0xffffffffu, v, of);\n";
       o << "    if ((tid & 31u) == 0u && v) atomicAdd(&bins[" << c << "], (unsigned long long)v); }\n";
     }
@@ -956,7 +966,7 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
 // interpreter is bound by its ~2000-cycle dependent latency per update (4096 chains: one warp per scheduler); the
 // straight-line block cuts that by an order of magnitude.
 static std::string gen_gibbs_sample_source(const Net& net, const std::vector<char>& ev_mask, int threads, int min_blocks,
-                                           int sync_every, uint32_t* n_free_out) {
+                                           int sync_every, uint32_t* n_free_out, const GibbsTables* gt = nullptr) {
   const int n = net.n;
   std::ostringstream o;
   uint32_t n_free = 0;
@@ -967,7 +977,7 @@ static std::string gen_gibbs_sample_source(const Net& net, const std::vector<cha
   o << "extern \"C\" __global__ void __launch_bounds__(NT, " << min_blocks << ") gibbs_sample_spec(const double* __restrict__ cpt, "
        "const int* __restrict__ orders, u32 order_stride, const unsigned char* __restrict__ init, u64 first_chain, "
        "u64 n_chains, u32 k0, u32 k1, long long burn_in, long long nsamples, long long thinning, "
-       "unsigned char* __restrict__ out_states, u64 n_rows) {\n";
+       "unsigned char* __restrict__ out_states, u64 n_rows, const u32* __restrict__ tab) {\n";
   o << "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
   o << "  const u32 tid = threadIdx.x;\n";
   o << "  unsigned char* st = smem_raw + tid;\n";
@@ -983,13 +993,20 @@ static std::string gen_gibbs_sample_source(const Net& net, const std::vector<cha
   o << "    const int* ord = orders + (u64)sweep * order_stride;\n";
   o << "    for (u32 f = 0; f < NFREE; ++f) {\n";
   o << "      u32 r; NEXT_R(r);\n";
-  o << "      const double uu = ((double)r + 0.5) * (1.0 / 4294967296.0);\n";
   o << "      switch (__ldg(ord + f)) {\n";
   uint32_t rank = 0;
   for (int i = 0; i < n; ++i) {
     if (ev_mask[i]) continue;
     const int K = net.card[i];
+    if (gt && gt->tab_off[i] >= 0) {
+      o << "      case " << rank++ << ": {  // node " << i << ": card " << K << ", tabulated conditional over " << gt->members[i].size() << " blanket nodes\n";
+      emit_table_update(o, net, *gt, i, "        ");
+      o << "        st[" << i << " * NT] = (unsigned char)pick;\n";
+      o << "      } break;\n";
+      continue;
+    }
     o << "      case " << rank++ << ": {  // node " << i << ": card " << K << ", " << (net.child_ptr[i + 1] - net.child_ptr[i]) << " children\n";
+    o << "        const double uu = ((double)r + 0.5) * (1.0 / 4294967296.0);\n";
     o << "        double";
     for (int v = 0; v < K; ++v) o << (v ? ", p" : " p") << v;
     o << ";\n";
@@ -1049,15 +1066,17 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
     BN_REQUIRE(!must, BN_UNSUPPORTED, "specialised Gibbs kernel unavailable: NVRTC / driver entry points missing");
     return BN_OK;
   }
-  bool ok = net->n <= 1024 && net->cpt_off[net->n] < (int64_t)0x7fffffff && total < (int64_t)(1ll << 26);  // 32 lanes x
+  bool ok = net->n <= 1024 && net->cpt_off[net->n] < (int64_t)0x7fffffff && total < (int64_t)(1ll << 26) &&
+            burn_in + thin < (int64_t)0x7fffffff;  // 32-bit countdowns; 32 lanes x
   // total kept samples must fit the u32 warp sums
   for (int i = 0; i < net->n && ok; ++i) ok = net->card[i] <= GIBBS_SPEC_MAX_CARD;
   const DevProps& dp = dev_props(net->device);
   // small CTAs: the grid balances dynamically and 64-thread CTAs measured fastest (profiles/r1d_gibbs_spec_sweep.txt)
   int T = n_chains >= (uint64_t)dp.sm_count * 256 ? 256 : 64;  // one 256-thread CTA per SM or more: see sync_every
-  while (T > 64 && (size_t)ncell * 8 + (size_t)net->n * T + 1024 > (size_t)dp.max_smem_optin) T -= 32;
+  while (T > 64 && (size_t)ncell * 8 + (size_t)(net->n + 4 * SPEC_MAX_REG_CELLS) * T + 1024 > (size_t)dp.max_smem_optin) T -= 32;
   if (const char* e = getenv("BN_GIBBS_THREADS")) T = atoi(e);
-  const size_t smem = (size_t)ncell * 8 + (size_t)net->n * T;
+  const size_t cnt_bytes = ncell <= (uint32_t)SPEC_MAX_REG_CELLS ? (size_t)ncell * T * 4 : 0;  // per-thread record counters
+  const size_t smem = (size_t)ncell * 8 + cnt_bytes + (size_t)net->n * T;
   if (!ok || smem + 1024 > (size_t)dp.max_smem_optin) {
     BN_REQUIRE(!must, BN_UNSUPPORTED, "network not supported by the specialised Gibbs kernel (card > %d or too large)",
                GIBBS_SPEC_MAX_CARD);
@@ -1143,11 +1162,20 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
   std::string key((size_t)net->n, '0');
   for (int i = 0; i < net->n; ++i) key[i] = ev_mask[i] ? '1' : '0';
   key += "|gsample" + std::to_string(T) + "s" + std::to_string(sync_every);
+  const GibbsTables* gt = nullptr;  // tabulated conditionals, exactly as in launch_gibbs_specialized
+  {
+    const uint32_t row_limit = gibbs_table_row_limit(*net);
+    if (row_limit > 0) {
+      BN_TRY(gibbs_tables_get(net, row_limit, &gt));
+      if (gt && (gt->words == 0 || gt->has_never)) gt = nullptr;
+      if (gt) key += "|t" + std::to_string(row_limit);
+    }
+  }
   SpecKernel* k = nullptr;
   static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e9);
   int32_t rc = acquire_kernel(net, key, must, (double)n_chains * (double)(burn_in + nsamples * (thinning + 1)) * n_free, thr,
                               [&](KernelRequest* rq) {
-    std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 512 / T, sync_every, nullptr);
+    std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 512 / T, sync_every, nullptr, gt);
     rq->entry = "gibbs_sample_spec";
     rq->threads = T;
     rq->smem = smem;
@@ -1158,8 +1186,10 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
   const double* cpt = net->d_cpt.p;
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   long long bi = burn_in, ns = nsamples, th = thinning;
+  const uint32_t* tab_dev = gt ? gt->tab.p : nullptr;
   void* args[] = {(void*)&cpt, (void*)&orders_dev, (void*)&order_stride, (void*)&init_dev, (void*)&first_chain, (void*)&n_chains,
-                  (void*)&k0, (void*)&k1, (void*)&bi, (void*)&ns, (void*)&th, (void*)&out_states_dev, (void*)&n_rows};
+                  (void*)&k0, (void*)&k1, (void*)&bi, (void*)&ns, (void*)&th, (void*)&out_states_dev, (void*)&n_rows,
+                  (void*)&tab_dev};
   const unsigned grid = (unsigned)((n_chains + k->threads - 1) / k->threads);
   CUresult r = drv.LaunchKernel(k->fn, grid, 1, 1, (unsigned)k->threads, 1, 1, (unsigned)k->smem, (CUstream)tl_stream, args, nullptr);
   if (r != CUDA_SUCCESS) return cu_fail("cuLaunchKernel(gibbs_sample_spec)", r);
