@@ -886,7 +886,9 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
   // Re-convergence barrier every N nodes: the generated code (~1.2 KB per node) is larger than the instruction caches,
   // and 20% of the warp-state samples were `no_inst`; 256-thread CTAs that meet every 32 nodes fetch each code
   // window once for 8 warps (C4: 0.84 -> 0.76 ms; profiles/r1f_gibbs_sync_sweep.txt).  64-thread CTAs do not sync.
-  const int sync_every = getenv("BN_GIBBS_SYNC") ? std::max(1, atoi(getenv("BN_GIBBS_SYNC"))) : (threads >= 128 ? 32 : (1 << 30));
+  // With the trimmed blocks of round 2 any interval between 48 and a whole sweep measures the same (0.57-0.58 ms),
+  // 16 is 4% slower, none at all 12% slower.
+  const int sync_every = getenv("BN_GIBBS_SYNC") ? std::max(1, atoi(getenv("BN_GIBBS_SYNC"))) : (threads >= 128 ? 64 : (1 << 30));
   for (int i = 0; i < n; ++i) {
     if (ev_mask[i]) continue;
     const int K = net.card[i];
