@@ -45,6 +45,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 METRIC = "lw_samples_per_s"
 UNIT = "samples/s"
 NCU_LW_FILE = os.path.join(ROOT, "profiles", "r2_lw_spec_ncu.json")  # written by profiles/summarize_ncu.py --json
+PIPE_MODEL_FILE = os.path.join(ROOT, "profiles", "r2_lw_spec_pipe_model.json")  # executed opcode mix of the same capture
 
 
 # ------------------------------------------------------------------------------------------ workload
@@ -317,10 +318,27 @@ def check_gibbs_c4(bn, torch, device, quick=False):
     c2 = im2.raw_counts(bn.InferenceState(net, query, evidence))
     pc2 = im2.last_chain_counts / im2.last_chain_counts.sum(axis=1, keepdims=True)
     z2 = (c2 / c2.sum() - p_lw) / np.sqrt(np.maximum((pc2.std(axis=0, ddof=1) / np.sqrt(n_chains)) ** 2 + lw_var, 1e-300))
+    # throughput with the device full: the same case at 1 M chains (2000 node updates each)
+    big = None
+    if not quick:
+        jobb = ShardedGibbs(net, query, evidence, 1 << 20, nsamples, burn_in, thin, seed=0, device=device)
+        jobb.step()
+        torch.cuda.synchronize()
+        msb = []
+        for r in range(3):
+            jobb.seed = 50 + r
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            jobb.step()
+            e1.record()
+            torch.cuda.synchronize()
+            msb.append(e0.elapsed_time(e1))
+        big = {"chains": 1 << 20, "ms": round(float(np.median(msb)), 3),
+               "node_updates_per_s": (1 << 20) * nsamples / (float(np.median(msb)) * 1e-3)}
     bn.set_gibbs_mode("auto")
     return {"config": f"C4: GibbsSamplingNodewise({nsamples}, {burn_in}, {thin}), rand_discrete_bn(200,3,4), 20 evidence, "
                       f"{n_chains} chains, 1 GPU", "ms": round(ms, 4), "node_updates_per_s": n_chains * nsamples / (ms * 1e-3),
-            "host_call_ms_with_chain_counts": round(call_ms, 3),
+            "host_call_ms_with_chain_counts": round(call_ms, 3), "one_million_chains": big,
             "posterior": [round(float(x), 6) for x in p_hat], "lw_reference": [round(float(x), 6) for x in p_lw],
             "lw_n_eff": lw.last_stats[0] ** 2 / lw.last_stats[1],
             "between_chain_sigma": [float(x) for x in sigma], "lw_sigma": [float(x) for x in np.sqrt(lw_var)],
@@ -334,7 +352,7 @@ def check_gibbs_c4(bn, torch, device, quick=False):
             "cpu_baseline": {"value": 256 * nsamples / cpu_dt, "unit": "node-updates/s", "cores": capi.num_threads(),
                              "kind": "port", "sample": "256 chains of the same case"},
             "multi_gpu_note": "65 536 chains x 2000 sequential updates is latency-bound: sharding the chains over 8 GPUs "
-                              "(8192 each) shortens the call only from 0.76 to 0.64 ms (profiles/r1f_gibbs_c4_8gpu.json); "
+                              "(8192 each) shortened the round-1 kernel only from 0.76 to 0.64 ms (profiles/r1f_gibbs_c4_8gpu.json); "
                               "at fixed chains per GPU it scales linearly (1.6e12 updates/s at 8.4 M chains on 8 GPUs)",
             "pass": bool(same and np.abs(z2).max() < 4.0)}
 
@@ -604,6 +622,18 @@ def run_gpu(args):
                          "warp_inst_per_particle": ncu["warp_inst_per_particle"],
                          "inst_per_node_sample": ncu["warp_inst_per_particle"] * 32 / lay.n,
                          "ncu": {k: ncu[k] for k in ("issue_active_pct", "fmaheavy_pct", "alu_pct", "source", "particles") if k in ncu}})
+        if os.path.exists(PIPE_MODEL_FILE):
+            # why issue slots cannot reach 1: the pipe that binds.  Busy cycles of the fmaheavy pipe per warp iteration
+            # (IMAD.WIDE of Philox4x32-10 = 4 cycles, other IMAD = 2; counts from the committed capture) over the
+            # elapsed cycles per warp iteration of THIS run
+            pm = json.load(open(PIPE_MODEL_FILE))
+            elapsed = kern_ms * 1e-3 * sm_clock * 1e6 / (per_gpu / 32.0 / (148 * 4))
+            roofline["binding_pipe"] = {"pipe": "fmaheavy", "busy_cycles_per_warp_iteration": pm["fmaheavy_cycles_per_warp_iteration"],
+                                        "elapsed_cycles_per_warp_iteration": elapsed,
+                                        "frac": pm["fmaheavy_cycles_per_warp_iteration"] / elapsed,
+                                        "alu_frac": pm["alu_cycles_per_warp_iteration"] / elapsed,
+                                        "per_warp_iteration": pm["per_warp_iteration"],
+                                        "source": "profiles/r2_lw_spec_pipe_model.json"}
     else:
         roofline.update({"achieved": None, "peak": None, "unit": "warp-inst/s", "frac": None, "traffic": None,
                          "note": "no committed ncu instruction count for this kernel variant"})

@@ -8,3 +8,5 @@ timeout 300 python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1
 tail -2 gpurun_out/${TAG}_smoke.log
 (time timeout 900 python bench.py) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 tail -c 2500 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+# ncu launch list of the same bench command (kernel shares of the step), after the plain run exited 0
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_bench_launches.csv python bench.py --steps 2 --warmup 3 --no-configs --no-cold > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu launch list rc=$?"
