@@ -15,6 +15,8 @@
 // exactly the order contract_kernel uses, so results are bit-identical to it and to the oracle (tests use array_equal).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace bn {
 
 constexpr int SEG_MAX = 6;      // kept segments (= summed dims + 1)
@@ -163,6 +165,14 @@ int32_t sum_segmented(const double* in, const std::vector<int32_t>& card, const 
   p.pair_step = pairs ? (uint32_t)Cs[0] : 0u;
   p.in = in;
   p.out = out;
+  {  // the largest input element any thread touches must lie inside the table (a wrong plan falls back, never reads out)
+    uint64_t hi = 0;
+    for (int i = 0; i < p.nseg; ++i) hi += (uint64_t)(p.K[i] - 1u) * p.instride[i];
+    int32_t smax = 0;
+    for (uint32_t st = 0; st < p.ns; st += (pairs ? 2u : 1u)) smax = std::max(smax, p.soff[st]);  // states a load starts at
+    hi += (uint64_t)smax + (pairs ? (uint64_t)p.pair_step : 0ull) + 1ull;
+    if (hi >= n_in) return BN_OK;
+  }
   const uint32_t nl = pairs ? p.ns / 2u : p.ns;
   const int ju = (pairs ? nl < 2u : nl < 3u) ? 4 : 2;
   const unsigned grid = (unsigned)((n_units + (uint64_t)SEG_THR * ju - 1) / ((uint64_t)SEG_THR * ju));
