@@ -744,7 +744,10 @@ constexpr int GIBBS_SPEC_MAX_CARD = 8;
 // is not per-node arithmetic stays out of line or out of the loop: the Philox refill every 4th update is a call, the
 // thinned record step counts in registers (<= 16 query cells) or through one MATCH.ANY-grouped atomic per cell.
 static const char* kGibbsPrelude = R"BNSRC(
-__device__ __noinline__ uint4 refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1) {  // by value: the block stays in registers
+#ifndef REFILL_ATTR
+#define REFILL_ATTR __noinline__
+#endif
+__device__ REFILL_ATTR uint4 refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1) {  // by value: the block stays in registers
   uint4 b;
   px(c0, c1, blk, 2u, k0, k1, b.x, b.y, b.z, b.w);
   return b;
@@ -810,6 +813,15 @@ static std::string gen_gibbs_source(const Net& net, const std::vector<char>& ev_
 
   o << "// generated by libbn_cuda (specialize.cu): Gibbs " << (full ? "Full" : "Nodewise") << ", " << n << " nodes, "
     << n_free << " free, query cells " << ncell << "\n";
+  // Draw d of a chain is word d & 3 of Philox block d >> 2, and d advances by one per update: when the number of free
+  // nodes is a multiple of 4 the compiler resolves d & 3 at every node (the refill sits at every 4th node, the word is
+  // a fixed register), and the refill can be INLINED there: the round keys become uniform-register operands (20 VIADD
+  // per block gone), no call / argument moves.  Otherwise the refill site depends on the sweep and stays a call.
+  {
+    const char* e = getenv("BN_GIBBS_INLINE_REFILL");
+    const bool inline_refill = e ? atoi(e) != 0 : (n_free % 4u == 0u);
+    if (inline_refill) o << "#define REFILL_ATTR __forceinline__\n";
+  }
   o << kPrelude << kGibbsPrelude;
   o << "#define NT " << threads << "\n#define NN " << n << "u\n#define NCELL " << ncell << "u\n";
   // record step, out of line (it runs once per `thin` updates, but inline it was ~35 instructions in EVERY node's
