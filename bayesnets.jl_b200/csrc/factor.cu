@@ -925,8 +925,35 @@ int32_t bn_factor_sum(bn_factor_t h, const int32_t* sum_dims, int32_t n_sum, bn_
   BN_REQUIRE(f && out, BN_BAD_ARG, "bn_factor_sum: bad arguments");
   BN_REQUIRE(n_sum == 0 || sum_dims, BN_BAD_ARG, "bn_factor_sum: sum_dims is NULL");
   BN_CUDA_TRY(cudaSetDevice(f->device));
+  // More joint summed states than one launch takes (MAX_NS): sum in stages, the dims grouped in the factor's own order
+  // (fastest first) so that every stage stays below the limit.  The stages re-associate the additions of the
+  // reference's single pass (same terms, <= 1e-15 relative apart; sums within the limit stay bit-identical).
+  long long ns_total = 1;
+  std::vector<int32_t> ordered;  // the summed dims in the factor's dim order, with their cards
+  std::vector<int32_t> ocard;
+  for (size_t i = 0; i < f->dims.size(); ++i)
+    for (int j = 0; j < n_sum; ++j)
+      if (sum_dims[j] == f->dims[i]) { ordered.push_back(f->dims[i]); ocard.push_back(f->card[i]); ns_total *= f->card[i]; break; }
   Factor* o = nullptr;
-  BN_TRY(eliminate_impl({f}, sum_dims, n_sum, &o));
+  if (ns_total <= MAX_NS || (int)ordered.size() != n_sum) {  // (unknown / repeated dims: eliminate_impl reports them)
+    BN_TRY(eliminate_impl({f}, sum_dims, n_sum, &o));
+  } else {
+    Factor* cur = f;
+    size_t i = 0;
+    while (i < ordered.size()) {
+      long long grp = 1;
+      size_t j = i;
+      while (j < ordered.size() && grp * ocard[j] <= MAX_NS) { grp *= ocard[j]; ++j; }
+      if (j == i) j = i + 1;  // a single dim of more than MAX_NS states cannot occur (card <= 255)
+      Factor* nxt = nullptr;
+      const int32_t rc = eliminate_impl({cur}, ordered.data() + i, (int32_t)(j - i), &nxt);
+      if (cur != f) delete cur;
+      if (rc != BN_OK) return rc;
+      cur = nxt;
+      i = j;
+    }
+    o = cur;
+  }
   *out = register_factor(o);
   return BN_OK;
 }

@@ -473,6 +473,22 @@ def test_block_cache_reuse_and_trim(bn):
     assert np.array_equal(fa.sum([names[0]]).potential, na.sum(0).potential)
 
 
+def test_sum_over_more_states_than_one_launch_takes(bn):
+    """sum(phi, dims) over 4^6 = 4096 and 2^13 = 8192 joint states (one launch takes 2048): summed in stages, dims in
+    the factor's order.  Same terms as the reference's single pass, re-associated: within 1e-12 (north_star) of the
+    oracle; sums within the limit stay bit-identical (the other tests)."""
+    rng = np.random.default_rng(31)
+    for cards, sd in (([4] * 6 + [2, 3], [0, 1, 2, 3, 4, 5]), ([2] * 16, list(range(1, 14))), ([3, 5, 7, 4, 6, 8, 2], [6, 4, 2, 1, 5, 0])):
+        names = [f"big{len(cards)}_{i}" for i in range(len(cards))]
+        A = rng.random(cards)
+        got = F(bn, names, A).sum([names[i] for i in sd])
+        ref = NpFactor(list(range(len(cards))), A).sum(sd)
+        assert got.dimensions == [names[i] for i in ref.dimensions]
+        np.testing.assert_allclose(got.potential, ref.potential, rtol=RTOL, atol=0)
+    with pytest.raises(ValueError):
+        F(bn, ["u1", "u2"], rng.random((2, 2))).sum(["u1", "u1"])
+
+
 def test_push_streaming_kernel_vs_oracle(bn, monkeypatch):
     """push!(phi, dim, length) (factors_main.jl:148-158) through the duplicate kernel: even and odd table lengths (odd
     falls back to the contraction), lengths 1..5, a ragged last CTA."""
