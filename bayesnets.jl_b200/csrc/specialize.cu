@@ -1310,7 +1310,9 @@ int32_t bn_lw_spec_source(int32_t n_nodes, const int32_t* card, const int32_t* p
   uint32_t nl = 0;
   std::vector<char> ev_mask((size_t)n_nodes, 0);
   for (int i = 0; i < n_nodes; ++i) ev_mask[i] = (evidence && evidence[i] >= 0) ? 1 : 0;
-  const std::string src = gen_source(SPEC_INFER, net, prg, ev_mask, query, (uint32_t)n_query, qstride, (uint32_t)cells, prune != 0, shp, &nl);
+  // n_query == 0 dumps the table sampler (rand(bn, n) / weighted rows) instead of the inference kernel
+  const std::string src = gen_source(n_query == 0 ? SPEC_TABLE : SPEC_INFER, net, prg, ev_mask, query, (uint32_t)n_query, qstride,
+                                     (uint32_t)cells, prune != 0 && n_query != 0, shp, &nl);
   if (n_live) *n_live = (int32_t)nl;
   *out_len = (int64_t)src.size();
   if (out_src && cap > 0) {
