@@ -741,8 +741,9 @@ int32_t launch_table_specialized(Net* net, const int8_t* evidence, int32_t kind,
 constexpr int GIBBS_SPEC_MAX_CARD = 8;
 
 // The sweep is one long straight-line block (~55 instructions per node, > 100 KB for 200 nodes).  Everything that
-// is not per-node arithmetic stays out of line or out of the loop: the Philox refill every 4th update is a call, the
-// thinned record step counts in registers (<= 16 query cells) or through one MATCH.ANY-grouped atomic per cell.
+// is not per-node arithmetic stays out of line or out of the loop: the Philox refill every 4th update is a call (inlined
+// where its site is static), the thinned record step is a call that counts in per-thread shared-memory counters (<= 16
+// query cells) or through one MATCH.ANY-grouped atomic per cell.
 static const char* kGibbsPrelude = R"BNSRC(
 #ifndef REFILL_ATTR
 #define REFILL_ATTR __noinline__
