@@ -240,6 +240,45 @@ def test_specialised_lw_source_compiles_without_a_gpu(bn):
     assert ("atomicAdd(&bins[cell], w)" in big) == (ncell > 16)
 
 
+def _gibbs_source(bn, lay, evidence, query, full=False, threads=256, compile=True):
+    from bayesnets_jl_b200 import _lib
+    import ctypes as C
+    ev, q = lay.evidence_vector(evidence), lay.query_indices(query)
+    n_len, cub = C.c_int64(0), C.c_int64(0)
+    args = [C.c_int32(lay.n), _lib.ptr(lay.card, _lib.i32p), _lib.ptr(lay.par_ptr, _lib.i32p),
+            _lib.ptr(lay.par_idx, _lib.i32p), _lib.ptr(lay.cpt_off, _lib.i64p), _lib.ptr(lay.cpt, _lib.f64p),
+            _lib.ptr(ev, _lib.i8p), _lib.ptr(q, _lib.i32p), C.c_int32(q.size), C.c_int32(1 if full else 0), C.c_int32(threads)]
+    _lib.check(_lib.lib().bn_gibbs_spec_source(*args, None, C.c_int64(0), C.byref(n_len), None))
+    buf = C.create_string_buffer(n_len.value + 1)
+    _lib.check(_lib.lib().bn_gibbs_spec_source(*args, buf, C.c_int64(n_len.value + 1), C.byref(n_len),
+                                               C.byref(cub) if compile else None))
+    return buf.value.decode(), cub.value
+
+
+def test_specialised_gibbs_source_tables_and_compile_without_a_gpu(bn, monkeypatch):
+    """The Gibbs generator on the host (csrc/specialize.cu, csrc/gibbs_tables.cu layout): small-blanket nodes get the
+    integer-threshold table block, the others the fp64 block; the record step is one out-of-line function; the Philox
+    refill is inlined exactly when the number of free nodes is a multiple of 4; BN_GIBBS_TABLE_ROWS=0 removes every
+    table block; and NVRTC compiles the result for sm_100a."""
+    net = bn.rand_discrete_bn(30, 3, 4, seed=5)
+    lay = bn.flatten(net)
+    src, cub = _gibbs_source(bn, lay, {"N3": 1, "N11": 2}, ["N7"])      # 28 free nodes: a multiple of 4
+    assert cub > 0 and "gibbs_spec" in src
+    n_tab, n_fp = src.count("tabulated conditional"), src.count("own CPD")
+    assert n_tab > 0 and n_tab + n_fp == 28                             # every free node has exactly one block
+    assert "__ldg(tp)" in src or "const uint2 t = __ldg" in src or "const uint4 t = __ldg" in src
+    assert src.count("__noinline__ void record(") == 1 and "#define RECORD record(" in src
+    assert "#define REFILL_ATTR __forceinline__" in src
+    src3, _ = _gibbs_source(bn, lay, {"N3": 1, "N11": 2, "N20": 1}, ["N7"], compile=False)  # 27 free nodes
+    assert "#define REFILL_ATTR __forceinline__" not in src3
+    monkeypatch.setenv("BN_GIBBS_TABLE_ROWS", "0")
+    src0, _ = _gibbs_source(bn, lay, {"N3": 1, "N11": 2}, ["N7"], compile=False)
+    assert "tabulated conditional" not in src0 and src0.count("own CPD") == 28
+    monkeypatch.setenv("BN_GIBBS_TABLE_ROWS", "4")
+    src4, _ = _gibbs_source(bn, lay, {"N3": 1, "N11": 2}, ["N7"], compile=False)
+    assert 0 <= src4.count("tabulated conditional") <= n_tab           # a tighter limit tables fewer nodes
+
+
 def test_sample_weighted_dataframe_scan(bn):
     """src/sampling.jl:182-197: cumulative scan `while c < u && i < n`; the last row absorbs rounding."""
     import pandas as pd
