@@ -147,6 +147,9 @@ void loopy_plan_free(LoopyPlan* p);
 
 struct Comm;  // comm.cu: NCCL communicator(s) + one stream per local device
 
+struct StatsPlan;  // stats.cu: node groups, warp counts and node records of the row-lane statistics kernel
+void stats_plan_free(StatsPlan* p);
+
 // gibbs_tables.cu: Markov-blanket conditionals as integer threshold tables (nodes with small blankets)
 struct GibbsTables {
   uint32_t row_limit = 0;
@@ -168,6 +171,7 @@ struct Net {
   ~Net();
   LoopyPlan* loopy = nullptr;
   GibbsTables* gtab = nullptr;
+  StatsPlan* stats_plan[2] = {nullptr, nullptr};  // stats.cu: row-lane kernel plan without / with TMA tiles
   mutable std::atomic<int> gibbs_row_limit{-1};  // specialize.cu: blanket-table row limit, decided at first use
   std::mutex mu;  // guards spec_cache, spec_demand, loopy, gtab
   std::unordered_map<std::string, SpecKernel*> spec_cache;

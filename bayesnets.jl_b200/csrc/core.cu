@@ -183,6 +183,7 @@ Net::~Net() {
   spec_cache_clear(this);
   loopy_plan_free(loopy);
   if (gtab) gibbs_tables_free(gtab);
+  for (StatsPlan* sp : stats_plan) if (sp) stats_plan_free(sp);
   for (Net* p : peers) {
     cudaSetDevice(p->device);
     delete p;

@@ -307,7 +307,7 @@ constexpr uint32_t ROWS_TR = 256;        // rows per tile = 8 per lane
 constexpr uint32_t ROWS_REC = 12;        // words per node record
 constexpr uint32_t ROWS_FLUSH = 31;      // tiles between folds: 31 * 8 = 248 <= 255
 constexpr uint32_t ROWS_GUARD = 32;      // counter word-rows behind the last node: where masked out-of-range bins may land
-constexpr uint32_t ROWS_MAX_WARPS = 24;  // consumer warps (+ 1 producer warp): 800 threads, <= 80 registers
+constexpr uint32_t ROWS_MAX_WARPS = 28;  // consumer warps (+ 1 producer warp): 928 threads, <= 70 registers
 
 struct RowArgs {
   const uint8_t* data;
@@ -543,48 +543,30 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// Plan + launch of the row-lane kernel, one launch per group of consecutive nodes whose counters fit shared memory
-// together; returns BN_OK with *handled = false when the network does not qualify (the node-lane kernel takes over).
-static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch,
-                                      unsigned long long* out_dev, bool* handled) {
-  *handled = false;
-  const DevProps& dp = dev_props(net->device);
-  cudaStream_t s = tl_stream;
+// The plan of the row-lane kernel depends on the network structure only (and on whether tiles arrive by TMA): node
+// groups that fit shared memory, the warp count of each, the node records and the counter-row map.  Built once per
+// net, kept with a device copy of the records (read-only, so concurrent calls share it); planning per call cost
+// ~0.1 ms of host time on a 0.8 ms kernel.
+struct StatsGroup {
+  int first = 0, last = 0, W = 0;
+  uint32_t n_wrows = 0, prog_words = 0;
+  std::vector<uint32_t> words;   // [prog | row_out]
+  DevBuf<uint32_t> dev;
+};
+struct StatsPlan {
+  bool ok = false, fatal = false;
+  std::vector<StatsGroup> groups;
+};
+void stats_plan_free(StatsPlan* p) { delete p; }
+
+static void build_stats_plan(Net* net, bool more, size_t budget, size_t tiles_b, StatsPlan* plan) {
   const int n = net->n;
-  const size_t budget = (size_t)dp.max_smem_optin - 1024;
-  if (net->cpt_off[n] >= (int64_t)(1u << 30) || n > 4096) return BN_OK;
-  for (int i = 0; i < n; ++i)
-    if (net->cpt_off[i + 1] - net->cpt_off[i] > 256) return BN_OK;  // a bin index must fit one byte
-  if (getenv("BN_STATS_NODELANES")) return BN_OK;
-  bool more = false;
-  for (int i = 0; i < n; ++i) more = more || (net->par_ptr[i + 1] - net->par_ptr[i] > 3);
-  // TMA needs a 16-byte aligned table and pitch, and 32-bit coordinates
-  const bool tma = pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(data_dev) % 16) == 0 && n_rows < (1ull << 32) &&
-                   pitch < (1ull << 40) && encode_tiled() != nullptr && !getenv("BN_STATS_NO_TMA");
-  const uint32_t n_boxes = (uint32_t)((n + 255) / 256), box_nodes = (uint32_t)((n + n_boxes - 1) / n_boxes);
-  const size_t tile_b = (size_t)(tma ? box_nodes * n_boxes : (uint32_t)n) * ROWS_TR;
-  const size_t tiles_b = tile_b * (tma ? 2 : 1);
   auto wrows_of = [&](int i) { return (uint32_t)((net->cpt_off[i + 1] - net->cpt_off[i] + 3) / 4); };
   auto rec_words_of = [&](int i) {
     const uint32_t np = (uint32_t)(net->par_ptr[i + 1] - net->par_ptr[i]);
     const uint32_t w = ROWS_REC + (np > 3 ? 2 * (np - 3) : 0);
     return more ? ((w + 3u) & ~3u) : ROWS_REC;
   };
-  const uint64_t n_tiles = (n_rows + ROWS_TR - 1) / ROWS_TR;
-  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)dp.sm_count);
-  BN_REQUIRE(n_rows / (uint64_t)grid < (1ull << 31), BN_UNSUPPORTED, "too many rows per CTA for the 32-bit CTA totals");
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
-  if (tma) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)n_rows, (cuuint64_t)n};
-    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
-    const cuuint32_t box[2] = {ROWS_TR, box_nodes};
-    const cuuint32_t estride[2] = {1, 1};
-    const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(data_dev), gdim, gstride, box,
-                                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    BN_REQUIRE(r == CUDA_SUCCESS, BN_CUDA_ERR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  }
   int first = 0;
   while (first < n) {
     size_t used = tiles_b + (ROWS_MAX_WARPS * 3 + 4) * 4 + 512 + ROWS_GUARD * 128 + 2 * ROWS_REC * 4;
@@ -597,17 +579,19 @@ static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_
       wrows += wrows_of(last);
       ++last;
     }
-    if (last == first) return first == 0 ? BN_OK : BN_UNSUPPORTED;  // a single node does not fit beside the tiles
-    // deal the group's nodes to warps, longest processing time first.  Warps cost issue slots per tile whether or not
-    // they are busy, and every warp waits for the slowest one sooner or later: pick the warp count that minimises
-    // (warps x longest warp), preferring enough warps to hide the counter read-modify-write latency.
+    if (last == first) { plan->ok = false; plan->fatal = first != 0; return; }  // a single node does not fit beside the tiles
+    // deal the group's nodes to warps, longest processing time first, and pick the warp count by a cost model fitted to
+    // measurements on the C2 net (2^24 rows; W = 12 / 16 / 17 / 20 / 24 / 25 / 26 / 28 consumer warps: 0.905 / 0.877 /
+    // 0.837 / 0.866 / 0.840 / 0.783 / 0.790 / 0.810 ms): time ~ longest warp + (work of all warps, dummy partners of odd
+    // nodes and per-tile overheads included) / 12.  The longest warp dominates (every warp waits for it at the ring),
+    // so counts that deal the nodes out evenly in PAIRS win: 100 nodes -> 25 warps of two pairs each.
     const int m = last - first;
     std::vector<int> order(m);
     for (int j = 0; j < m; ++j) order[j] = first + j;
     auto cost = [&](int i) { return 34 + 4 * std::min(3, net->par_ptr[i + 1] - net->par_ptr[i] > 1 ? 3 : 1); };
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost(x) > cost(y); });
-    static const int warps_env = getenv("BN_STATS_WARPS") ? atoi(getenv("BN_STATS_WARPS")) : 0;
-    auto deal = [&](int W, std::vector<std::vector<int>>* out) {  // -> longest warp (nodes are walked in pairs)
+    const int warps_env = getenv("BN_STATS_WARPS") ? atoi(getenv("BN_STATS_WARPS")) : 0;
+    auto deal = [&](int W, std::vector<std::vector<int>>* out) {  // -> modelled time (nodes are walked in pairs)
       std::vector<int> load(W, 0);
       std::vector<std::vector<int>> mine(W);
       for (int i : order) {
@@ -615,24 +599,25 @@ static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_
         load[w] += cost(i);
         mine[w].push_back(i);
       }
-      int longest = 0;
+      int longest = 0, total = 0;
       for (int w = 0; w < W; ++w) {
         int l = 40;  // per-tile overhead of a warp
         for (size_t j = 0; j < mine[w].size(); j += 2) l += 2 * cost(mine[w][j]);  // an odd node drags a dummy partner
         longest = std::max(longest, l);
+        total += l;
       }
       if (out) out->swap(mine);
-      return longest;
+      return (double)longest + (double)total / 12.0;
     };
     int best_w = 1;
     double best_t = 1e300;
     for (int W = std::min<int>(ROWS_MAX_WARPS, m); W >= 1; --W) {
       if (warps_env && W != std::min(warps_env, std::min<int>(ROWS_MAX_WARPS, m))) continue;
-      double tm = (double)W * deal(W, nullptr);
-      if (W < 16) tm *= 16.0 / W;  // too few warps leave the schedulers idle
+      const double tm = deal(W, nullptr);
       if (tm < best_t) { best_t = tm; best_w = W; }
     }
     const int W = best_w;
+    if (getenv("BN_STATS_DEBUG")) fprintf(stderr, "[bn stats] nodes %d..%d: %d consumer warps (model %.1f)\n", first, last - 1, W, best_t);
     std::vector<std::vector<int>> mine;
     deal(W, &mine);
     uint32_t total_rows = 0;
@@ -682,34 +667,93 @@ static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_
       prog[3 * w + 2] = row_begin | ((row - row_begin) << 16);
     }
     while (prog.size() % 4) prog.push_back(0);
+    plan->groups.emplace_back();
+    StatsGroup& g = plan->groups.back();
+    g.first = first; g.last = last; g.W = W; g.n_wrows = row;
+    g.prog_words = (uint32_t)prog.size();
+    g.words = prog;
+    g.words.insert(g.words.end(), row_out.begin(), row_out.end());
+    first = last;
+  }
+  plan->ok = true;
+}
+
+// Plan + launch of the row-lane kernel, one launch per group of consecutive nodes whose counters fit shared memory
+// together; returns BN_OK with *handled = false when the network does not qualify (the node-lane kernel takes over).
+static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_t n_rows, uint64_t pitch,
+                                      unsigned long long* out_dev, bool* handled) {
+  *handled = false;
+  const DevProps& dp = dev_props(net->device);
+  cudaStream_t s = tl_stream;
+  const int n = net->n;
+  const size_t budget = (size_t)dp.max_smem_optin - 1024;
+  if (net->cpt_off[n] >= (int64_t)(1u << 30) || n > 4096) return BN_OK;
+  for (int i = 0; i < n; ++i)
+    if (net->cpt_off[i + 1] - net->cpt_off[i] > 256) return BN_OK;  // a bin index must fit one byte
+  if (getenv("BN_STATS_NODELANES")) return BN_OK;
+  bool more = false;
+  for (int i = 0; i < n; ++i) more = more || (net->par_ptr[i + 1] - net->par_ptr[i] > 3);
+  // TMA needs a 16-byte aligned table and pitch, and 32-bit coordinates
+  const bool tma = pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(data_dev) % 16) == 0 && n_rows < (1ull << 32) &&
+                   pitch < (1ull << 40) && encode_tiled() != nullptr && !getenv("BN_STATS_NO_TMA");
+  const uint32_t n_boxes = (uint32_t)((n + 255) / 256), box_nodes = (uint32_t)((n + n_boxes - 1) / n_boxes);
+  const size_t tile_b = (size_t)(tma ? box_nodes * n_boxes : (uint32_t)n) * ROWS_TR;
+  const size_t tiles_b = tile_b * (tma ? 2 : 1);
+  const uint64_t n_tiles = (n_rows + ROWS_TR - 1) / ROWS_TR;
+  const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)dp.sm_count);
+  BN_REQUIRE(n_rows / (uint64_t)grid < (1ull << 31), BN_UNSUPPORTED, "too many rows per CTA for the 32-bit CTA totals");
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (tma) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_rows, (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {ROWS_TR, box_nodes};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(data_dev), gdim, gstride, box,
+                                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BN_REQUIRE(r == CUDA_SUCCESS, BN_CUDA_ERR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+  StatsPlan* plan = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(net->mu);
+    StatsPlan*& slot = net->stats_plan[tma ? 1 : 0];
+    if (!slot || getenv("BN_STATS_WARPS")) {  // (the sweep knob rebuilds the plan every call)
+      if (slot) stats_plan_free(slot);
+      slot = new StatsPlan();
+      build_stats_plan(net, more, budget, tiles_b, slot);
+      for (StatsGroup& g : slot->groups) {
+        BN_CUDA_TRY(g.dev.upload(g.words.data(), g.words.size(), s));
+        BN_CUDA_TRY(cudaStreamSynchronize(s));  // the host vector is pageable; once per net
+      }
+    }
+    plan = slot;
+  }
+  if (!plan->ok) return plan->fatal ? BN_UNSUPPORTED : BN_OK;
+  for (StatsGroup& g : plan->groups) {
     RowArgs a{};
     a.data = data_dev;
     a.n_rows = n_rows;
     a.pitch = pitch;
-    a.prog_words = (uint32_t)prog.size();
+    a.prog_words = g.prog_words;
     a.n_nodes = (uint32_t)n;
-    a.n_warps = (uint32_t)W;
-    a.n_wrows = row;
+    a.n_warps = (uint32_t)g.W;
+    a.n_wrows = g.n_wrows;
     a.box_nodes = box_nodes;
     a.n_boxes = n_boxes;
     a.out = out_dev;
-    TmpBuf<uint32_t> stage;  // per call, freed in stream order after the kernel
-    BN_CUDA_TRY(stage.alloc(prog.size() + row_out.size()));
-    BN_CUDA_TRY(cudaMemcpyAsync(stage.p, prog.data(), prog.size() * 4, cudaMemcpyHostToDevice, s));
-    BN_CUDA_TRY(cudaMemcpyAsync(stage.p + prog.size(), row_out.data(), row_out.size() * 4, cudaMemcpyHostToDevice, s));
-    a.prog = stage.p;
-    a.row_out = stage.p + prog.size();
-    const size_t smem = (((size_t)a.prog_words + 31) & ~(size_t)31) * 4 + ((size_t)row + ROWS_GUARD) * 128 +
-                        (((size_t)row * 4 + 31) & ~(size_t)31) * 4 + tiles_b;
+    a.prog = g.dev.p;
+    a.row_out = g.dev.p + g.prog_words;
+    const size_t smem = (((size_t)a.prog_words + 31) & ~(size_t)31) * 4 + ((size_t)g.n_wrows + ROWS_GUARD) * 128 +
+                        (((size_t)g.n_wrows * 4 + 31) & ~(size_t)31) * 4 + tiles_b;
     void (*kern)(const RowArgs, const CUtensorMap) =
         tma ? (more ? statistics_rows_kernel<true, true> : statistics_rows_kernel<false, true>)
             : (more ? statistics_rows_kernel<true, false> : statistics_rows_kernel<false, false>);
     BN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin - 1024));
     BN_REQUIRE(smem <= budget, BN_CUDA_ERR, "statistics plan exceeds shared memory (%zu bytes)", smem);
-    kern<<<grid, (W + (tma ? 1 : 0)) * 32, smem, s>>>(a, tmap);
+    kern<<<grid, (g.W + (tma ? 1 : 0)) * 32, smem, s>>>(a, tmap);
     count_launch();
     BN_CUDA_TRY(cudaGetLastError());
-    first = last;
   }
   *handled = true;
   return BN_OK;
