@@ -35,5 +35,15 @@ if __name__ == "__main__":
             ms.append(e0.elapsed_time(e1))
         return float(np.median(ms))
     pair, samp, cnt = timed(job.step), timed(job.sample), timed(job.launch)
+    import time
+
+    def host(fn, reps=20):
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+            torch.cuda.synchronize()
+        return float(np.median(ts)) * 1e3
+    print(json.dumps({"host_ms_sample_call": round(host(job.sample), 4), "host_ms_count_call": round(host(job.launch), 4)}))
     print(json.dumps({"rows": n, "pair_ms": round(pair, 4), "pair_rows_per_s": n / (pair * 1e-3), "sample_ms": round(samp, 4),
                       "sample_rows_per_s": n / (samp * 1e-3), "count_ms": round(cnt, 4), "count_rows_per_s": n / (cnt * 1e-3)}))
