@@ -163,6 +163,7 @@ struct GibbsTables {
 void gibbs_tables_free(GibbsTables* t);
 void gibbs_tables_layout(const Net& net, uint32_t row_limit, GibbsTables* g);
 int32_t gibbs_tables_get(Net* net, uint32_t row_limit, const GibbsTables** out);
+uint32_t gibbs_table_row_limit(const Net& net);  // specialize.cu: rows a blanket may have to be tabulated (0 = no tables)
 
 // Threading contract (include/bn_cuda.h): any number of host threads / streams may use one net concurrently.  Per-call
 // staging (programs, tables, evidence bytes, results) is allocated from the stream-ordered pool per call, never shared;

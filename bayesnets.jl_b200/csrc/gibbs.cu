@@ -22,7 +22,10 @@ struct GibbsProgram {
   uint32_t n_free = 0;
 };
 
-static int32_t compile_gibbs(const Net& net, const int8_t* evidence, uint32_t T, GibbsProgram* out) {
+// gt != nullptr: nodes with a tabulated conditional (gibbs_tables.cu) get a TABLE update record instead:
+//   [node | 0x80000000, table offset (words), K | nmem << 16, (member * T, stride * row words) x nmem]
+static int32_t compile_gibbs(const Net& net, const int8_t* evidence, uint32_t T, GibbsProgram* out,
+                             const GibbsTables* gt = nullptr) {
   const int n = net.n;
   BN_REQUIRE(net.cpt_off[n] < (int64_t)0x7fffffff, BN_UNSUPPORTED, "CPT too large for the Gibbs kernel");
   std::vector<uint32_t>& w = out->words;
@@ -46,6 +49,18 @@ static int32_t compile_gibbs(const Net& net, const int8_t* evidence, uint32_t T,
       continue;
     }
     out->upd_off.push_back((uint32_t)w.size());
+    if (gt && gt->tab_off[i] >= 0) {
+      const int K = net.card[i];
+      const uint32_t W = K <= 2 ? 1u : (K == 3 ? 2u : (K == 4 ? 4u : 8u));
+      w.push_back((uint32_t)i | 0x80000000u);
+      w.push_back((uint32_t)gt->tab_off[i]);
+      w.push_back((uint32_t)K | ((uint32_t)gt->members[i].size() << 16));
+      for (size_t m = 0; m < gt->members[i].size(); ++m) {
+        w.push_back((uint32_t)gt->members[i][m] * T);
+        w.push_back(gt->strides[i][m] * W);
+      }
+      continue;
+    }
     w.push_back((uint32_t)i);
     w.push_back(rec[i]);
     w.push_back((uint32_t)(net.child_ptr[i + 1] - net.child_ptr[i]));
@@ -70,6 +85,7 @@ struct GibbsArgs {
   const uint32_t* prog;     // program words
   const uint32_t* upd_off;  // [n_free]
   const double* cpt;
+  const uint32_t* tab;      // gibbs_tables.cu thresholds (nullptr: no table records in the program)
   const int8_t* evidence;   // [n_nodes]
   const int32_t* card;      // [n_nodes]
   uint32_t n_nodes, n_free;
@@ -141,7 +157,18 @@ __device__ __forceinline__ void mb_chunk(const GibbsArgs& a, const uint32_t* __r
 // x_n ~ P(x_n | mb(x_n)): eval_mb_cpd + sample(Weights) (src/Inference/gibbs.jl:110-112)
 __device__ __forceinline__ void gibbs_update(const GibbsArgs& a, uint32_t upd, uint8_t* st, uint32_t T, uint32_t r) {
   const uint32_t* u = a.prog + upd;
-  const uint32_t node = __ldg(u + 0);
+  const uint32_t w0 = __ldg(u + 0);
+  if (w0 & 0x80000000u) {  // tabulated conditional: pick = #{v : r >= R_v}, the same decision as the scan below
+    const uint32_t info = __ldg(u + 2), K = info & 0xffffu, nmem = info >> 16;
+    uint32_t off = __ldg(u + 1);
+    for (uint32_t m = 0; m < nmem; ++m) off += __ldg(u + 4 + 2 * m) * (uint32_t)st[__ldg(u + 3 + 2 * m)];
+    const uint32_t* tp = a.tab + off;
+    uint32_t pick = 0;
+    for (uint32_t v = 0; v + 1 < K; ++v) pick += (uint32_t)(r >= __ldg(tp + v));
+    st[(w0 & 0x7fffffffu) * T] = (uint8_t)pick;
+    return;
+  }
+  const uint32_t node = w0;
   const uint32_t K = __ldg(a.prog + __ldg(u + 1));
   const double uu = ((double)r + 0.5) * (1.0 / 4294967296.0);
   double p[8];
@@ -212,14 +239,16 @@ __global__ void __launch_bounds__(256) gibbs_infer_kernel(const GibbsArgs a) {
       init_uniform(a, chain, st, T);
     ChainRng rng;
     rng.init(chain, STREAM_GIBBS_UPDATE, a.seed_lo, a.seed_hi);
-    int64_t num_iters = 0, num_smpls = 0;
+    // a sample is kept at iterations burn_in + k * thin, k >= 1 (src/Inference/gibbs.jl:118-121): a countdown instead
+    // of a 64-bit modulo per update
+    int64_t until = a.burn_in + a.thin, num_smpls = 0;
     bool finished = (a.n_free == 0 && !a.full);
     while (!finished) {
       for (uint32_t f = 0; f < a.n_free; ++f) {
         gibbs_update(a, __ldg(a.upd_off + f), st, T, rng.next());
         if (!a.full) {
-          ++num_iters;  // one node update = one iteration (src/Inference/gibbs.jl:120)
-          if (num_iters > a.burn_in && ((num_iters - a.burn_in) % a.thin) == 0) {
+          if (--until == 0) {  // one node update = one iteration (src/Inference/gibbs.jl:120)
+            until = a.thin;
             uint32_t cell = 0;
             for (uint32_t j = 0; j < a.n_query; ++j) cell += a.query[2 * j + 1] * (uint32_t)st[a.query[2 * j]];
             atomicAdd(&bins[cell], 1ull);
@@ -230,8 +259,8 @@ __global__ void __launch_bounds__(256) gibbs_infer_kernel(const GibbsArgs a) {
         }
       }
       if (a.full) {
-        ++num_iters;  // one sweep = one iteration (:214)
-        if (num_iters > a.burn_in && ((num_iters - a.burn_in) % a.thin) == 0) {
+        if (--until == 0) {  // one sweep = one iteration (:214)
+          until = a.thin;
           uint32_t cell = 0;
           for (uint32_t j = 0; j < a.n_query; ++j) cell += a.query[2 * j + 1] * (uint32_t)st[a.query[2 * j]];
           atomicAdd(&bins[cell], 1ull);
@@ -321,8 +350,16 @@ struct GibbsDevice {
 
 static int32_t stage_gibbs(Net* net, const int8_t* evidence, uint32_t T, const int32_t* query, int32_t n_query,
                            const std::vector<int64_t>& qstride, GibbsDevice* dev, GibbsArgs* a) {
+  // tabulated conditionals for small-blanket nodes, shared with the specialised kernels (built once per net)
+  const GibbsTables* gt = nullptr;
+  const uint32_t row_limit = gibbs_table_row_limit(*net);
+  if (row_limit > 0) {
+    BN_TRY(gibbs_tables_get(net, row_limit, &gt));
+    if (gt && (gt->words == 0 || gt->has_never)) gt = nullptr;
+  }
   GibbsProgram gp;
-  BN_TRY(compile_gibbs(*net, evidence, T, &gp));
+  BN_TRY(compile_gibbs(*net, evidence, T, &gp, gt));
+  a->tab = gt ? gt->tab.p : nullptr;
   cudaStream_t s = tl_stream;
   BN_CUDA_TRY(dev->prog.upload(gp.words.data(), gp.words.size(), s));
   BN_CUDA_TRY(dev->upd_off.upload(gp.upd_off.data(), gp.upd_off.size(), s));

@@ -761,7 +761,7 @@ __device__ REFILL_ATTR uint4 refill(u32 c0, u32 c1, u32 blk, u32 k0, u32 k1) {  
 // after two CTAs' state columns, ~124 KB): measured on the C4 net (CPT 64 KB), 256 rows (61 KB of tables) is 8% faster
 // than no tables, 1024 rows (126 KB) 7% slower.  So: the largest power of two whose tables + CPTs stay within 128 KB.
 // BN_GIBBS_TABLE_ROWS overrides (0 = no tables).
-static uint32_t gibbs_table_row_limit(const Net& net) {
+uint32_t gibbs_table_row_limit(const Net& net) {
   if (const char* e = getenv("BN_GIBBS_TABLE_ROWS")) return (uint32_t)atoi(e);
   if (net.gibbs_row_limit >= 0) return (uint32_t)net.gibbs_row_limit;  // decided once per net (structure only)
   const uint64_t budget = 128u << 10, cpt_bytes = (uint64_t)net.cpt_off[net.n] * 8;
