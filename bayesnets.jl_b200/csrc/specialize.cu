@@ -1114,7 +1114,7 @@ int32_t launch_gibbs_specialized(Net* net, const int8_t* evidence, const int32_t
     }
   }
   SpecKernel* k = nullptr;
-  static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e9);
+  static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e8);
   BN_TRY(acquire_kernel(net, key, must, (double)n_chains * (double)(burn_in + total * thin) * (full ? net->n : 1), thr,
                         [&](KernelRequest* rq) {
     uint32_t n_free = 0;
@@ -1187,7 +1187,7 @@ int32_t launch_gibbs_sample_specialized(Net* net, const int8_t* evidence, const 
     }
   }
   SpecKernel* k = nullptr;
-  static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e9);
+  static const double thr = auto_threshold("BN_GIBBS_AUTO_THRESHOLD", 2e8);
   int32_t rc = acquire_kernel(net, key, must, (double)n_chains * (double)(burn_in + nsamples * (thinning + 1)) * n_free, thr,
                               [&](KernelRequest* rq) {
     std::string src = gen_gibbs_sample_source(*net, ev_mask, T, 512 / T, sync_every, nullptr, gt);

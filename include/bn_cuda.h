@@ -159,7 +159,7 @@ int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* que
  * mode : 0 = auto: the network-specialised kernel is used as soon as its cubin is at hand -- in the process, or in the
  *            on-disk cache a previous process left; otherwise the generic interpreter kernel serves the call and, once
  *            the cumulative work requested for the same (structure, evidence mask, query) reaches 5e7 particles/rows
- *            (2e9 node updates for Gibbs), NVRTC compiles the kernel on a BACKGROUND host thread (~10 ms per node);
+ *            (2e8 node updates for Gibbs), NVRTC compiles the kernel on a BACKGROUND host thread (~10 ms per node);
  *            later calls switch over when it is ready.  No call ever waits for a compile;
  *        1 = generic interpreter only, 2 = specialised required (compiled on first use, blocking; error if unavailable).
  * prune: != 0 lets the specialised kernel skip "barren" nodes (not an ancestor of a query or evidence node);
