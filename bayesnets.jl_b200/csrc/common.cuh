@@ -124,7 +124,9 @@ struct PoolBuf {
     n = count;
     s = tl_stream;
     bytes = (count ? count : 1) * sizeof(T);
-    return pool_alloc((void**)&p, bytes, s, &device);
+    const cudaError_t e = pool_alloc((void**)&p, bytes, s, &device);
+    if (e != cudaSuccess) { p = nullptr; n = 0; }  // nothing to release later
+    return e;
   }
   cudaError_t upload(const T* host, size_t count, cudaStream_t st) {
     cudaError_t e = alloc(count);

@@ -122,10 +122,13 @@ int32_t gibbs_tables_get(Net* net, uint32_t row_limit, const GibbsTables** out) 
   std::lock_guard<std::mutex> lk(net->mu);
   if (net->gtab && net->gtab->row_limit == row_limit) { *out = net->gtab; return BN_OK; }
   if (net->gtab) { gibbs_tables_free(net->gtab); net->gtab = nullptr; }
-  auto* g = new GibbsTables();
+  struct Holder {  // the net gets the tables only when they are complete: an error below leaves it without any
+    GibbsTables* g = new GibbsTables();
+    ~Holder() { if (g) gibbs_tables_free(g); }
+  } hold;
+  GibbsTables* g = hold.g;
   gibbs_tables_layout(*net, row_limit, g);
-  net->gtab = g;
-  if (g->words == 0) { *out = g; return BN_OK; }
+  if (g->words == 0) { net->gtab = g; hold.g = nullptr; *out = g; return BN_OK; }
   BN_REQUIRE(g->words < (1ull << 31), BN_UNSUPPORTED, "Gibbs conditional tables too large (%llu words)", (unsigned long long)g->words);
   // programs
   const int n = net->n;
@@ -182,6 +185,8 @@ int32_t gibbs_tables_get(Net* net, uint32_t row_limit, const GibbsTables** out) 
   BN_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost, s));
   BN_CUDA_TRY(cudaStreamSynchronize(s));
   g->has_never = flag != 0;
+  net->gtab = g;
+  hold.g = nullptr;
   *out = g;
   return BN_OK;
 }

@@ -719,13 +719,18 @@ static int32_t statistics_launch_rows(Net* net, const uint8_t* data_dev, uint64_
     std::lock_guard<std::mutex> lk(net->mu);
     StatsPlan*& slot = net->stats_plan[tma ? 1 : 0];
     if (!slot || getenv("BN_STATS_WARPS")) {  // (the sweep knob rebuilds the plan every call)
-      if (slot) stats_plan_free(slot);
-      slot = new StatsPlan();
-      build_stats_plan(net, more, budget, tiles_b, slot);
-      for (StatsGroup& g : slot->groups) {
+      if (slot) { stats_plan_free(slot); slot = nullptr; }
+      struct Holder {  // the net gets the plan only when its device copies exist
+        StatsPlan* p = new StatsPlan();
+        ~Holder() { if (p) stats_plan_free(p); }
+      } hold;
+      build_stats_plan(net, more, budget, tiles_b, hold.p);
+      for (StatsGroup& g : hold.p->groups) {
         BN_CUDA_TRY(g.dev.upload(g.words.data(), g.words.size(), s));
         BN_CUDA_TRY(cudaStreamSynchronize(s));  // the host vector is pageable; once per net
       }
+      slot = hold.p;
+      hold.p = nullptr;
     }
     plan = slot;
   }
