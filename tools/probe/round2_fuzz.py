@@ -6,7 +6,9 @@
   gibbs: chains of the NVRTC Gibbs kernel with tabulated conditionals (random row limits) vs without tables
          (BN_GIBBS_TABLE_ROWS=0) on random nets: counts and final states identical.
 
-    python tools/probe/round2_fuzz.py [--sums 2000] [--nets 40]
+  stats: statistics of a device table through the row-lane kernel vs the node-lane kernel (BN_STATS_NODELANES).
+
+    python tools/probe/round2_fuzz.py [--sums 2000] [--nets 40] [--tables 60]
 """
 import argparse
 import json
@@ -76,10 +78,54 @@ def fuzz_gibbs(bn, n_nets, rng):
     return bad
 
 
+def fuzz_stats(bn, n_cases, rng):
+    """statistics of a sampled device table: row-lane kernel vs node-lane kernel (BN_STATS_NODELANES), random nets of
+    1..160 nodes (every warp count the plan can choose, odd node counts, ragged last tiles, pitch > rows)."""
+    import ctypes as C
+    from bayesnets_jl_b200 import _lib
+    from bayesnets_jl_b200.device_layout import DeviceNet
+    from bayesnets_jl_b200.learning import statistics_device
+    bad = []
+    L = _lib.lib()
+    for case in range(n_cases):
+        n_nodes = int(rng.integers(2, 161))
+        net = bn.rand_discrete_bn(n_nodes, int(rng.integers(1, min(4, n_nodes))), int(rng.integers(2, 6)), seed=int(rng.integers(0, 1 << 30)))
+        lay = bn.flatten(net)
+        dn = DeviceNet(lay, 0)
+        n_rows = int(rng.choice([1, 31, 255, 256, 257, 1000, 4096, 70001, 262144]))
+        pitch = n_rows if rng.random() < 0.5 else (n_rows + 15) // 16 * 16 + 16 * int(rng.integers(0, 3))
+        tab = _lib.DeviceBuffer(lay.n * pitch, 0, zero=True)
+        ev = np.full(lay.n, -1, np.int8)
+        if pitch == n_rows:
+            _lib.check(L.bn_sample_dev(_lib.h64(dn.handle), _lib.ptr(ev, _lib.i8p), C.c_int32(0), C.c_int32(1), C.c_uint64(0),
+                                       C.c_uint64(n_rows), C.c_uint64(case), C.c_void_p(tab.ptr), None, None))
+        else:  # padded pitch: upload a host table
+            host = np.zeros((lay.n, pitch), np.uint8)
+            for i in range(lay.n):
+                host[i, :n_rows] = rng.integers(0, lay.card[i], n_rows)
+            tab.upload(host)
+        res = []
+        for nl in (None, "1"):
+            if nl:
+                os.environ["BN_STATS_NODELANES"] = nl
+            else:
+                os.environ.pop("BN_STATS_NODELANES", None)
+            _, c = statistics_device(dn, tab.ptr, n_rows, pitch)
+            res.append(c)
+        os.environ.pop("BN_STATS_NODELANES", None)
+        ok = np.array_equal(res[0], res[1]) and int(res[0][lay.cpt_off[0]:lay.cpt_off[1]].sum()) == n_rows
+        if not ok:
+            bad.append({"case": case, "n_nodes": n_nodes, "rows": n_rows, "pitch": pitch})
+        tab.close()
+        dn.close()
+    return bad
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--sums", type=int, default=2000)
     ap.add_argument("--nets", type=int, default=40)
+    ap.add_argument("--tables", type=int, default=60)
     a = ap.parse_args()
     import bayesnets_jl_b200 as bn
     rng = np.random.default_rng(20261020)
@@ -87,7 +133,11 @@ if __name__ == "__main__":
     bad_s = fuzz_sums(bn, a.sums, rng)
     t1 = time.time()
     bad_g = fuzz_gibbs(bn, a.nets, rng)
+    t2 = time.time()
+    bad_t = fuzz_stats(bn, a.tables, rng)
+    print(json.dumps({"stats_tables": a.tables, "stats_mismatches": bad_t[:5], "n_stats_mismatches": len(bad_t),
+                      "stats_seconds": round(time.time() - t2, 1)}))
     print(json.dumps({"sum_and_push_cases": a.sums, "sum_mismatches": bad_s[:5], "n_sum_mismatches": len(bad_s),
                       "gibbs_nets": a.nets, "gibbs_mismatches": bad_g[:5], "n_gibbs_mismatches": len(bad_g),
                       "seconds": [round(t1 - t0, 1), round(time.time() - t1, 1)]}))
-    sys.exit(1 if (bad_s or bad_g) else 0)
+    sys.exit(1 if (bad_s or bad_g or bad_t) else 0)
