@@ -49,3 +49,13 @@ if __name__ == "__main__":
         fn()
         h, tot = loop(fn)
         print(f"{name:40s} host {h:6.2f} us/op   incl. drain {tot:6.2f} us/op")
+    # short bursts (the launch queue never fills, so this is the host's own cost per op)
+    for name, fn in [("sum + free, bursts of 200", f_sum), ("product + free, bursts of 200", f_prod)]:
+        ts = []
+        for _ in range(30):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                fn()
+            ts.append((time.perf_counter() - t0) / 200 * 1e6)
+        print(f"{name:40s} host {np.median(ts):6.2f} us/op")
