@@ -167,7 +167,10 @@ int32_t bn_lw_infer_dev(bn_net_t net, const int8_t* evidence, const int32_t* que
 int32_t bn_set_lw_mode(int32_t mode, int32_t prune);
 /* Same selection for bn_gibbs_infer and bn_gibbs_sample: 0 = auto, 1 = generic interpreter kernel, 2 = specialised
  * (bn_gibbs_infer: required; bn_gibbs_sample: used whenever the network qualifies -- <= 8 states per node -- else the
- * interpreter serves the call).  Chains, counts and tables are identical either way. */
+ * interpreter serves the call).  Chains, counts and tables are identical either way.
+ * Both kinds of kernel draw the nodes with small Markov blankets from integer threshold tables built once per net
+ * (csrc/gibbs_tables.cu): the same decision as the fp64 cumulative scan for every 32-bit draw, so nothing observable
+ * changes; BN_GIBBS_TABLE_ROWS=0 turns the tables off. */
 int32_t bn_set_gibbs_mode(int32_t mode);
 /* Number of NVRTC compiles since load (kernels are cached process-wide by generated source). */
 uint64_t bn_lw_spec_compile_count(void);
